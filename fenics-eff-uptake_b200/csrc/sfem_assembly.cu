@@ -1,0 +1,392 @@
+// Element / facet kernels, gather-style CSR assembly and Dirichlet application.
+//
+// Layout: per-cell geometry is SoA (geo[k][cell], k = x0,y0,x1,y1,x2,y2) so a warp reads six
+// contiguous spans; element matrices are written AoS ([cell][i][j], row-major) so the gather
+// kernel -- one thread per CSR slot, contributions in fixed (family, cell) order, no atomics --
+// finds the 6 entries of a matrix row of one cell inside one 48-byte span.
+//
+// Element conventions: reference triangle (0,0),(1,0),(0,1), barycentrics
+// l0=1-x-y, l1=x, l2=y; P2 dofs 0..2 at vertices (l_i(2l_i-1)), 3..5 on the edges opposite
+// vertex 0,1,2 (4 l1 l2, 4 l0 l2, 4 l0 l1); affine cells with |det J| (cells are stored with
+// ascending vertex ids so orientation may be negative).
+#include "sfem_common.cuh"
+#include "sfem_internal.h"
+
+namespace sfem {
+
+namespace {
+
+struct TriGeom {
+  double gx[3], gy[3];   // physical gradients of the barycentrics
+  double adet;           // |det J| = 2 * area
+};
+
+__device__ __forceinline__ TriGeom load_geom(const double* __restrict__ geo, int nc, int c) {
+  const double x0 = geo[0 * (size_t)nc + c], y0 = geo[1 * (size_t)nc + c];
+  const double x1 = geo[2 * (size_t)nc + c], y1 = geo[3 * (size_t)nc + c];
+  const double x2 = geo[4 * (size_t)nc + c], y2 = geo[5 * (size_t)nc + c];
+  const double det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+  const double inv = 1.0 / det;
+  TriGeom g;
+  g.gx[0] = (y1 - y2) * inv; g.gy[0] = (x2 - x1) * inv;
+  g.gx[1] = (y2 - y0) * inv; g.gy[1] = (x0 - x2) * inv;
+  g.gx[2] = (y0 - y1) * inv; g.gy[2] = (x1 - x0) * inv;
+  g.adet = fabs(det);
+  return g;
+}
+
+__device__ __forceinline__ void p2_basis(double l0, double l1, double l2, double* phi) {
+  phi[0] = l0 * (2.0 * l0 - 1.0);
+  phi[1] = l1 * (2.0 * l1 - 1.0);
+  phi[2] = l2 * (2.0 * l2 - 1.0);
+  phi[3] = 4.0 * l1 * l2;
+  phi[4] = 4.0 * l0 * l2;
+  phi[5] = 4.0 * l0 * l1;
+}
+
+// physical gradients of the six P2 basis functions at barycentric point (l0,l1,l2)
+__device__ __forceinline__ void p2_grads(const TriGeom& g, double l0, double l1, double l2, double* Gx, double* Gy) {
+  const double a0 = 4.0 * l0 - 1.0, a1 = 4.0 * l1 - 1.0, a2 = 4.0 * l2 - 1.0;
+  Gx[0] = a0 * g.gx[0]; Gy[0] = a0 * g.gy[0];
+  Gx[1] = a1 * g.gx[1]; Gy[1] = a1 * g.gy[1];
+  Gx[2] = a2 * g.gx[2]; Gy[2] = a2 * g.gy[2];
+  Gx[3] = 4.0 * (l2 * g.gx[1] + l1 * g.gx[2]); Gy[3] = 4.0 * (l2 * g.gy[1] + l1 * g.gy[2]);
+  Gx[4] = 4.0 * (l2 * g.gx[0] + l0 * g.gx[2]); Gy[4] = 4.0 * (l2 * g.gy[0] + l0 * g.gy[2]);
+  Gx[5] = 4.0 * (l1 * g.gx[0] + l0 * g.gx[1]); Gy[5] = 4.0 * (l1 * g.gy[0] + l0 * g.gy[1]);
+}
+
+// degree-2 rule: 3 interior points, weights 1/6 (reference area 1/2)
+__constant__ double kQ2[3][3] = {{2.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0}, {1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0}, {1.0 / 6.0, 2.0 / 3.0, 1.0 / 6.0}};
+// degree-5 rule: 7 points (Radon); barycentrics and weights (sum 1/2)
+#define SFEM_S15 3.872983346207417
+#define SFEM_A1 ((6.0 - SFEM_S15) / 21.0)
+#define SFEM_A2 ((6.0 + SFEM_S15) / 21.0)
+#define SFEM_W1 ((155.0 - SFEM_S15) / 2400.0)
+#define SFEM_W2 ((155.0 + SFEM_S15) / 2400.0)
+__constant__ double kQ5[7][4] = {
+    {1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0, 9.0 / 80.0},
+    {1.0 - 2.0 * SFEM_A1, SFEM_A1, SFEM_A1, SFEM_W1}, {SFEM_A1, SFEM_A1, 1.0 - 2.0 * SFEM_A1, SFEM_W1}, {SFEM_A1, 1.0 - 2.0 * SFEM_A1, SFEM_A1, SFEM_W1},
+    {1.0 - 2.0 * SFEM_A2, SFEM_A2, SFEM_A2, SFEM_W2}, {SFEM_A2, SFEM_A2, 1.0 - 2.0 * SFEM_A2, SFEM_W2}, {SFEM_A2, 1.0 - 2.0 * SFEM_A2, SFEM_A2, SFEM_W2}};
+// Gauss-Legendre on [0,1]: 4 points (exact to degree 7) and 3 points (exact to degree 5)
+__constant__ double kGL4x[4] = {0.06943184420297371, 0.33000947820757187, 0.66999052179242813, 0.93056815579702629};
+__constant__ double kGL4w[4] = {0.17392742256872692, 0.32607257743127308, 0.32607257743127308, 0.17392742256872692};
+
+// ------------------------------------------------------------------ P2 advection-diffusion
+template <bool ADV>
+__global__ void __launch_bounds__(128) k_elem_p2(int nc, const double* __restrict__ geo, const int* __restrict__ celldofs,
+                                                 double D, const double* __restrict__ ux, const double* __restrict__ uy,
+                                                 double* __restrict__ E) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    const TriGeom g = load_geom(geo, nc, c);
+    double Ke[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) Ke[k] = 0.0;
+    const double wk = D * g.adet / 6.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double Gx[6], Gy[6];
+      p2_grads(g, kQ2[q][0], kQ2[q][1], kQ2[q][2], Gx, Gy);
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Ke[i * 6 + j] = fma(wk, fma(Gx[i], Gx[j], Gy[i] * Gy[j]), Ke[i * 6 + j]);
+    }
+    if (ADV) {
+      double vx[6], vy[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int d = celldofs[k * (size_t)nc + c];
+        vx[k] = ux[d];
+        vy[k] = uy[d];
+      }
+#pragma unroll 1
+      for (int q = 0; q < 7; ++q) {
+        const double l0 = kQ5[q][0], l1 = kQ5[q][1], l2 = kQ5[q][2], w = kQ5[q][3] * g.adet;
+        double phi[6], Gx[6], Gy[6];
+        p2_basis(l0, l1, l2, phi);
+        p2_grads(g, l0, l1, l2, Gx, Gy);
+        double uqx = 0.0, uqy = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { uqx = fma(phi[k], vx[k], uqx); uqy = fma(phi[k], vy[k], uqy); }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const double aj = w * fma(uqx, Gx[j], uqy * Gy[j]);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) Ke[i * 6 + j] = fma(phi[i], aj, Ke[i * 6 + j]);
+        }
+      }
+    }
+    double2* out = reinterpret_cast<double2*>(E + (size_t)c * 36);
+#pragma unroll
+    for (int k = 0; k < 18; ++k) out[k] = make_double2(Ke[2 * k], Ke[2 * k + 1]);
+  }
+}
+
+// ------------------------------------------------------------------ P1 (multigrid coarse levels)
+__global__ void __launch_bounds__(kThreads) k_elem_p1(int nc, const double* __restrict__ geo,
+                                                      const int* __restrict__ cellverts, double D,
+                                                      const double* __restrict__ ux, const double* __restrict__ uy,
+                                                      int upwind, double* __restrict__ E) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    const TriGeom g = load_geom(geo, nc, c);
+    const double area = 0.5 * g.adet;
+    double Dc = D, ucx = 0.0, ucy = 0.0;
+    if (ux != nullptr) {
+      for (int k = 0; k < 3; ++k) {
+        const int v = cellverts[k * (size_t)nc + c];
+        ucx += ux[v];
+        ucy += uy[v];
+      }
+      ucx *= (1.0 / 3.0);
+      ucy *= (1.0 / 3.0);
+      if (upwind) {
+        const double pe = sqrt(ucx * ucx + ucy * ucy) * sqrt(g.adet) / (2.0 * D);
+        Dc = D * fmax(1.0, pe);
+      }
+    }
+    double* out = E + (size_t)c * 9;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double v = Dc * area * (g.gx[i] * g.gx[j] + g.gy[i] * g.gy[j]);
+        if (ux != nullptr) v += (area / 3.0) * (ucx * g.gx[j] + ucy * g.gy[j]);
+        out[i * 3 + j] = v;
+      }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_elem_p1_mass(int nc, const double* __restrict__ geo, double* __restrict__ E) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    const TriGeom g = load_geom(geo, nc, c);
+    const double a = g.adet / 24.0;        // area/12
+    double* out = E + (size_t)c * 9;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) out[i * 3 + j] = (i == j) ? 2.0 * a : a;
+  }
+}
+
+// ------------------------------------------------------------------ Taylor-Hood Stokes
+// a = grad u:grad v - div(v) p - q div(u); cell layout [ux x6, uy x6, p x3]; 15x15 row-major.
+__global__ void __launch_bounds__(128) k_elem_th(int nc, const double* __restrict__ geo, double* __restrict__ E) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    const TriGeom g = load_geom(geo, nc, c);
+    double K[36], Bx[18], By[18];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) K[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 18; ++k) { Bx[k] = 0.0; By[k] = 0.0; }
+    const double wk = g.adet / 6.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      double Gx[6], Gy[6];
+      const double l[3] = {kQ2[q][0], kQ2[q][1], kQ2[q][2]};
+      p2_grads(g, l[0], l[1], l[2], Gx, Gy);
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) K[i * 6 + j] = fma(wk, fma(Gx[i], Gx[j], Gy[i] * Gy[j]), K[i * 6 + j]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          Bx[k * 6 + j] = fma(-wk * l[k], Gx[j], Bx[k * 6 + j]);
+          By[k * 6 + j] = fma(-wk * l[k], Gy[j], By[k * 6 + j]);
+        }
+    }
+    double* out = E + (size_t)c * 225;
+    for (int i = 0; i < 6; ++i) {
+      for (int j = 0; j < 6; ++j) {
+        out[i * 15 + j] = K[i * 6 + j];
+        out[i * 15 + 6 + j] = 0.0;
+        out[(6 + i) * 15 + j] = 0.0;
+        out[(6 + i) * 15 + 6 + j] = K[i * 6 + j];
+      }
+      for (int k = 0; k < 3; ++k) {
+        out[i * 15 + 12 + k] = Bx[k * 6 + i];
+        out[(6 + i) * 15 + 12 + k] = By[k * 6 + i];
+      }
+    }
+    for (int k = 0; k < 3; ++k) {
+      for (int j = 0; j < 6; ++j) {
+        out[(12 + k) * 15 + j] = Bx[k * 6 + j];
+        out[(12 + k) * 15 + 6 + j] = By[k * 6 + j];
+      }
+      for (int m = 0; m < 3; ++m) out[(12 + k) * 15 + 12 + m] = 0.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ Robin facets
+// P2 trace basis on a facet parametrised by t in [0,1] from vertex a to vertex b: [a, b, mid]
+template <int NDOF>
+__global__ void __launch_bounds__(kThreads) k_facet_robin(int nf, const double* __restrict__ fgeo,
+                                                          const int* __restrict__ fdofs, double mu_const,
+                                                          const double* __restrict__ mu_nodal, int clamp,
+                                                          double* __restrict__ F) {
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    const double xa = fgeo[0 * (size_t)nf + f], ya = fgeo[1 * (size_t)nf + f];
+    const double xb = fgeo[2 * (size_t)nf + f], yb = fgeo[3 * (size_t)nf + f];
+    const double len = sqrt((xb - xa) * (xb - xa) + (yb - ya) * (yb - ya));
+    double mun[NDOF];
+    for (int k = 0; k < NDOF; ++k) mun[k] = mu_nodal ? mu_nodal[fdofs[k * (size_t)nf + f]] : mu_const;
+    double M[NDOF * NDOF];
+    for (int k = 0; k < NDOF * NDOF; ++k) M[k] = 0.0;
+    for (int q = 0; q < 4; ++q) {
+      const double t = kGL4x[q];
+      double phi[NDOF];
+      if (NDOF == 3) {
+        phi[0] = (1.0 - t) * (1.0 - 2.0 * t);
+        phi[1] = t * (2.0 * t - 1.0);
+        phi[2] = 4.0 * t * (1.0 - t);
+      } else {
+        phi[0] = 1.0 - t;
+        phi[1] = t;
+      }
+      double mu = 0.0;
+      for (int k = 0; k < NDOF; ++k) mu = fma(phi[k], mun[k], mu);
+      if (clamp && !(mu >= 0.0)) mu = 0.0;
+      const double w = kGL4w[q] * len * mu;
+      for (int i = 0; i < NDOF; ++i)
+        for (int j = 0; j < NDOF; ++j) M[i * NDOF + j] = fma(w * phi[i], phi[j], M[i * NDOF + j]);
+    }
+    double* out = F + (size_t)f * (NDOF * NDOF);
+    for (int k = 0; k < NDOF * NDOF; ++k) out[k] = M[k];
+  }
+}
+
+// ------------------------------------------------------------------ gather + Dirichlet
+__global__ void __launch_bounds__(kThreads) k_gather(int nnz, const int* __restrict__ cptr, const int* __restrict__ code,
+                                                     const double* __restrict__ E, double* __restrict__ vals) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nnz; s += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    const int e = cptr[s + 1];
+    for (int k = cptr[s]; k < e; ++k) acc += E[code[k]];
+    vals[s] = acc;
+  }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kThreads) k_dirichlet(int n, const int* __restrict__ rowptr, const int* __restrict__ cols,
+                                                        double* __restrict__ vals, double* __restrict__ rhs,
+                                                        const unsigned char* __restrict__ flag,
+                                                        const double* __restrict__ g, int mode) {
+  constexpr int ROWS = kThreads / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int sub = threadIdx.x / LANES;
+  for (long long base = (long long)blockIdx.x * ROWS; base < n; base += (long long)gridDim.x * ROWS) {
+    const int row = (int)base + sub;
+    const bool valid = row < n;
+    double lift = 0.0;
+    bool isbc = false;
+    if (valid) {
+      isbc = flag[row] != 0;
+      const int s = rowptr[row], e = rowptr[row + 1];
+      for (int k = s + lane; k < e; k += LANES) {
+        const int cj = cols[k];
+        if (isbc) {
+          vals[k] = (cj == row) ? 1.0 : 0.0;
+        } else if (mode == 1 && flag[cj]) {
+          lift = fma(vals[k], g[cj], lift);
+          vals[k] = 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LANES >> 1; o > 0; o >>= 1) lift += __shfl_xor_sync(0xffffffffu, lift, o);
+    if (valid && lane == 0) {
+      if (isbc) rhs[row] = g[row];
+      else if (mode == 1) rhs[row] -= lift;
+    }
+  }
+}
+
+}  // namespace
+
+}  // namespace sfem
+
+using namespace sfem;
+
+extern "C" {
+
+int sfem_elem_p2_advdiff(int nc, const double* geo, const int* celldofs, double D, const double* ux,
+                         const double* uy, double* E, void* stream) {
+  if (nc <= 0) return SFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(nc, 128, 16);
+  if (ux != nullptr && uy != nullptr) {
+    if (celldofs == nullptr) { set_error("celldofs required with a velocity field"); return SFEM_ERR_ARG; }
+    k_elem_p2<true><<<grid, 128, 0, st>>>(nc, geo, celldofs, D, ux, uy, E);
+  } else {
+    k_elem_p2<false><<<grid, 128, 0, st>>>(nc, geo, celldofs, D, ux, uy, E);
+  }
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_elem_p1_advdiff(int nc, const double* geo, const int* cellverts, double D, const double* ux,
+                         const double* uy, int upwind, double* E, void* stream) {
+  if (nc <= 0) return SFEM_OK;
+  if ((ux != nullptr) != (uy != nullptr)) { set_error("ux/uy must both be given"); return SFEM_ERR_ARG; }
+  k_elem_p1<<<grid_for(nc, kThreads), kThreads, 0, (cudaStream_t)stream>>>(nc, geo, cellverts, D, ux, uy, upwind, E);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_elem_th_stokes(int nc, const double* geo, double* E, void* stream) {
+  if (nc <= 0) return SFEM_OK;
+  k_elem_th<<<grid_for(nc, 128, 16), 128, 0, (cudaStream_t)stream>>>(nc, geo, E);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_elem_p1_mass(int nc, const double* geo, double* E, void* stream) {
+  if (nc <= 0) return SFEM_OK;
+  k_elem_p1_mass<<<grid_for(nc, kThreads), kThreads, 0, (cudaStream_t)stream>>>(nc, geo, E);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_facet_p2_robin(int nf, const double* fgeo, const int* fdofs, double mu_const, const double* mu_nodal,
+                        int clamp, double* F, void* stream) {
+  if (nf <= 0) return SFEM_OK;
+  k_facet_robin<3><<<grid_for(nf, kThreads), kThreads, 0, (cudaStream_t)stream>>>(nf, fgeo, fdofs, mu_const, mu_nodal, clamp, F);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_facet_p1_robin(int nf, const double* fgeo, const int* fdofs, double mu_const, const double* mu_nodal,
+                        int clamp, double* F, void* stream) {
+  if (nf <= 0) return SFEM_OK;
+  k_facet_robin<2><<<grid_for(nf, kThreads), kThreads, 0, (cudaStream_t)stream>>>(nf, fgeo, fdofs, mu_const, mu_nodal, clamp, F);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_gather_csr(int nnz, const int* contrib_ptr, const int* contrib_code, const double* E, double* vals,
+                    void* stream) {
+  if (nnz <= 0) return SFEM_OK;
+  k_gather<<<grid_for(nnz, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(nnz, contrib_ptr, contrib_code, E, vals);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_apply_dirichlet(int n, int nnz, const int* rowptr, const int* cols, double* vals, double* rhs,
+                         const unsigned char* bc_flag, const double* bc_val, int mode, void* stream) {
+  if (n <= 0) return SFEM_OK;
+  if (mode != 0 && mode != 1) { set_error("dirichlet mode must be 0 or 1"); return SFEM_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int lanes = pick_lanes(nnz, n);
+  switch (lanes) {
+    case 1: case 2:
+      k_dirichlet<2><<<grid_for(n, kThreads / 2), kThreads, 0, st>>>(n, rowptr, cols, vals, rhs, bc_flag, bc_val, mode); break;
+    case 4:
+      k_dirichlet<4><<<grid_for(n, kThreads / 4), kThreads, 0, st>>>(n, rowptr, cols, vals, rhs, bc_flag, bc_val, mode); break;
+    case 8:
+      k_dirichlet<8><<<grid_for(n, kThreads / 8), kThreads, 0, st>>>(n, rowptr, cols, vals, rhs, bc_flag, bc_val, mode); break;
+    default:
+      k_dirichlet<16><<<grid_for(n, kThreads / 16), kThreads, 0, st>>>(n, rowptr, cols, vals, rhs, bc_flag, bc_val, mode); break;
+  }
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+// Internal (non-ABI) declarations shared by the translation units of libsulcusfem.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sfem {
+
+struct Csr {
+  int nrows = 0;
+  int ncols = 0;
+  long long nnz = 0;
+  const int* rowptr = nullptr;
+  const int* cols = nullptr;
+  const double* vals = nullptr;
+  // shared-memory staged SpMV plan (0 = use the vector kernel): rows per tile, exact max nnz of a
+  // tile (from the host copy of rowptr) and pipeline depth
+  int tile_rows = 0;
+  int tile_cap = 0;
+  int stages = 3;
+};
+
+// sfem_spmv.cu
+int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st);
+int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* nparts, cudaStream_t st);
+int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
+              double c1, double c2, int last, cudaStream_t st);
+int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
+             double c0, cudaStream_t st);
+// sfem_spmv_staged.cu
+int spmv_staged_plan(const Csr& A, int tile_rows, int tile_cap, int stages, const double* x, const double* b,
+                     double* y, int mode, cudaStream_t st);
+
+// sfem_vector.cu
+int vec_set(int n, double a, double* x, cudaStream_t st);
+int vec_copy(int n, const double* x, double* y, cudaStream_t st);
+int vec_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st);
+int vec_mul_scale(int n, double a, const double* d, const double* x, double* y, cudaStream_t st);   // y = a d.*x
+int vec_dot_partial(int n, const double* x, const double* y, double* partial, int* nparts, cudaStream_t st);
+int vec_dot_host(int n, const double* x, const double* y, double* scratch, double* h_out, cudaStream_t st);
+int extract_diag_inv(const Csr& A, double* dinv, cudaStream_t st);
+int dense_gemv(int n, const double* M, const double* x, double* y, cudaStream_t st);
+
+}  // namespace sfem

@@ -1,0 +1,246 @@
+// Vector kernels: axpby family, deterministic two-stage dot products, diagonal extraction, dense
+// coarse-level gemv, concentration post-processing (solvers.py:86-105,154-173).
+#include "sfem_common.cuh"
+#include "sfem_internal.h"
+
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+namespace sfem {
+
+// ------------------------------------------------------------------ global state
+static thread_local std::string t_last_error;
+std::atomic<long long> g_launches{0};
+
+void set_error(const std::string& msg) { t_last_error = msg; }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      sms = v;
+    else
+      sms = 148;
+  }
+  return sms;
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_set(int n, double a, double* __restrict__ x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = a;
+}
+
+__global__ void k_axpby(int n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
+}
+
+__global__ void k_mul_scale(int n, double a, const double* __restrict__ d, const double* x,
+                            double* y) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a * d[i] * x[i];
+}
+
+__global__ void __launch_bounds__(kThreads) k_dot_partial(int n, const double* __restrict__ x,
+                                                          const double* __restrict__ y, double* __restrict__ partial) {
+  __shared__ double sh[33];
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc = fma(x[i], y[i], acc);
+  const double t = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kThreads) k_sum_partials(const double* __restrict__ partial, int n,
+                                                           double* __restrict__ out) {
+  __shared__ double sh[33];
+  const double t = block_sum_array(partial, n, sh);
+  if (threadIdx.x == 0) out[0] = t;
+}
+
+__global__ void k_diag_inv(int n, const int* __restrict__ rowptr, const int* __restrict__ cols,
+                           const double* __restrict__ vals, double* __restrict__ dinv) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double d = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      if (cols[k] == i) d = vals[k];
+    dinv[i] = (d != 0.0) ? 1.0 / d : 1.0;
+  }
+}
+
+// y = M x for a small dense row-major matrix (coarsest multigrid level): one warp per row.
+__global__ void __launch_bounds__(kThreads) k_dense_gemv(int n, const double* __restrict__ M,
+                                                         const double* __restrict__ x, double* __restrict__ y) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n; row += gridDim.x * warps_per_block) {
+    const double* m = M + (size_t)row * n;
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) acc = fma(m[j], x[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[row] = acc;
+  }
+}
+
+// stats: [0] #nonfinite, [1] #negative, [2] min, [3] max, [4] sum   (per block partials, 5 each)
+__global__ void __launch_bounds__(kThreads) k_conc_stats(int n, double* __restrict__ c, int fix_nonfinite,
+                                                         double* __restrict__ partial) {
+  __shared__ double sh[33];
+  double nbad = 0.0, nneg = 0.0, mn = INFINITY, mx = -INFINITY, sum = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double v = c[i];
+    if (!isfinite(v)) {
+      nbad += 1.0;
+      if (fix_nonfinite) { v = 0.0; c[i] = 0.0; } else continue;
+    }
+    if (v < 0.0) nneg += 1.0;
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+    sum += v;
+  }
+  const double a = block_sum(nbad, sh);
+  const double bq = block_sum(nneg, sh);
+  const double s = block_sum(sum, sh);
+  // min / max through the same shared scratch
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ double smn[32], smx[32];
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w) { mn = fmin(mn, smn[w]); mx = fmax(mx, smx[w]); }
+    double* p = partial + 5 * blockIdx.x;
+    p[0] = a; p[1] = bq; p[2] = mn; p[3] = mx; p[4] = s;
+  }
+}
+
+__global__ void k_clamp_negative(int n, double* __restrict__ c) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (c[i] < 0.0) c[i] = 0.0;
+}
+
+// ------------------------------------------------------------------ host wrappers
+int vec_set(int n, double a, double* x, cudaStream_t st) {
+  if (n <= 0) return SFEM_OK;
+  k_set<<<grid_for(n, kThreads * 4), kThreads, 0, st>>>(n, a, x);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int vec_copy(int n, const double* x, double* y, cudaStream_t st) {
+  if (n <= 0) return SFEM_OK;
+  SFEM_CUDA(cudaMemcpyAsync(y, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return SFEM_OK;
+}
+
+int vec_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st) {
+  if (n <= 0) return SFEM_OK;
+  k_axpby<<<grid_for(n, kThreads * 4), kThreads, 0, st>>>(n, a, x, b, y);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int vec_mul_scale(int n, double a, const double* d, const double* x, double* y, cudaStream_t st) {
+  if (n <= 0) return SFEM_OK;
+  k_mul_scale<<<grid_for(n, kThreads * 4), kThreads, 0, st>>>(n, a, d, x, y);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int vec_dot_partial(int n, const double* x, const double* y, double* partial, int* nparts, cudaStream_t st) {
+  const int grid = grid_for(n, kThreads * 4, 4);
+  k_dot_partial<<<grid, kThreads, 0, st>>>(n, x, y, partial);
+  SFEM_LAUNCH_CHECK();
+  *nparts = grid;
+  return SFEM_OK;
+}
+
+// scratch: kMaxPartials + 1 doubles
+int vec_dot_host(int n, const double* x, const double* y, double* scratch, double* h_out, cudaStream_t st) {
+  int np = 0;
+  SFEM_TRY(vec_dot_partial(n, x, y, scratch, &np, st));
+  k_sum_partials<<<1, kThreads, 0, st>>>(scratch, np, scratch + kMaxPartials);
+  SFEM_LAUNCH_CHECK();
+  SFEM_CUDA(cudaMemcpyAsync(h_out, scratch + kMaxPartials, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  return SFEM_OK;
+}
+
+int extract_diag_inv(const Csr& A, double* dinv, cudaStream_t st) {
+  if (A.nrows <= 0) return SFEM_OK;
+  k_diag_inv<<<grid_for(A.nrows, kThreads), kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int dense_gemv(int n, const double* M, const double* x, double* y, cudaStream_t st) {
+  if (n <= 0) return SFEM_OK;
+  k_dense_gemv<<<grid_for(n, kThreads / 32), kThreads, 0, st>>>(n, M, x, y);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+}  // namespace sfem
+
+// ------------------------------------------------------------------ C ABI
+using namespace sfem;
+
+extern "C" {
+
+const char* sfem_last_error(void) { return t_last_error.c_str(); }
+int sfem_version(void) { return 100; }
+int sfem_device_sms(void) { return num_sms(); }
+long long sfem_launch_count(void) { return g_launches.load(); }
+void sfem_launch_count_reset(void) { g_launches.store(0); }
+
+int sfem_vec_axpby(int n, double a, const double* x, double b, double* y, void* stream) {
+  return vec_axpby(n, a, x, b, y, (cudaStream_t)stream);
+}
+
+int sfem_vec_dot(int n, const double* x, const double* y, double* h_out, void* stream) {
+  double* scratch = nullptr;
+  SFEM_CUDA(cudaMalloc(&scratch, (kMaxPartials + 1) * sizeof(double)));
+  int r = vec_dot_host(n, x, y, scratch, h_out, (cudaStream_t)stream);
+  cudaFree(scratch);
+  return r;
+}
+
+int sfem_extract_diag_inv(int n, const int* rowptr, const int* cols, const double* vals, double* dinv, void* stream) {
+  Csr A;
+  A.nrows = A.ncols = n;
+  A.rowptr = rowptr; A.cols = cols; A.vals = vals;
+  return extract_diag_inv(A, dinv, (cudaStream_t)stream);
+}
+
+int sfem_postprocess_concentration(int n, double* c, int fix_nonfinite, double* h_stats, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) { set_error("empty vector"); return SFEM_ERR_ARG; }
+  const int grid = grid_for(n, kThreads * 4, 4);
+  double* partial = nullptr;
+  SFEM_CUDA(cudaMalloc(&partial, (size_t)grid * 5 * sizeof(double)));
+  k_conc_stats<<<grid, kThreads, 0, st>>>(n, c, fix_nonfinite, partial);
+  g_launches.fetch_add(1);
+  std::vector<double> h((size_t)grid * 5);
+  cudaError_t e = cudaMemcpyAsync(h.data(), partial, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaFree(partial); set_error(cudaGetErrorString(e)); return SFEM_ERR_CUDA; }
+  double nbad = 0, nneg = 0, mn = INFINITY, mx = -INFINITY, sum = 0;
+  for (int b = 0; b < grid; ++b) {
+    nbad += h[5 * b]; nneg += h[5 * b + 1];
+    mn = std::fmin(mn, h[5 * b + 2]); mx = std::fmax(mx, h[5 * b + 3]); sum += h[5 * b + 4];
+  }
+  double clamped = 0.0;
+  if (nneg > 0 && std::fabs(mn) < 1e-12) {     // solvers.py:161-164: only tiny negatives are clipped
+    k_clamp_negative<<<grid_for(n, kThreads * 4), kThreads, 0, st>>>(n, c);
+    g_launches.fetch_add(1);
+    clamped = 1.0;
+  }
+  cudaFree(partial);
+  h_stats[0] = nbad; h_stats[1] = nneg; h_stats[2] = mn; h_stats[3] = mx; h_stats[4] = sum / n; h_stats[5] = clamped;
+  return SFEM_OK;
+}
+
+}  // extern "C"

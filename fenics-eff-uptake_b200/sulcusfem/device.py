@@ -1,0 +1,506 @@
+"""Device-side problem objects: upload the host maps once, then assemble / solve / reduce on the GPU.
+
+PyTorch is used only as the device-memory allocator and stream provider (tensors are passed to the
+C ABI as raw pointers); every arithmetic step of the solve path is a kernel of ``libsulcusfem.so``.
+There is no CPU fallback: constructing any of these classes without a CUDA device raises.
+
+Replaces the dolfin objects the reference builds in ``simulation.py:128-130,146`` (function spaces:
+DOF maps + sparsity) and the work of ``solve(a == L, ...)`` in ``solvers.py:55,84,151,213,298``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from . import dofmap as dm
+from . import hierarchy as hy
+from .hostmesh import HostMesh
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Context:
+    """Library handle + CUDA device + stream."""
+    _inst = None
+
+    def __init__(self, device=None):
+        torch = _torch()
+        self.lib = capi.load()
+        if not torch.cuda.is_available():
+            raise capi.SulcusFemError("no CUDA device: sulcusfem has no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            cls._inst = Context()
+        return cls._inst
+
+    @property
+    def stream(self):
+        return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+    def up(self, arr, dtype):
+        torch = _torch()
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        return torch.from_numpy(a).to(self.device, non_blocking=False)
+
+    def zeros(self, n, dtype=None):
+        torch = _torch()
+        return torch.zeros(int(n), dtype=dtype or torch.float64, device=self.device)
+
+    def empty(self, n, dtype=None):
+        torch = _torch()
+        return torch.empty(int(n), dtype=dtype or torch.float64, device=self.device)
+
+
+P = capi.ptr
+
+
+class DeviceCsr:
+    """CSR matrix in HBM (int32 indices, FP64 values); arrays padded for the staged SpMV."""
+    PAD = 16
+
+    def __init__(self, ctx: Context, nrows, ncols, rowptr, cols, vals=None, tile_rows=128):
+        torch = _torch()
+        self.ctx = ctx
+        self.nrows, self.ncols = int(nrows), int(ncols)
+        self.nnz = int(len(cols))
+        rp = np.zeros(self.nrows + 1 + self.PAD, dtype=np.int32)
+        rp[:self.nrows + 1] = rowptr
+        rp[self.nrows + 1:] = rowptr[-1]
+        cc = np.zeros(self.nnz + self.PAD, dtype=np.int32)
+        cc[:self.nnz] = cols
+        self.rowptr = ctx.up(rp, np.int32)
+        self.cols = ctx.up(cc, np.int32)
+        self.vals_buf = torch.zeros(self.nnz + self.PAD, dtype=torch.float64, device=ctx.device)
+        self.vals = self.vals_buf[:self.nnz]
+        if vals is not None:
+            self.vals.copy_(ctx.up(vals, np.float64))
+        # staged-SpMV plan: exact max nnz of a tile (with the 16-byte rounding of the span start)
+        self.tile_rows = int(tile_rows)
+        r0 = np.arange(0, self.nrows, self.tile_rows)
+        r1 = np.minimum(r0 + self.tile_rows, self.nrows)
+        rpa = np.asarray(rowptr, dtype=np.int64)
+        self.tile_cap = int(np.max(rpa[r1] - (rpa[r0] & ~3))) if self.nrows else 0
+
+    def spmv(self, x, y=None, b=None, mode=0, staged=False, stages=3):
+        ctx = self.ctx
+        if y is None:
+            y = ctx.empty(self.nrows)
+        if staged:
+            capi.check(ctx.lib.sfem_spmv_csr_f64_staged(self.nrows, self.nnz, P(self.rowptr), P(self.cols), P(self.vals_buf),
+                                                        P(x), P(b), P(y), mode, self.tile_rows, self.tile_cap, stages,
+                                                        ctx.stream), 'sfem_spmv_csr_f64_staged')
+        else:
+            capi.check(ctx.lib.sfem_spmv_csr_f64(self.nrows, self.nnz, P(self.rowptr), P(self.cols), P(self.vals),
+                                                 P(x), P(b), P(y), mode, ctx.stream), 'sfem_spmv_csr_f64')
+        return y
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.vals.cpu().numpy(), self.cols[:self.nnz].cpu().numpy(),
+                              self.rowptr[:self.nrows + 1].cpu().numpy()), shape=(self.nrows, self.ncols))
+
+
+def cell_geometry(mesh: HostMesh) -> np.ndarray:
+    """[6][nc] SoA vertex coordinates x0,y0,x1,y1,x2,y2."""
+    p = mesh.coords[mesh.cells]
+    return np.ascontiguousarray(p.reshape(mesh.num_cells, 6).T)
+
+
+def facet_geometry(mesh: HostMesh, facets: np.ndarray) -> np.ndarray:
+    e = mesh.edges[facets]
+    return np.ascontiguousarray(np.concatenate([mesh.coords[e[:, 0]], mesh.coords[e[:, 1]]], axis=1).T)
+
+
+class ScalarLevel:
+    """One scalar Lagrange space (P2 system level or P1 multigrid level) on one mesh."""
+
+    def __init__(self, ctx: Context, mesh: HostMesh, bc_markers: np.ndarray, degree: int,
+                 dirichlet_ids: Sequence[int], robin_id: Optional[int]):
+        self.ctx, self.mesh, self.degree = ctx, mesh, degree
+        nc = mesh.num_cells
+        self.nc = nc
+        if degree == 2:
+            cd = dm.p2_cell_dofs(mesh)
+            self.n = dm.p2_num_dofs(mesh)
+        else:
+            cd = dm.p1_cell_dofs(mesh)
+            self.n = mesh.num_vertices
+        self.ndof_cell = cd.shape[1]
+        fam = [(cd, cd)]
+        self.nf = 0
+        if robin_id is not None:
+            f, _, _ = dm.boundary_facets(mesh, bc_markers, robin_id)
+            fd = dm.p2_facet_dofs(mesh, f) if degree == 2 else mesh.edges[f].astype(np.int32)
+            fam.append((fd, fd))
+            self.nf = len(f)
+            self.fgeo = ctx.up(facet_geometry(mesh, f), np.float64) if self.nf else None
+            self.fdofs = ctx.up(np.ascontiguousarray(fd.T), np.int32) if self.nf else None
+            self.robin_facets = f
+        self.pattern = dm.build_pattern(self.n, self.n, fam)
+        pat = self.pattern
+        self.A = DeviceCsr(ctx, self.n, self.n, pat.rowptr, pat.cols)
+        self.contrib_ptr = ctx.up(pat.contrib_ptr, np.int32)
+        self.contrib_code = ctx.up(pat.contrib_code, np.int32)
+        self.E = ctx.zeros(max(pat.buffer_len, 1))
+        self.facet_base = pat.family_base[1] if len(fam) > 1 else pat.buffer_len
+        self.geo = ctx.up(cell_geometry(mesh), np.float64)
+        self.celldofs = ctx.up(np.ascontiguousarray(cd.T), np.int32)
+        # Dirichlet data (later ids overwrite earlier ones on shared dofs, like a list of dolfin bcs)
+        flag = np.zeros(self.n, dtype=np.uint8)
+        self.bc_dofs = {}
+        for i in dirichlet_ids:
+            d = dm.dirichlet_dofs_p2(mesh, bc_markers, i) if degree == 2 else dm.dirichlet_dofs_p1(mesh, bc_markers, i)
+            self.bc_dofs[i] = d
+            flag[d] = 1
+        self.bc_flag_host = flag
+        self.bc_flag = ctx.up(flag, np.uint8)
+        self.bc_val = ctx.zeros(self.n)
+        self.rhs = ctx.zeros(self.n)
+
+    def set_bc_values(self, values: Dict[int, object]):
+        """values[id] = scalar or array over the dofs of that id; applied in dict order."""
+        g = np.zeros(self.n)
+        for i, v in values.items():
+            g[self.bc_dofs[i]] = v
+        self.bc_val.copy_(self.ctx.up(g, np.float64))
+        return g
+
+    def assemble(self, D: float, ux=None, uy=None, mu_const: float = 0.0, mu_nodal=None, clamp=False,
+                 upwind=False, robin=True):
+        ctx, lib = self.ctx, self.ctx.lib
+        if self.degree == 2:
+            capi.check(lib.sfem_elem_p2_advdiff(self.nc, P(self.geo), P(self.celldofs), float(D), P(ux), P(uy),
+                                                P(self.E), ctx.stream), 'sfem_elem_p2_advdiff')
+        else:
+            capi.check(lib.sfem_elem_p1_advdiff(self.nc, P(self.geo), P(self.celldofs), float(D), P(ux), P(uy),
+                                                int(bool(upwind)), P(self.E), ctx.stream), 'sfem_elem_p1_advdiff')
+        if self.nf:
+            F = self.E[self.facet_base:]
+            if robin:
+                fn = lib.sfem_facet_p2_robin if self.degree == 2 else lib.sfem_facet_p1_robin
+                capi.check(fn(self.nf, P(self.fgeo), P(self.fdofs), float(mu_const), P(mu_nodal), int(bool(clamp)),
+                              P(F), ctx.stream), 'sfem_facet_robin')
+            else:
+                F.zero_()
+        capi.check(lib.sfem_gather_csr(self.A.nnz, P(self.contrib_ptr), P(self.contrib_code), P(self.E), P(self.A.vals),
+                                       ctx.stream), 'sfem_gather_csr')
+
+    def apply_bc(self, mode: int, rhs=None):
+        ctx = self.ctx
+        rhs = self.rhs if rhs is None else rhs
+        capi.check(ctx.lib.sfem_apply_dirichlet(self.n, self.A.nnz, P(self.A.rowptr), P(self.A.cols), P(self.A.vals), P(rhs),
+                                                P(self.bc_flag), P(self.bc_val), mode, ctx.stream), 'sfem_apply_dirichlet')
+        return rhs
+
+
+class DeviceTransfer:
+    def __init__(self, ctx: Context, T: hy.Transfer, fine_bc: np.ndarray, coarse_bc: np.ndarray):
+        keep = (fine_bc[np.repeat(np.arange(T.n_fine), np.diff(T.rowptr))] == 0) & (coarse_bc[T.cols] == 0)
+        vals = np.where(keep, T.vals, 0.0)
+        self.P = DeviceCsr(ctx, T.n_fine, T.n_coarse, T.rowptr, T.cols, vals)
+        self.R = DeviceCsr(ctx, T.n_coarse, T.n_fine, T.t_rowptr, T.t_cols, vals[T.t_perm])
+        self.nested = T.nested
+        if not T.nested:
+            # unfiltered restriction + reciprocal row sums: weighted average used to carry the
+            # velocity to the non-nested coarse mesh (preconditioner data only)
+            self.Rfull = DeviceCsr(ctx, T.n_coarse, T.n_fine, T.t_rowptr, T.t_cols, T.t_vals)
+            rs = np.add.reduceat(T.t_vals, T.t_rowptr[:-1].astype(np.int64)) if len(T.t_vals) else np.ones(T.n_coarse)
+            rs[np.diff(T.t_rowptr) == 0] = 1.0
+            self.rinv = ctx.up(1.0 / rs, np.float64)
+
+
+class Multigrid:
+    """sfem_mg handle over [system level, P1 levels...]."""
+
+    def __init__(self, ctx: Context, levels: List[ScalarLevel], transfers: List[DeviceTransfer],
+                 cheb_degree=2, eig_ratio=8.0):
+        self.ctx, self.levels, self.transfers = ctx, levels, transfers
+        nl = len(levels)
+        self.coarse_inv = ctx.zeros(levels[-1].n ** 2) if nl > 1 else None
+        IntArr, PtrArr = C.c_int * nl, C.c_void_p * nl
+
+        def parr(ts):
+            vals = [t.data_ptr() if t is not None else None for t in ts] + [None] * (nl - len(ts))
+            return PtrArr(*vals)
+        self._keep = dict(
+            n=IntArr(*[l.n for l in levels]), annz=IntArr(*[l.A.nnz for l in levels]),
+            arp=parr([l.A.rowptr for l in levels]), ac=parr([l.A.cols for l in levels]), av=parr([l.A.vals for l in levels]),
+            pnnz=IntArr(*([t.P.nnz for t in transfers] + [0])),
+            prp=parr([t.P.rowptr for t in transfers]), pc=parr([t.P.cols for t in transfers]), pv=parr([t.P.vals for t in transfers]),
+            rrp=parr([t.R.rowptr for t in transfers]), rc=parr([t.R.cols for t in transfers]), rv=parr([t.R.vals for t in transfers]))
+        k = self._keep
+        self.handle = ctx.lib.sfem_mg_create(nl, k['n'], k['annz'], k['arp'], k['ac'], k['av'], k['pnnz'], k['prp'], k['pc'],
+                                             k['pv'], k['rrp'], k['rc'], k['rv'], P(self.coarse_inv), int(cheb_degree),
+                                             float(eig_ratio))
+        if not self.handle:
+            raise capi.SulcusFemError("sfem_mg_create failed: " + ctx.lib.sfem_last_error().decode())
+
+    def setup(self):
+        ctx = self.ctx
+        if self.coarse_inv is not None:
+            c = self.levels[-1]
+            capi.check(ctx.lib.sfem_dense_inverse_csr(c.n, P(c.A.rowptr), P(c.A.cols), P(c.A.vals), P(self.coarse_inv),
+                                                      ctx.stream), 'sfem_dense_inverse_csr')
+        capi.check(ctx.lib.sfem_mg_setup(self.handle, ctx.stream), 'sfem_mg_setup')
+
+    def vcycle(self, b, x=None):
+        x = self.ctx.empty(self.levels[0].n) if x is None else x
+        capi.check(self.ctx.lib.sfem_mg_vcycle(self.handle, P(b), P(x), self.ctx.stream), 'sfem_mg_vcycle')
+        return x
+
+    def lambda_max(self):
+        out = (C.c_double * len(self.levels))()
+        capi.check(self.ctx.lib.sfem_mg_lambda_max(self.handle, out), 'sfem_mg_lambda_max')
+        return list(out)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.ctx.lib.sfem_mg_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class ScalarProblem:
+    """P2 scalar advection-diffusion-Robin problem with its multigrid hierarchy (one mesh)."""
+
+    def __init__(self, mesh: HostMesh, bc_markers: np.ndarray, dirichlet_ids=(1, 2), robin_id: Optional[int] = 4,
+                 hierarchy: Optional[hy.Hierarchy] = None, ctx: Optional[Context] = None,
+                 cheb_degree=2, eig_ratio=8.0):
+        self.ctx = ctx or Context.get()
+        self.mesh = mesh
+        self.hierarchy = hierarchy or hy.build_hierarchy(mesh)
+        H = self.hierarchy
+        self.fine = ScalarLevel(self.ctx, mesh, bc_markers, 2, dirichlet_ids, robin_id)
+        self.levels = [self.fine]
+        for m in H.meshes:
+            mk = bc_markers if m is mesh else hy.level_markers(m)['bc_markers'].values
+            self.levels.append(ScalarLevel(self.ctx, m, mk, 1, dirichlet_ids, robin_id))
+        self.transfers = [DeviceTransfer(self.ctx, T, self.levels[l].bc_flag_host, self.levels[l + 1].bc_flag_host)
+                          for l, T in enumerate(H.transfers)]
+        self.mg = Multigrid(self.ctx, self.levels, self.transfers, cheb_degree, eig_ratio)
+        self.n = self.fine.n
+        self.x = self.ctx.zeros(self.n)
+        self.last_info = None
+
+    def _coarse_velocity(self, ux, uy):
+        """P1 nodal velocity on every multigrid level (prefix for nested, weighted average otherwise)."""
+        out = []
+        cu, cv = ux, uy
+        for l, T in enumerate(self.transfers):
+            lev = self.levels[l + 1]
+            if T.nested:
+                cu, cv = cu[:lev.n], cv[:lev.n]
+            else:
+                lib, ctx = self.ctx.lib, self.ctx
+                nu, nv_ = ctx.empty(lev.n), ctx.empty(lev.n)
+                for src, dst in ((cu, nu), (cv, nv_)):
+                    T.Rfull.spmv(src, dst)
+                    capi.check(lib.sfem_vec_pointwise_mul(lev.n, 1.0, P(T.rinv), P(dst), P(dst), ctx.stream), 'pointwise_mul')
+                cu, cv = nu, nv_
+            out.append((cu.contiguous(), cv.contiguous()))
+        return out
+
+    def assemble(self, D, ux=None, uy=None, mu_const=0.0, mu_nodal=None, clamp=False, bc_values=None,
+                 bc_mode=1, robin=True, coarse_mu: Optional[float] = None):
+        """Assemble the system level (+ BCs) and rediscretise the multigrid levels."""
+        f = self.fine
+        f.set_bc_values(bc_values if bc_values is not None else {i: 0.0 for i in f.bc_dofs})
+        f.assemble(D, ux, uy, mu_const, mu_nodal, clamp, robin=robin)
+        f.rhs.zero_()
+        f.apply_bc(bc_mode)
+        self.bc_mode = bc_mode
+        vel = self._coarse_velocity(ux, uy) if ux is not None else [(None, None)] * len(self.transfers)
+        # coarse levels are preconditioner data only: a spatially varying mu is represented there by
+        # the constant `coarse_mu` (mean of mu over the Robin boundary)
+        for l, lev in enumerate(self.levels[1:]):
+            cu, cv = vel[l]
+            lev.assemble(D, cu, cv, mu_const if coarse_mu is None else coarse_mu, None, False,
+                         upwind=ux is not None, robin=robin)
+            lev.apply_bc(1)
+        self.mg.setup()
+
+    def solve(self, method='cg', rtol=1e-13, maxit=400, restart=80, x0=None):
+        ctx, f = self.ctx, self.fine
+        torch = _torch()
+        if x0 is None:
+            self.x.copy_(f.bc_val * f.bc_flag.to(torch.float64))
+        else:
+            self.x.copy_(x0)
+        info = (C.c_double * 4)()
+        A = f.A
+        if method == 'cg':
+            rc = ctx.lib.sfem_krylov_cg(f.n, A.nnz, P(A.rowptr), P(A.cols), P(A.vals), self.mg.handle, P(f.rhs), P(self.x),
+                                        float(rtol), int(maxit), info, ctx.stream)
+            capi.check(rc, 'sfem_krylov_cg')
+        elif method == 'fgmres':
+            rc = ctx.lib.sfem_krylov_fgmres(f.n, A.nnz, P(A.rowptr), P(A.cols), P(A.vals), self.mg.handle, P(f.rhs), P(self.x),
+                                            float(rtol), int(restart), int(maxit), info, ctx.stream)
+            capi.check(rc, 'sfem_krylov_fgmres')
+        else:
+            raise ValueError(f"unknown method {method!r}")
+        self.last_info = {'iterations': int(info[0]), 'relres': float(info[1]), 'converged': bool(info[2]),
+                          'estimate': float(info[3]), 'method': method}
+        return self.x
+
+
+class StokesProblem:
+    """Taylor-Hood Stokes system (solvers.py:237-306) with MINRES + block-diagonal multigrid."""
+
+    def __init__(self, mesh: HostMesh, bc_markers: np.ndarray, hierarchy: Optional[hy.Hierarchy] = None,
+                 ctx: Optional[Context] = None, velocity_ids=(1, 4, 3)):
+        self.ctx = ctx or Context.get()
+        ctx = self.ctx
+        self.mesh = mesh
+        self.n2 = dm.p2_num_dofs(mesh)
+        self.nv = mesh.num_vertices
+        self.n = 2 * self.n2 + self.nv
+        self.nc = mesh.num_cells
+        cd = dm.th_cell_dofs(mesh)
+        self.pattern = dm.build_pattern(self.n, self.n, [(cd, cd)])
+        self.A = DeviceCsr(ctx, self.n, self.n, self.pattern.rowptr, self.pattern.cols)
+        self.contrib_ptr = ctx.up(self.pattern.contrib_ptr, np.int32)
+        self.contrib_code = ctx.up(self.pattern.contrib_code, np.int32)
+        self.E = ctx.zeros(self.pattern.buffer_len)
+        self.geo = ctx.up(cell_geometry(mesh), np.float64)
+        # velocity preconditioner: scalar stiffness hierarchy with the velocity Dirichlet set
+        self.vel = ScalarProblem(mesh, bc_markers, dirichlet_ids=tuple(velocity_ids), robin_id=None,
+                                 hierarchy=hierarchy, ctx=ctx)
+        # pressure mass matrix (P1)
+        c1 = dm.p1_cell_dofs(mesh)
+        mp = dm.build_pattern(self.nv, self.nv, [(c1, c1)])
+        self.Mp = DeviceCsr(ctx, self.nv, self.nv, mp.rowptr, mp.cols)
+        self._mp = (ctx.up(mp.contrib_ptr, np.int32), ctx.up(mp.contrib_code, np.int32), ctx.zeros(mp.buffer_len))
+        # Dirichlet data on W.sub(0): both components on every velocity id
+        self.bc_markers = bc_markers
+        self.velocity_ids = tuple(velocity_ids)
+        self.bc_flag_host = np.zeros(self.n, dtype=np.uint8)
+        self.bc_flag = None
+        self.bc_val = ctx.zeros(self.n)
+        self.rhs = ctx.zeros(self.n)
+        self.x = ctx.zeros(self.n)
+        self.last_info = None
+
+    def set_bcs(self, values_by_id):
+        """values_by_id: ordered {id: (gx over dofs, gy over dofs)} -- later ids overwrite earlier."""
+        g = np.zeros(self.n)
+        flag = np.zeros(self.n, dtype=np.uint8)
+        for i, (gx, gy) in values_by_id.items():
+            d = dm.dirichlet_dofs_p2(self.mesh, self.bc_markers, i)
+            g[d] = gx
+            g[d + self.n2] = gy
+            flag[d] = 1
+            flag[d + self.n2] = 1
+        self.bc_flag_host = flag
+        self.bc_flag = self.ctx.up(flag, np.uint8)
+        self.bc_val.copy_(self.ctx.up(g, np.float64))
+        return g
+
+    def assemble(self, bc_mode=1):
+        ctx, lib = self.ctx, self.ctx.lib
+        capi.check(lib.sfem_elem_th_stokes(self.nc, P(self.geo), P(self.E), ctx.stream), 'sfem_elem_th_stokes')
+        capi.check(lib.sfem_gather_csr(self.A.nnz, P(self.contrib_ptr), P(self.contrib_code), P(self.E), P(self.A.vals),
+                                       ctx.stream), 'sfem_gather_csr')
+        self.rhs.zero_()
+        capi.check(lib.sfem_apply_dirichlet(self.n, self.A.nnz, P(self.A.rowptr), P(self.A.cols), P(self.A.vals), P(self.rhs),
+                                            P(self.bc_flag), P(self.bc_val), bc_mode, ctx.stream), 'sfem_apply_dirichlet')
+        # preconditioner pieces
+        self.vel.assemble(1.0, robin=False)
+        cp, cc, E = self._mp
+        capi.check(lib.sfem_elem_p1_mass(self.nc, P(self.geo), P(E), ctx.stream), 'sfem_elem_p1_mass')
+        capi.check(lib.sfem_gather_csr(self.Mp.nnz, P(cp), P(cc), P(E), P(self.Mp.vals), ctx.stream), 'sfem_gather_csr')
+
+    def solve(self, rtol=1e-14, maxit=2000):
+        ctx = self.ctx
+        torch = _torch()
+        self.x.copy_(self.bc_val * self.bc_flag.to(torch.float64))
+        info = (C.c_double * 4)()
+        A, Mp = self.A, self.Mp
+        rc = ctx.lib.sfem_krylov_minres_stokes(self.n2, self.nv, A.nnz, P(A.rowptr), P(A.cols), P(A.vals), self.vel.mg.handle,
+                                               Mp.nnz, P(Mp.rowptr), P(Mp.cols), P(Mp.vals), P(self.rhs), P(self.x),
+                                               float(rtol), int(maxit), info, ctx.stream)
+        capi.check(rc, 'sfem_krylov_minres_stokes')
+        self.last_info = {'iterations': int(info[0]), 'relres': float(info[1]), 'converged': bool(info[2]),
+                          'estimate': float(info[3]), 'method': 'minres'}
+        n2 = self.n2
+        return self.x[:n2], self.x[n2:2 * n2], self.x[2 * n2:]
+
+
+class FunctionalPlan:
+    """Facet / cell groups of the reference's integration measures (mesh.py:721-737), built once."""
+    GROUPS = ['left', 'right', 'top', 'bottom', 'bottom_left', 'sulcus', 'bottom_right', 'y0_ext', 'mouth']
+
+    def __init__(self, mesh: HostMesh, markers: dict, domain_type: str, ctx: Optional[Context] = None):
+        self.ctx = ctx or Context.get()
+        ctx = self.ctx
+        self.mesh, self.domain_type = mesh, domain_type
+        bc = markers['bc_markers'].values
+        ent_cell, ent_loc, ptr = [], [], [0]
+
+        def add(facets, cells, locs):
+            ent_cell.append(np.asarray(cells, dtype=np.int64))
+            ent_loc.append(np.asarray(locs, dtype=np.int64))
+            ptr.append(ptr[-1] + len(facets))
+        for mid in (1, 2, 3, 4):
+            add(*dm.boundary_facets(mesh, bc, mid))
+        if domain_type == 'sulcus':
+            bs = markers['bottom_segment_markers'].values
+            y0 = markers['y0_markers'].values
+            dmk = markers['domain_markers'].values
+            for mid in (5, 6, 7):
+                add(*dm.boundary_facets(mesh, bs, mid))
+            add(*dm.boundary_facets(mesh, y0, 10))
+            # interior y0 facets: channel-side (cell marker 2) trace, analysis.py:217-237
+            f = np.flatnonzero((y0 == 10) & ~mesh.edge_on_boundary)
+            c0, c1 = mesh.edge_cells[f, 0], mesh.edge_cells[f, 1]
+            chan0, chan1 = dmk[c0] == 2, dmk[c1] == 2
+            if np.any(chan0 & chan1):
+                raise ValueError("interior y0 facet with channel cells on both sides")
+            sel = chan0 | chan1
+            f = f[sel]
+            cells = np.where(chan0[sel], c0[sel], c1[sel])
+            locs = np.where(chan0[sel], mesh.edge_local[f, 0], mesh.edge_local[f, 1])
+            add(f, cells, locs)
+        self.ngroups = len(ptr) - 1
+        self.grp_ptr = ctx.up(np.asarray(ptr), np.int32)
+        ec = np.concatenate(ent_cell) if ent_cell else np.zeros(0)
+        el = np.concatenate(ent_loc) if ent_loc else np.zeros(0)
+        self.ent_cell = ctx.up(np.concatenate([ec, [0]]), np.int32)
+        self.ent_local = ctx.up(np.concatenate([el, [0]]), np.int32)
+        self.geo = ctx.up(cell_geometry(mesh), np.float64)
+        self.celldofs = ctx.up(np.ascontiguousarray(dm.p2_cell_dofs(mesh).T), np.int32)
+        if domain_type == 'sulcus':
+            self.cell_marker = ctx.up(markers['domain_markers'].values, np.int32)
+            self.nmarkers = 3
+        else:
+            self.cell_marker = None
+            self.nmarkers = 1
+        self.out_f = ctx.zeros(self.ngroups * 8)
+        self.out_c = ctx.zeros(self.nmarkers * 2)
+
+    def evaluate(self, c, ux=None, uy=None, D=1.0, mu_const=0.0, mu_nodal=None):
+        """Returns (facet[ngroups,8], cell[nmarkers,2]) as numpy arrays (one D2H copy each)."""
+        ctx, lib, m = self.ctx, self.ctx.lib, self.mesh
+        capi.check(lib.sfem_facet_functionals(self.ngroups, P(self.grp_ptr), P(self.ent_cell), P(self.ent_local), P(self.geo),
+                                              P(self.celldofs), m.num_cells, P(c), P(ux), P(uy), float(D), float(mu_const),
+                                              P(mu_nodal), P(self.out_f), ctx.stream), 'sfem_facet_functionals')
+        if self.cell_marker is None:
+            # marker pointer NULL -> every cell counts for marker 0
+            capi.check(lib.sfem_cell_functionals(m.num_cells, P(self.geo), P(self.celldofs), None, 1, P(c), P(self.out_c),
+                                                 ctx.stream), 'sfem_cell_functionals')
+        else:
+            capi.check(lib.sfem_cell_functionals(m.num_cells, P(self.geo), P(self.celldofs), P(self.cell_marker), self.nmarkers,
+                                                 P(c), P(self.out_c), ctx.stream), 'sfem_cell_functionals')
+        return (self.out_f.cpu().numpy().reshape(self.ngroups, 8).copy(),
+                self.out_c.cpu().numpy().reshape(self.nmarkers, 2).copy())

@@ -1,0 +1,158 @@
+"""DOF maps, CSR sparsity patterns and gather-style scatter maps (host side, built once per mesh).
+
+Replaces what dolfin's ``DofMapBuilder`` / ``SparsityPatternBuilder`` do when the reference calls
+``FunctionSpace(mesh,"CG",2)`` (reference ``simulation.py:146``) and
+``VectorFunctionSpace``/``MixedElement`` (``simulation.py:128-130``).
+
+Numbering contract: the UFC numbering dolfin starts from *before* its
+build-dependent graph reordering -- P1 dof = vertex index; P2 dof = vertex index for the three
+vertex dofs and ``n_v + edge index`` for the three edge dofs (edges numbered lexicographically by
+sorted vertex pair); the Taylor-Hood space concatenates ``[u_x (P2), u_y (P2), p (P1)]`` with
+offsets and uses the cell layout ``[u_x x6, u_y x6, p x3]``.
+
+Sparsity (App. B.2): union over cells of the full clique of the element dofs, *including* the
+structural zeros (u_x-u_y and p-p blocks of the Stokes matrix); exterior-facet integrals add
+nothing new.  Column indices are sorted inside each row.
+
+The scatter map is stored gather-style: for every CSR slot the list of element-buffer positions
+that contribute to it, sorted by (family, cell) so device assembly is a fixed-order sum with no
+atomics and is bit-reproducible.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .hostmesh import HostMesh
+
+# local vertices of local facet l (the facet opposite local vertex l), UFC ordering
+FACET_LOCAL_VERTS = np.array([[1, 2], [0, 2], [0, 1]], dtype=np.int64)
+
+
+def p1_cell_dofs(mesh: HostMesh) -> np.ndarray:
+    return mesh.cells.astype(np.int32)
+
+
+def p2_cell_dofs(mesh: HostMesh) -> np.ndarray:
+    nv = mesh.num_vertices
+    return np.concatenate([mesh.cells, mesh.cell_edges + nv], axis=1).astype(np.int32)
+
+
+def p2_num_dofs(mesh: HostMesh) -> int:
+    return mesh.num_vertices + mesh.num_edges
+
+
+def th_num_dofs(mesh: HostMesh) -> int:
+    return 2 * p2_num_dofs(mesh) + mesh.num_vertices
+
+
+def th_cell_dofs(mesh: HostMesh) -> np.ndarray:
+    n2 = p2_num_dofs(mesh)
+    c2 = p2_cell_dofs(mesh).astype(np.int64)
+    return np.concatenate([c2, c2 + n2, mesh.cells.astype(np.int64) + 2 * n2], axis=1).astype(np.int32)
+
+
+def p2_dof_coordinates(mesh: HostMesh) -> np.ndarray:
+    return np.concatenate([mesh.coords, mesh.edge_midpoints()], axis=0)
+
+
+def p2_facet_dofs(mesh: HostMesh, facets: np.ndarray) -> np.ndarray:
+    """Global P2 dofs [va, vb, edge] of each facet (va < vb)."""
+    facets = np.asarray(facets, dtype=np.int64)
+    nv = mesh.num_vertices
+    return np.concatenate([mesh.edges[facets].astype(np.int64), (facets + nv)[:, None]], axis=1).astype(np.int32)
+
+
+def p2_facet_local_dofs(local_facet: np.ndarray) -> np.ndarray:
+    """Cell-local P2 dof indices [a, b, 3+l] of local facet l."""
+    l = np.asarray(local_facet, dtype=np.int64)
+    return np.concatenate([FACET_LOCAL_VERTS[l], (3 + l)[:, None]], axis=1).astype(np.int32)
+
+
+@dataclass
+class CsrPattern:
+    nrows: int
+    ncols: int
+    rowptr: np.ndarray          # int32 [nrows+1]
+    cols: np.ndarray            # int32 [nnz]
+    contrib_ptr: np.ndarray     # int32 [nnz+1]   gather map: slot -> range in contrib_code
+    contrib_code: np.ndarray    # int32 [total]   positions in the element buffer
+    family_base: List[int]      # element-buffer offset of each family
+    buffer_len: int             # total doubles in the element buffer
+
+    @property
+    def nnz(self) -> int:
+        return int(self.cols.shape[0])
+
+
+def build_pattern(nrows: int, ncols: int,
+                  families: Sequence[Tuple[np.ndarray, np.ndarray]]) -> CsrPattern:
+    """CSR pattern + gather map for a list of element families.
+
+    ``families[f] = (row_dofs [n_f, a_f], col_dofs [n_f, b_f])``.  The element buffer is SoA per
+    family: entry (unit u, local i, local j) of family f lives at
+    ``family_base[f] + (i*b_f + j)*n_f + u`` so that consecutive units are contiguous (coalesced
+    element-kernel writes).
+    """
+    key_parts, code_parts, bases = [], [], []
+    base = 0
+    for rows, cols in families:
+        rows = np.asarray(rows, dtype=np.int64)
+        cols = np.asarray(cols, dtype=np.int64)
+        n, a = rows.shape
+        b = cols.shape[1]
+        bases.append(base)
+        if n:
+            keys = (rows[:, :, None] * ncols + cols[:, None, :]).reshape(n, a * b)
+            codes = base + np.arange(a * b, dtype=np.int64)[None, :] * n + np.arange(n, dtype=np.int64)[:, None]
+            key_parts.append(keys.ravel())
+            code_parts.append(codes.ravel())
+        base += n * a * b
+    if base >= 2 ** 31:
+        raise ValueError("element buffer exceeds int32 addressing")
+    keys = np.concatenate(key_parts) if key_parts else np.zeros(0, dtype=np.int64)
+    codes = np.concatenate(code_parts) if code_parts else np.zeros(0, dtype=np.int64)
+    order = np.argsort(keys, kind='stable')       # stable: contributions stay in (family, unit) order
+    skeys = keys[order]
+    new = np.ones(len(skeys), dtype=bool)
+    new[1:] = skeys[1:] != skeys[:-1]
+    starts = np.flatnonzero(new)
+    ukeys = skeys[starts]
+    contrib_ptr = np.concatenate([starts, [len(skeys)]]).astype(np.int32)
+    contrib_code = codes[order].astype(np.int32)
+    r = ukeys // ncols
+    c = (ukeys % ncols).astype(np.int32)
+    rowptr = np.zeros(nrows + 1, dtype=np.int64)
+    np.add.at(rowptr, r + 1, 1)
+    rowptr = np.cumsum(rowptr).astype(np.int32)
+    return CsrPattern(nrows, ncols, rowptr, c, contrib_ptr, contrib_code, bases, base)
+
+
+def transpose_csr(nrows, ncols, rowptr, cols, vals=None):
+    """CSR transpose; returns (rowptr_t, cols_t, perm) with ``vals_t = vals[perm]``."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    rows = np.repeat(np.arange(nrows, dtype=np.int64), np.diff(rowptr))
+    perm = np.argsort(np.asarray(cols, dtype=np.int64) * nrows + rows, kind='stable')
+    cols_t = rows[perm].astype(np.int32)
+    cnt = np.bincount(np.asarray(cols, dtype=np.int64), minlength=ncols)
+    rowptr_t = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    return rowptr_t, cols_t, perm.astype(np.int64)
+
+
+def boundary_facets(mesh: HostMesh, markers: np.ndarray, marker_id: int):
+    """Exterior facets with the given id (a ``ds(id)`` measure): (facet, cell, local facet)."""
+    f = np.flatnonzero((np.asarray(markers) == marker_id) & mesh.edge_on_boundary)
+    return f, mesh.edge_cells[f, 0].astype(np.int64), mesh.edge_local[f, 0].astype(np.int64)
+
+
+def dirichlet_dofs_p2(mesh: HostMesh, markers: np.ndarray, marker_id: int) -> np.ndarray:
+    """P2 dofs of ``DirichletBC(V, g, markers, id)`` (topological: both vertices + edge dof)."""
+    f = np.flatnonzero(np.asarray(markers) == marker_id)
+    return np.unique(p2_facet_dofs(mesh, f).ravel()).astype(np.int64)
+
+
+def dirichlet_dofs_p1(mesh: HostMesh, markers: np.ndarray, marker_id: int) -> np.ndarray:
+    f = np.flatnonzero(np.asarray(markers) == marker_id)
+    return np.unique(mesh.edges[f].ravel()).astype(np.int64)

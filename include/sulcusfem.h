@@ -1,0 +1,163 @@
+/*
+ * sulcusfem.h -- C ABI of libsulcusfem.so, the B200 (sm_100a) finite-element solve path behind
+ * the reference's solvers.py / analysis.py entry points.
+ *
+ * The reference (jesstunn/fenics-eff-uptake) has no FFI of its own: every entry below replaces a
+ * piece of work that the reference hands to dolfin 2019.1 (C++/FFC/PETSc) through a Python call.
+ * The "replaces" notes cite the reference call site (file:line under /root/reference) whose native
+ * work the entry point takes over.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors are used as buffers by
+ *     the Python host) unless the parameter name starts with h_ (host pointer);
+ *   - all floating point data is IEEE double, all index data int32;
+ *   - every call takes a cudaStream_t as `void* stream` and only enqueues work on it (the Krylov
+ *     drivers synchronise that stream when they poll convergence);
+ *   - return value 0 = success, negative = error; sfem_last_error() returns a message for the
+ *     calling thread;
+ *   - handles own their internal work space, allocated at *_create and released at *_destroy.
+ */
+#ifndef SULCUSFEM_H
+#define SULCUSFEM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFEM_OK 0
+#define SFEM_ERR_CUDA (-1)
+#define SFEM_ERR_ARG (-2)
+#define SFEM_ERR_NOCONV (-3)
+
+const char* sfem_last_error(void);
+int sfem_version(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int sfem_device_sms(void);
+/* kernels launched by this library since the last reset (bench.py `gpu_launches`) */
+long long sfem_launch_count(void);
+void sfem_launch_count_reset(void);
+
+/* ------------------------------------------------------------------ sparse mat-vec ---------- */
+/* y = A x (mode 0), y = b - A x (mode 1), y += A x (mode 2).  FP64 values, int32 indices.
+ * replaces: PETSc MatMult inside solve(a == L, ...)  solvers.py:55,84,151,213,298
+ * (sub-warp-per-row vector kernel, grid-stride, grid = multiple of the SM count) */
+int sfem_spmv_csr_f64(int nrows, int nnz, const int* rowptr, const int* cols, const double* vals,
+                      const double* x, const double* b, double* y, int mode, void* stream);
+/* Shared-memory staged variant (modes 0 and 1): tiles of `tile_rows` consecutive rows (multiple of
+ * 4) are streamed HBM -> shared memory by 1-D bulk async copies (TMA) through a `stages`-deep
+ * mbarrier pipeline.  `tile_cap` = exact maximum over tiles of
+ * rowptr[min(r0+tile_rows,nrows)] - (rowptr[r0] & ~3)  (the host has rowptr).  rowptr / cols / vals
+ * must be 16-byte aligned and allocated with >= 4 elements of padding past their logical end. */
+int sfem_spmv_csr_f64_staged(int nrows, int nnz, const int* rowptr, const int* cols, const double* vals,
+                             const double* x, const double* b, double* y, int mode,
+                             int tile_rows, int tile_cap, int stages, void* stream);
+
+/* ------------------------------------------------------------------ assembly ---------------- */
+/* Element matrices of  D grad(c).grad(phi) + (u.grad c) phi  on P2 triangles.
+ *   geo      [6][nc] SoA vertex coordinates x0,y0,x1,y1,x2,y2 of every cell
+ *   celldofs [6][nc] SoA global P2 dofs (only read when ux != NULL)
+ *   ux, uy   P2 nodal velocity components (NULL = no advection)
+ *   E        [nc][36] row-major element matrices (out)
+ * replaces: FFC tabulate_tensor of the cell integrals in solvers.py:43-44,78,140,207 */
+int sfem_elem_p2_advdiff(int nc, const double* geo, const int* celldofs, double D,
+                         const double* ux, const double* uy, double* E, void* stream);
+/* Same on P1 triangles for the multigrid coarse levels (velocity given at vertices; `upwind`
+ * adds cell-wise artificial diffusion D*max(1,Pe_h) -- preconditioner only, never the solution
+ * operator).  cellverts [3][nc] SoA, E [nc][9]. */
+int sfem_elem_p1_advdiff(int nc, const double* geo, const int* cellverts, double D,
+                         const double* ux, const double* uy, int upwind, double* E, void* stream);
+/* Taylor-Hood element matrices of grad u:grad v - div(v) p - q div(u), cell layout
+ * [ux x6, uy x6, p x3]; E [nc][225].   replaces: tabulate_tensor for solvers.py:291-293 */
+int sfem_elem_th_stokes(int nc, const double* geo, double* E, void* stream);
+/* P1 mass element matrices (pressure Schur-complement preconditioner); E [nc][9]. */
+int sfem_elem_p1_mass(int nc, const double* geo, double* E, void* stream);
+/* Robin boundary mass  mu phi_j phi_i ds  on exterior facets.
+ *   fgeo   [4][nf] SoA xa,ya,xb,yb;  fdofs [ndof][nf] SoA global dofs (P2: va,vb,edge; P1: va,vb)
+ *   mu_nodal  nodal values of mu at the dofs of the space (NULL -> mu_const); P2: the P2
+ *             interpolant of the expression, as dolfin builds it for a degree-2 UserExpression
+ *   clamp  1 = conditional(ge(mu,0),mu,0) at the quadrature points (solvers.py:204)
+ *   F      [nf][9] (P2) or [nf][4] (P1)
+ * replaces: tabulate_tensor of  mu*c*phi*ds(4)  solvers.py:48,79,144,208 */
+int sfem_facet_p2_robin(int nf, const double* fgeo, const int* fdofs, double mu_const,
+                        const double* mu_nodal, int clamp, double* F, void* stream);
+int sfem_facet_p1_robin(int nf, const double* fgeo, const int* fdofs, double mu_const,
+                        const double* mu_nodal, int clamp, double* F, void* stream);
+/* vals[s] = sum_k E[contrib_code[k]], k in [contrib_ptr[s], contrib_ptr[s+1])  -- fixed order, no
+ * atomics.   replaces: dolfin Assembler global scatter-add (MatSetValues ADD_VALUES) */
+int sfem_gather_csr(int nnz, const int* contrib_ptr, const int* contrib_code, const double* E,
+                    double* vals, void* stream);
+/* Dirichlet conditions.  bc_flag[n] (uint8) marks constrained dofs, bc_val[n] their values.
+ *   mode 0: DirichletBC.apply(A,b) as dolfin does it -- identity rows, b_i=g_i, columns untouched
+ *   mode 1: symmetric elimination -- additionally b -= A[:,bc] g and the bc columns are zeroed
+ * replaces: DirichletBC::apply inside solve()  solvers.py:30-31,68-69,127-128,188-189,262-264 */
+int sfem_apply_dirichlet(int n, int nnz, const int* rowptr, const int* cols, double* vals, double* rhs,
+                         const unsigned char* bc_flag, const double* bc_val, int mode, void* stream);
+
+/* ------------------------------------------------------------------ vectors ------------------ */
+int sfem_vec_axpby(int n, double a, const double* x, double b, double* y, void* stream);   /* y = a x + b y */
+int sfem_vec_dot(int n, const double* x, const double* y, double* h_out, void* stream);    /* syncs stream */
+int sfem_vec_set(int n, double a, double* x, void* stream);                                /* x = a */
+int sfem_vec_pointwise_mul(int n, double a, const double* d, const double* x, double* y, void* stream); /* y = a d.*x */
+/* out (n x n row-major) = inverse of a small CSR matrix (coarsest multigrid level, n <= 2048) */
+int sfem_dense_inverse_csr(int n, const int* rowptr, const int* cols, const double* vals, double* out, void* stream);
+int sfem_extract_diag_inv(int n, const int* rowptr, const int* cols, const double* vals, double* dinv, void* stream);
+/* solvers.py:86-105,154-164,216-224: clamp non-finite to 0, then tiny negatives (|min|<1e-12) to 0;
+ * h_stats[6] = {n_nonfinite, n_negative, min, max, mean, clamped(0/1)} (syncs stream) */
+int sfem_postprocess_concentration(int n, double* c, int fix_nonfinite, double* h_stats, void* stream);
+
+/* ------------------------------------------------------------------ multigrid ---------------- */
+typedef struct sfem_mg* sfem_mg_t;
+/* Geometric multigrid V-cycle with Chebyshev-Jacobi smoothing.  Level 0 is the system level.
+ * Per level l: operator CSR (A_*[l]); for l < nlevels-1 the prolongation from level l+1
+ * (P_*[l], n[l] x n[l+1]) and its transpose (R_*[l]).  coarse_inv: dense row-major inverse of the
+ * coarsest operator (n[last]^2).  All arrays are host arrays of device pointers. */
+sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
+                         const int* const* h_A_rowptr, const int* const* h_A_cols, const double* const* h_A_vals,
+                         const int* h_P_nnz,
+                         const int* const* h_P_rowptr, const int* const* h_P_cols, const double* const* h_P_vals,
+                         const int* const* h_R_rowptr, const int* const* h_R_cols, const double* const* h_R_vals,
+                         const double* coarse_inv, int cheb_degree, double eig_ratio);
+/* (re)compute D^-1 and lambda_max(D^-1 A) of every level from the current operator values */
+int sfem_mg_setup(sfem_mg_t mg, void* stream);
+int sfem_mg_vcycle(sfem_mg_t mg, const double* b, double* x, void* stream);   /* x = M^-1 b */
+int sfem_mg_lambda_max(sfem_mg_t mg, double* h_out);                            /* per level, host */
+void sfem_mg_destroy(sfem_mg_t mg);
+
+/* ------------------------------------------------------------------ Krylov ------------------- */
+/* replaces: the sparse LU behind solve(a == L, u, bcs) (dolfin default linear solver).
+ * The operator is CSR; the preconditioner is a multigrid handle (NULL = Jacobi).
+ * h_info[4] = {iterations, final true relative residual ||b-Ax||/||b||, converged(1/0), estimate} */
+int sfem_krylov_cg(int n, int nnz, const int* rowptr, const int* cols, const double* vals, sfem_mg_t mg,
+                   const double* b, double* x, double rtol, int maxit, double* h_info, void* stream);
+int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const double* vals, sfem_mg_t mg,
+                       const double* b, double* x, double rtol, int restart, int maxit,
+                       double* h_info, void* stream);
+/* Taylor-Hood saddle point [ux | uy | p] with n2 velocity dofs per component and nv pressure dofs:
+ * MINRES with the block-diagonal preconditioner diag(MG, MG, Chebyshev(Mp)); mg acts on one
+ * velocity component; Mp_* is the P1 pressure mass matrix. */
+int sfem_krylov_minres_stokes(int n2, int nv, int nnz, const int* rowptr, const int* cols, const double* vals,
+                              sfem_mg_t mg, int Mp_nnz, const int* Mp_rowptr, const int* Mp_cols, const double* Mp_vals,
+                              const double* b, double* x, double rtol, int maxit, double* h_info, void* stream);
+
+/* ------------------------------------------------------------------ functionals -------------- */
+/* Facet functionals of analysis.py, all groups in one launch.
+ *   entries: ne facet entries sorted by group; ent_cell[ne], ent_local[ne] (local facet 0..2 of
+ *   that cell: the cell whose trace and outward normal are used), grp_ptr[ngroups+1]
+ *   out [ngroups][8] = { int -D grad c.n, int (u.n) c, int mu c, int c, int 1,
+ *                        int |q|, int max(q,0), int max(-q,0) },  q = -D grad c.n + (u.n) c
+ * replaces: the ~30 assemble(expr*ds/dS) calls of analysis.py:61-62,212-213,239-247,266-271,311,
+ *           323-325,914,918,930-931 */
+int sfem_facet_functionals(int ngroups, const int* grp_ptr, const int* ent_cell, const int* ent_local,
+                           const double* geo, const int* celldofs, int nc,
+                           const double* c, const double* ux, const double* uy,
+                           double D, double mu_const, const double* mu_nodal,
+                           double* out, void* stream);
+/* Cell functionals: out[m][2] = { int_{cells with marker m} c dx, area }, m < nmarkers.
+ * replaces: assemble(c*dx(i)), assemble(1*dx(i))  analysis.py:688-694,711-712 */
+int sfem_cell_functionals(int nc, const double* geo, const int* celldofs, const int* cell_marker,
+                          int nmarkers, const double* c, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SULCUSFEM_H */

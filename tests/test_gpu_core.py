@@ -1,0 +1,219 @@
+"""GPU parity tests of the device kernels against the CPU oracle (through the C ABI)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from sulcusfem.device import Context
+    return Context.get()
+
+
+@pytest.fixture(scope='module')
+def small():
+    """Small unstructured sulcus mesh + markers + oracle mesh."""
+    from sulcusfem import hostmesh as hm
+    from sulcusfem.unstructured import mesh_domain
+    from oracle import cpu_oracle as co
+    mesh = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.08, 'sulcus')
+    mk = hm.build_markers(mesh, 10.0, 1.0, 4.75, 5.25, 'sulcus')
+    om = co.Mesh(mesh.coords, mesh.cells)
+    return mesh, mk, om
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_spmv_variants(ctx):
+    import torch
+    import scipy.sparse as sp
+    from sulcusfem.device import DeviceCsr
+    rng = np.random.default_rng(0)
+    for n, dens in ((1, 1.0), (37, 0.3), (1000, 0.02), (20011, 0.0006)):
+        A = sp.random(n, n, dens, random_state=1, format='csr') + sp.eye(n, format='csr')
+        A.sort_indices()
+        # an empty row and a long row
+        if n > 100:
+            A = A.tolil(); A[5, :] = 0; A[7, :200] = 1.5; A = A.tocsr(); A.eliminate_zeros(); A.sort_indices()
+        dA = DeviceCsr(ctx, n, n, A.indptr, A.indices, A.data)
+        x = rng.random(n); b = rng.random(n)
+        dx = torch.from_numpy(x).cuda(); db = torch.from_numpy(b).cuda()
+        ref = A @ x
+        for staged in (False, True):
+            y = dA.spmv(dx, staged=staged)
+            assert _rel(y.cpu().numpy(), ref) < 1e-14, (n, staged)
+            r = dA.spmv(dx, b=db, mode=1, staged=staged)
+            assert _rel(r.cpu().numpy(), b - ref) < 1e-13, (n, staged)
+        y2 = torch.from_numpy(b.copy()).cuda()
+        dA.spmv(dx, y=y2, mode=2)
+        assert _rel(y2.cpu().numpy(), b + ref) < 1e-14
+
+
+def test_p2_assembly_matches_oracle(ctx, small):
+    import torch
+    from oracle import cpu_oracle as co
+    from sulcusfem.device import ScalarLevel
+    mesh, mk, om = small
+    bm = mk['bc_markers'].values
+    lev = ScalarLevel(ctx, mesh, bm, 2, (1, 2), 4)
+    # bit-exact pattern vs the oracle's clique pattern
+    ip, ix = co.clique_pattern(om.p2_cell_dofs(), om.n_p2)
+    assert np.array_equal(ip, lev.pattern.rowptr) and np.array_equal(ix, lev.pattern.cols)
+    X = om.p2_dof_coords()
+    ux = 4 * np.clip(X[:, 1], 0, 1) * (1 - np.clip(X[:, 1], 0, 1)) + 0.1 * X[:, 0]
+    uy = 0.3 * np.sin(X[:, 0]) * X[:, 1]
+    f4 = np.flatnonzero((bm == 4) & om.on_boundary)
+    K = co.assemble_p2_stiffness(om)
+    Cm = co.assemble_p2_advection(om, ux, uy)
+    mun = 0.5 + np.cos(3 * X[:, 0])          # changes sign -> exercises the clamp
+    cases = [
+        (dict(D=1.0, mu_const=1.0), 1.0 * K + co.assemble_p2_robin(om, f4, mu_const=1.0)),
+        (dict(D=0.025, ux=ux, uy=uy, mu_const=0.3), 0.025 * K + Cm + co.assemble_p2_robin(om, f4, mu_const=0.3)),
+        (dict(D=0.1, ux=ux, uy=uy, mu_nodal=mun), 0.1 * K + Cm + co.assemble_p2_robin(om, f4, mu_nodal=mun)),
+        (dict(D=1.0, mu_nodal=mun, clamp=True), K + co.assemble_p2_robin(om, f4, mu_nodal=mun, clamp=True)),
+    ]
+    for kw, ref in cases:
+        kw = dict(kw)
+        for k in ('ux', 'uy', 'mu_nodal'):
+            if k in kw:
+                kw[k] = torch.from_numpy(np.ascontiguousarray(kw[k])).cuda()
+        lev.assemble(**kw)
+        got = lev.A.to_scipy()
+        d = abs(got - ref)
+        assert d.max() <= 1e-13 * abs(ref).max(), kw.keys()
+
+
+def test_stokes_assembly_and_dirichlet(ctx, small):
+    import torch
+    from oracle import cpu_oracle as co
+    from sulcusfem.device import StokesProblem
+    from sulcusfem import dofmap as dm
+    mesh, mk, om = small
+    bm = mk['bc_markers'].values
+    sp_ = StokesProblem(mesh, bm, ctx=ctx)
+    ip, ix = co.clique_pattern(om.th_cell_dofs(), 2 * om.n_p2 + om.nv)
+    assert np.array_equal(ip, sp_.pattern.rowptr) and np.array_equal(ix, sp_.pattern.cols)
+    X = dm.p2_dof_coordinates(mesh)
+    d1 = dm.dirichlet_dofs_p2(mesh, bm, 1)
+    zeros = lambda i: (0.0, 0.0)
+    sp_.set_bcs({1: (4 * X[d1, 1] * (1 - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+    sp_.assemble(bc_mode=0)
+    A0 = co.assemble_stokes(om)
+    dofs, vals = co.stokes_bcs(om, bm, 1.0)
+    assert np.array_equal(np.flatnonzero(sp_.bc_flag_host), dofs)
+    Aref, bref = co.apply_dirichlet_rows(A0, np.zeros(A0.shape[0]), dofs, vals)
+    got = sp_.A.to_scipy()
+    assert abs(got - Aref).max() <= 1e-13 * abs(Aref).max()
+    assert np.abs(sp_.rhs.cpu().numpy() - bref).max() < 1e-15
+
+
+def test_dense_inverse(ctx):
+    import torch
+    import scipy.sparse as sp
+    from sulcusfem import capi
+    from sulcusfem.device import DeviceCsr, P
+    n = 150
+    A = (sp.random(n, n, 0.05, random_state=3) + sp.eye(n) * 3).tocsr()
+    A.sort_indices()
+    dA = DeviceCsr(ctx, n, n, A.indptr, A.indices, A.data)
+    out = ctx.zeros(n * n)
+    capi.check(ctx.lib.sfem_dense_inverse_csr(n, P(dA.rowptr), P(dA.cols), P(dA.vals), P(out), ctx.stream))
+    inv = out.cpu().numpy().reshape(n, n)
+    assert np.abs(inv @ A.toarray() - np.eye(n)).max() < 1e-11
+
+
+def test_diffusion_solve_matches_lu(ctx, small):
+    from oracle import cpu_oracle as co
+    from sulcusfem.device import ScalarProblem
+    mesh, mk, om = small
+    bm = mk['bc_markers'].values
+    prob = ScalarProblem(mesh, bm, ctx=ctx)
+    for mu in (0.1, 1.0, 10.0):
+        prob.assemble(1.0, mu_const=mu, bc_values={1: 1.0, 2: 0.0})
+        c = prob.solve('cg', rtol=1e-13).cpu().numpy()
+        ref, _, _ = co.solve_concentration(om, bm, 1.0, mu=mu)
+        print('cg', mu, prob.last_info, prob.mg.lambda_max())
+        assert prob.last_info['converged']
+        assert prob.last_info['iterations'] < 60
+        assert _rel(c, ref) < 1e-10      # north_star: fields within 1e-10 relative L2
+
+
+def test_advdiff_solve_matches_lu(ctx, small):
+    import torch
+    from oracle import cpu_oracle as co
+    from sulcusfem.device import ScalarProblem
+    mesh, mk, om = small
+    bm = mk['bc_markers'].values
+    X = om.p2_dof_coords()
+    y = np.clip(X[:, 1], 0, 1)
+    ux, uy = 4 * y * (1 - y), np.zeros(len(y))
+    prob = ScalarProblem(mesh, bm, ctx=ctx)
+    dux, duy = torch.from_numpy(ux).cuda(), torch.from_numpy(uy).cuda()
+    for D in (0.025, 1.0):
+        prob.assemble(D, dux, duy, mu_const=1.0, bc_values={1: 1.0, 2: 0.0})
+        c = prob.solve('fgmres', rtol=1e-13).cpu().numpy()
+        ref, _, _ = co.solve_concentration(om, bm, D, mu=1.0, ux=ux, uy=uy)
+        print('fgmres', D, prob.last_info)
+        assert prob.last_info['converged']
+        assert _rel(c, ref) < 1e-10
+
+
+def test_stokes_solve_matches_lu(ctx, small):
+    from oracle import cpu_oracle as co
+    from sulcusfem.device import StokesProblem
+    from sulcusfem import dofmap as dm
+    mesh, mk, om = small
+    bm = mk['bc_markers'].values
+    sp_ = StokesProblem(mesh, bm, ctx=ctx)
+    X = dm.p2_dof_coordinates(mesh)
+    d1 = dm.dirichlet_dofs_p2(mesh, bm, 1)
+    sp_.set_bcs({1: (4 * X[d1, 1] * (1 - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+    sp_.assemble(bc_mode=1)
+    ux, uy, p = [t.cpu().numpy() for t in sp_.solve(rtol=1e-14)]
+    rx, ry, rp, _, _ = co.solve_stokes(om, bm, 1.0)
+    print('minres', sp_.last_info)
+    un = np.linalg.norm(np.concatenate([rx, ry]))
+    assert np.linalg.norm(np.concatenate([ux - rx, uy - ry])) / un < 1e-10
+    assert _rel(p, rp) < 1e-9
+
+
+def test_functionals_match_oracle(ctx, small):
+    import torch
+    from oracle import cpu_oracle as co
+    from sulcusfem.device import FunctionalPlan
+    mesh, mk, om = small
+    rng = np.random.default_rng(1)
+    X = om.p2_dof_coords()
+    c = 1.0 - X[:, 0] / 10 + 0.1 * np.sin(5 * X[:, 0]) * np.cos(3 * X[:, 1])
+    ux = 4 * np.clip(X[:, 1], 0, 1) * (1 - np.clip(X[:, 1], 0, 1))
+    uy = 0.2 * np.sin(X[:, 0] * 7) * (X[:, 1] - 0.3)
+    D, mu = 0.025, 0.7
+    omk = {k: v.values for k, v in mk.items()}
+    ref = co.flux_metrics(om, omk, 'sulcus', D, c, ux, uy, mu=mu)
+    refm = co.mass_metrics(om, c, 'sulcus', omk['domain_markers'])
+    plan = FunctionalPlan(mesh, mk, 'sulcus', ctx=ctx)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    F, Cc = plan.evaluate(t(c), t(ux), t(uy), D=D, mu_const=mu)
+    names = plan.GROUPS
+
+    def close(a, b, tol=1e-11):
+        assert abs(a - b) <= tol * max(1.0, abs(b)), (a, b)
+    for i, nm in enumerate(names[:4]):
+        close(F[i, 0], ref['physical_flux'][nm]['diffusive'])
+        close(F[i, 1], ref['physical_flux'][nm]['advective'])
+    close(F[3, 2], ref['uptake_flux'])
+    seg = ref['sulcus_specific']['physical_flux']
+    for i, nm in ((4, 'bottom_left'), (5, 'sulcus'), (6, 'bottom_right')):
+        close(F[i, 0], seg[nm]['diffusive'])
+        close(F[i, 1], seg[nm]['advective'])
+        close(F[i, 2], ref['sulcus_specific']['uptake_flux'][nm])
+    close(F[8, 0], seg['sulcus_opening']['diffusive'])
+    close(F[8, 1], seg['sulcus_opening']['advective'])
+    ex = seg['sulcus_opening_extra']
+    close(F[8, 5], ex['E_L1']); close(F[8, 6], ex['Q_in']); close(F[8, 7], ex['Q_out']); close(F[8, 4], ex['length'])
+    close(F[7, 3], ref['_conc']['C_y0_ext']); close(F[8, 3], ref['_conc']['C_mouth'])
+    close(Cc[1, 0], refm['sulcus_mass']); close(Cc[2, 0], refm['rectangle_mass'])
+    close(Cc[1, 1], refm['sulcus_area']); close(Cc[2, 1], refm['rectangle_area'])
