@@ -91,10 +91,10 @@ def build_pattern(nrows: int, ncols: int,
                   families: Sequence[Tuple[np.ndarray, np.ndarray]]) -> CsrPattern:
     """CSR pattern + gather map for a list of element families.
 
-    ``families[f] = (row_dofs [n_f, a_f], col_dofs [n_f, b_f])``.  The element buffer is SoA per
+    ``families[f] = (row_dofs [n_f, a_f], col_dofs [n_f, b_f])``.  The element buffer is AoS per
     family: entry (unit u, local i, local j) of family f lives at
-    ``family_base[f] + (i*b_f + j)*n_f + u`` so that consecutive units are contiguous (coalesced
-    element-kernel writes).
+    ``family_base[f] + u*a_f*b_f + i*b_f + j`` (one row-major element matrix per unit), so the
+    gather kernel finds the entries of one matrix row of one cell inside one short span.
     """
     key_parts, code_parts, bases = [], [], []
     base = 0
@@ -106,7 +106,7 @@ def build_pattern(nrows: int, ncols: int,
         bases.append(base)
         if n:
             keys = (rows[:, :, None] * ncols + cols[:, None, :]).reshape(n, a * b)
-            codes = base + np.arange(a * b, dtype=np.int64)[None, :] * n + np.arange(n, dtype=np.int64)[:, None]
+            codes = base + np.arange(n, dtype=np.int64)[:, None] * (a * b) + np.arange(a * b, dtype=np.int64)[None, :]
             key_parts.append(keys.ravel())
             code_parts.append(codes.ravel())
         base += n * a * b
