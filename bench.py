@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the sulcus FEM hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--refine R] [--h H] [--impl reference]
+
+One *step* = one full advection-diffusion sulcus run (BASELINE.json configs[1]): Taylor-Hood Stokes
+assembly + MINRES solve, P2 advection-diffusion assembly (Pe = 40, Robin mu = 1) + FGMRES solve, and
+all flux / mass functionals, on a synthetic sulcus mesh (w = 0.5, d = 1.0, h = 0.02, R uniform
+refinements).  Metric: DOFs/s = (Taylor-Hood dofs + P2 dofs) solved per second, whole job.
+N > 1: every rank solves its own independent sweep case (no data-path collective) -> weak scaling.
+
+`value`    device-resident inputs, CUDA-event timed per step, L2 flushed between steps.
+`e2e`      the same run through the reference-facing API (sulcusfem.solvers / analysis) with host
+           inputs and host results, wall clock around each call (H2D / D2H inside).
+`roofline` dominant kernel family, from a per-launch CUDA-event profile of one extra step.
+`cpu_baseline` the CPU oracle (numpy assembly + SuperLU) on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'fenics-eff-uptake_b200'))
+
+import numpy as np  # noqa: E402
+
+W_SULCUS, D_SULCUS, L_CH, H_CH = 0.5, 1.0, 10.0, 1.0
+PE, MU = 40.0, 1.0
+CAT_NAMES = ['spmv', 'spmv_dot', 'cheb_step', 'resid_d0', 'elem', 'gather', 'vec', 'other', 'spmv_staged']
+
+
+def build_mesh(h, refine):
+    from sulcusfem import hostmesh as hm
+    from sulcusfem.unstructured import mesh_domain
+    mesh = mesh_domain(L_CH, H_CH, W_SULCUS, D_SULCUS, h, 'sulcus')
+    mesh = hm.refine_n(mesh, refine)
+    mk = hm.build_markers(mesh, L_CH, H_CH, L_CH / 2 - W_SULCUS / 2, L_CH / 2 + W_SULCUS / 2, 'sulcus')
+    res = {'mesh': mesh, 'mesh_info': {}}
+    res.update(mk)
+    return res
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def oracle_step(h, mu=MU):
+    """One step of the same workload on the CPU oracle (numpy assembly + SuperLU), timed."""
+    from oracle import cpu_oracle as co
+    mr = build_mesh(h, 0)
+    mesh = mr['mesh']
+    om = co.Mesh(mesh.coords, mesh.cells)
+    bm = mr['bc_markers'].values
+    mk = {k: mr[k].values for k in ('bc_markers', 'bottom_segment_markers', 'y0_markers', 'domain_markers')}
+    t0 = time.perf_counter()
+    ux, uy, p, _, _ = co.solve_stokes(om, bm, H_CH)
+    c, _, _ = co.solve_concentration(om, bm, 1.0 / PE, mu=mu, ux=ux, uy=uy)
+    fl = co.flux_metrics(om, mk, 'sulcus', 1.0 / PE, c, ux, uy, mu=mu)
+    co.mass_metrics(om, c, 'sulcus', mk['domain_markers'])
+    dt = time.perf_counter() - t0
+    ndof = 2 * om.n_p2 + om.nv + om.n_p2
+    return dt, ndof, fl
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    hs = args.cpu_h
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        oracle_step(hs)
+    times, ndof = [], 0
+    for _ in range(args.steps):
+        dt, ndof, _ = oracle_step(hs)
+        times.append(dt)
+    val = ndof * len(times) / sum(times)
+    sample = (f"same adv-diff sulcus step (Stokes + adv-diff + functionals) on the h={hs} mesh, {ndof} dofs, "
+              f"numpy assembly + scipy SuperLU, 1 thread")
+    line = {
+        "impl": "reference", "metric": "fem_dofs_per_s", "value": val, "unit": "DOFs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": "DOFs/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "DOFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "dolfin/PETSc is not installable in this image; the CPU arm is the oracle port of the reference path",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"adv-diff sulcus (BASELINE configs[1]): Stokes TH + adv-diff P2 + functionals, "
+                        f"w={W_SULCUS} d={D_SULCUS} Pe={PE:g} mu={MU:g}, synthetic Delaunay mesh h={args.h} "
+                        f"+ {args.refine} uniform refinements",
+            "h": args.h, "refine": args.refine, "l2": "flushed between steps (512 MiB memset)",
+            "krylov_rtol": 1e-13, "parallelism": f"case-sharded x{args.gpus} (no collectives)"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, rank, world):
+    import torch
+    import ctypes as C
+    from sulcusfem import capi, dofmap as dm
+    from sulcusfem.device import Context, FunctionalPlan, ScalarProblem, StokesProblem
+    from sulcusfem.hierarchy import build_hierarchy
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+    ctx = Context.get()
+    lib = ctx.lib
+    mu = MU + 0.05 * rank                      # every rank: its own sweep case
+    t_setup = time.perf_counter()
+    mr = build_mesh(args.h, args.refine)
+    mesh, bm = mr['mesh'], mr['bc_markers'].values
+    hier = build_hierarchy(mesh)
+    stokes = StokesProblem(mesh, bm, hierarchy=hier, ctx=ctx)
+    scalar = ScalarProblem(mesh, bm, hierarchy=hier, ctx=ctx)
+    plan = FunctionalPlan(mesh, mr, 'sulcus', ctx=ctx)
+    # the reference-facing API (e2e leg) finds the same device objects through the per-mesh cache
+    mesh._sfem_cache = {'hierarchy': hier, 'stokes': stokes, ('scalar', 4): scalar, ('functionals', 'sulcus'): plan}
+    X = dm.p2_dof_coordinates(mesh)
+    d1 = dm.dirichlet_dofs_p2(mesh, bm, 1)
+    stokes.set_bcs({1: (4.0 * X[d1, 1] * (H_CH - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    ndof = stokes.n + scalar.n
+    D = 1.0 / PE
+    info = {}
+
+    def step():
+        stokes.assemble(bc_mode=1)
+        ux, uy, p = stokes.solve(rtol=1e-14)
+        scalar.assemble(D, ux, uy, mu_const=mu, bc_values={1: 1.0, 2: 0.0})
+        c = scalar.solve('fgmres', rtol=1e-13)
+        F, M = plan.evaluate(c, ux, uy, D=D, mu_const=mu)
+        info['stokes'], info['advdiff'] = dict(stokes.last_info), dict(scalar.last_info)
+        return F, M
+
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.sfem_launch_count_reset()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record()
+        F, M = step()
+        e1.record()
+    barrier()
+    launches = int(lib.sfem_launch_count())
+    clocks = sampler.stop() if sampler else None
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=ctx.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+
+    # ---- e2e through the reference-facing API (host in, host out)
+    from sulcusfem import solvers, analysis
+    from sulcusfem.fem import Constant, FunctionSpace, MixedElement, VectorFunctionSpace
+    from sulcusfem.parameters import Parameters
+    V = VectorFunctionSpace(mesh, "P", 2)
+    Q = FunctionSpace(mesh, "P", 1)
+    Wsp = FunctionSpace(mesh, MixedElement([V.ufl_element(), Q.ufl_element()]))
+    Csp = FunctionSpace(mesh, "CG", 2)
+    import contextlib
+    import io
+
+    def api_step():
+        with contextlib.redirect_stdout(io.StringIO()):
+            u, p = solvers.stokes_solver(mr, Wsp, L_CH, H_CH, 'sulcus')
+            u._dev = None                                  # velocity re-enters from its host array (H2D)
+            c = solvers.advdiff_solver(mr, u, Csp, Constant(D), Constant(mu), 'sulcus')
+            c._dev = None
+            fm = analysis.compute_flux_metrics(c, u, mr, 'sulcus', {}, D, mu)
+            mm = analysis.compute_mass_metrics(c, {}, 'sulcus')
+        return fm, mm
+    api_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
+        flush.zero_()
+        fm, mm = api_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=ctx.device)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    n2, nv = stokes.n2, stokes.nv
+    h2d = 8 * (2 * n2) + 8 * n2          # velocity components + concentration re-uploaded for the functionals
+    d2h = 8 * (2 * n2 + nv) + 8 * n2 + 8 * (plan.ngroups * 8 + plan.nmarkers * 2)
+
+    if rank != 0:
+        return
+    # ---- per-launch profile of one extra step (roofline of the dominant kernel family)
+    cap = 400000
+    lib.sfem_profile_start(cap)
+    step()
+    cats, byts, mss = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)()
+    n = lib.sfem_profile_stop(cap, cats, byts, mss)
+    cats, byts, mss = np.array(cats[:n]), np.array(byts[:n]), np.array(mss[:n], dtype=np.float64)
+    per_cat = {}
+    for k, name in enumerate(CAT_NAMES):
+        sel = cats == k
+        if sel.any():
+            per_cat[name] = {"launches": int(sel.sum()), "ms": float(mss[sel].sum()), "gbytes": float(byts[sel].sum() / 1e9)}
+    spmv_family = np.isin(cats, [0, 1, 2, 3, 8])
+    big = spmv_family & (byts >= 0.5 * byts[spmv_family].max())
+    ach = float(byts[big].sum() / 1e9 / (mss[big].sum() / 1e3))
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "FP64 CSR SpMV family on the system-level matrices (k_spmv / k_spmv_dot / k_cheb_step / k_resid_d0)",
+                "launches": int(big.sum()), "avg_launch_ms": float(mss[big].mean()),
+                "algorithmic_bytes_per_launch": float(byts[big].mean()),
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if 'hbm_gbs' in peaks else "fallback 6650 GB/s",
+                "share_of_profiled_step": float(mss[big].sum() / mss.sum()),
+                "by_category": per_cat, "profiled_step_kernel_ms": float(mss.sum())}
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 only
+    cpu = None
+    if not args.no_cpu:
+        dt, nd, _ = oracle_step(args.cpu_h)
+        cpu = {"value": nd / dt, "unit": "DOFs/s", "cores": 1, "kind": "port",
+               "sample": f"one step of the same workload on the h={args.cpu_h} mesh ({nd} dofs): numpy assembly + SuperLU, {dt:.1f} s",
+               "host_cores": os.cpu_count()}
+
+    value = world * ndof * args.steps / (ms_total / 1e3)
+    line = {
+        "metric": "fem_dofs_per_s", "value": value, "unit": "DOFs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "solves_per_s": world * args.steps / (ms_total / 1e3), "dofs_per_case": ndof,
+        "dofs": {"taylor_hood": stokes.n, "p2": scalar.n, "cells": int(mesh.num_cells)},
+        "iterations": {"stokes_minres": info['stokes']['iterations'], "advdiff_fgmres": info['advdiff']['iterations'],
+                       "stokes_relres": info['stokes']['relres'], "advdiff_relres": info['advdiff']['relres']},
+        "e2e": {"value": world * ndof / e2e_s, "unit": "DOFs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s, "api": "sulcusfem.solvers.stokes_solver + advdiff_solver + analysis.compute_*_metrics"},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "setup_s": t_setup,
+        "functionals": {"uptake_flux": fm['uptake_flux'], "total_mass": mm['total_mass']},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--h', type=float, default=0.02)
+    ap.add_argument('--refine', type=int, default=int(os.environ.get('SFEM_BENCH_REFINE', 1)))
+    ap.add_argument('--cpu-h', type=float, default=0.04)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    run_gpu(args, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -312,6 +312,7 @@ int sfem_elem_p2_advdiff(int nc, const double* geo, const int* celldofs, double 
   if (nc <= 0) return SFEM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(nc, 128, 16);
+  Prof prof(PC_ELEM, (double)nc * (48.0 + 288.0 + ((ux && uy) ? 24.0 + 96.0 : 0.0)), st);
   if (ux != nullptr && uy != nullptr) {
     if (celldofs == nullptr) { set_error("celldofs required with a velocity field"); return SFEM_ERR_ARG; }
     k_elem_p2<true><<<grid, 128, 0, st>>>(nc, geo, celldofs, D, ux, uy, E);
@@ -333,6 +334,7 @@ int sfem_elem_p1_advdiff(int nc, const double* geo, const int* cellverts, double
 
 int sfem_elem_th_stokes(int nc, const double* geo, double* E, void* stream) {
   if (nc <= 0) return SFEM_OK;
+  Prof prof(PC_ELEM, (double)nc * (48.0 + 1800.0), (cudaStream_t)stream);
   k_elem_th<<<grid_for(nc, 128, 16), 128, 0, (cudaStream_t)stream>>>(nc, geo, E);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
@@ -364,6 +366,7 @@ int sfem_facet_p1_robin(int nf, const double* fgeo, const int* fdofs, double mu_
 int sfem_gather_csr(int nnz, const int* contrib_ptr, const int* contrib_code, const double* E, double* vals,
                     void* stream) {
   if (nnz <= 0) return SFEM_OK;
+  Prof prof(PC_GATHER, (double)nnz * 12.0, (cudaStream_t)stream);   // + 12 B per contribution, unknown here
   k_gather<<<grid_for(nnz, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(nnz, contrib_ptr, contrib_code, E, vals);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;

@@ -14,6 +14,20 @@ void set_error(const std::string& msg);
 int num_sms();
 extern std::atomic<long long> g_launches;
 
+// Optional per-launch timing (bench.py roofline): when enabled every instrumented launch is
+// bracketed by a CUDA event pair on its stream; sfem_profile_stop() returns (category, algorithmic
+// bytes, milliseconds) per launch.  Disabled -> a single relaxed load per launch.
+enum ProfCat {
+  PC_SPMV = 0, PC_SPMV_DOT = 1, PC_CHEB = 2, PC_RESID_D0 = 3, PC_ELEM = 4, PC_GATHER = 5, PC_VEC = 6,
+  PC_OTHER = 7, PC_SPMV_STAGED = 8
+};
+struct Prof {
+  Prof(int cat, double bytes, cudaStream_t st);
+  ~Prof();
+  int idx;
+  cudaStream_t st;
+};
+
 #define SFEM_CUDA(call)                                                                   \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \

@@ -306,7 +306,8 @@ int sfem_krylov_cg(int n, int nnz, const int* rowptr, const int* cols, const dou
       k_cg_alpha<<<1, kThreads, 0, st>>>(part0, npq, S);
       SFEM_LAUNCH_CHECK();
       nrr = grid_for(n, kThreads * 4, 4);
-      k_cg_update<<<nrr, kThreads, 0, st>>>(n, S, p, q, x, r, part1);
+      { Prof prof(PC_VEC, 48.0 * n, st);
+      k_cg_update<<<nrr, kThreads, 0, st>>>(n, S, p, q, x, r, part1); }
       SFEM_LAUNCH_CHECK();
       SFEM_TRY(precond_apply(mg, dinv, n, r, z, st));
       SFEM_TRY(vec_dot_partial(n, r, z, part0, &nrz, st));
@@ -383,12 +384,14 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
       int nww = 0;
       for (int pass = 0; pass < 2; ++pass) {             // classical Gram-Schmidt, twice
         dim3 grid(gx, nvec);
-        k_multidot<<<grid, kThreads, 0, st>>>(n, V, nvec, w, partial, gx);
+        { Prof prof(PC_VEC, 8.0 * n * (nvec + 1), st);
+        k_multidot<<<grid, kThreads, 0, st>>>(n, V, nvec, w, partial, gx); }
         SFEM_LAUNCH_CHECK();
         k_gs_coeff<<<nvec, kThreads, 0, st>>>(partial, gx, hcol, hstep, pass);
         SFEM_LAUNCH_CHECK();
         nww = grid_for(n, kThreads * 4, 4);
-        k_gs_update<<<nww, kThreads, nvec * sizeof(double), st>>>(n, V, nvec, hstep, w, part1);
+        { Prof prof(PC_VEC, 8.0 * n * (nvec + 2), st);
+        k_gs_update<<<nww, kThreads, nvec * sizeof(double), st>>>(n, V, nvec, hstep, w, part1); }
         SFEM_LAUNCH_CHECK();
       }
       k_gmres_givens<<<1, kThreads, 0, st>>>(part1, nww, j, m, H, cs, sn, g, misc);
@@ -468,12 +471,14 @@ int sfem_krylov_minres_stokes(int n2, int nv, int nnz, const int* rowptr, const 
   if (gamma1 > 0.0) {
     const int gv = grid_for(n, kThreads * 4);
     for (it = 1; it <= maxit; ++it) {
-      k_minres_scale<<<gv, kThreads, 0, st>>>(n, S, z);
+      { Prof prof(PC_VEC, 16.0 * n, st);
+      k_minres_scale<<<gv, kThreads, 0, st>>>(n, S, z); }
       SFEM_LAUNCH_CHECK();
       SFEM_TRY(spmv_dot(A, z, Az, part, &np, st));
       k_minres_delta<<<1, kThreads, 0, st>>>(part, np, S);
       SFEM_LAUNCH_CHECK();
-      k_minres_vnext<<<gv, kThreads, 0, st>>>(n, S, Az, v, v_prev);
+      { Prof prof(PC_VEC, 32.0 * n, st);
+      k_minres_vnext<<<gv, kThreads, 0, st>>>(n, S, Az, v, v_prev); }
       SFEM_LAUNCH_CHECK();
       { double* t = v; v = v_prev; v_prev = t; }          // v now holds v_{j+1}, v_prev holds v_j
       // z_j is still needed for w_{j+1}: keep it in Az's place after the precond writes z_next
@@ -482,7 +487,8 @@ int sfem_krylov_minres_stokes(int n2, int nv, int nnz, const int* rowptr, const 
       SFEM_TRY(vec_dot_partial(n, z, v, part, &np, st));
       k_minres_rot<<<1, kThreads, 0, st>>>(part, np, S);
       SFEM_LAUNCH_CHECK();
-      k_minres_wx<<<gv, kThreads, 0, st>>>(n, S, Az, w, w_prev, x);
+      { Prof prof(PC_VEC, 48.0 * n, st);
+      k_minres_wx<<<gv, kThreads, 0, st>>>(n, S, Az, w, w_prev, x); }
       SFEM_LAUNCH_CHECK();
       { double* t = w; w = w_prev; w_prev = t; }
       SFEM_TRY(read_double(S + 4, &eta, st));

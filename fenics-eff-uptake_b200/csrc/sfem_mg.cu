@@ -10,6 +10,8 @@
 #include "sfem_mg.h"
 
 #include <cmath>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 namespace sfem {
@@ -33,7 +35,43 @@ __global__ void k_fill_pseudo(int n, double* __restrict__ v) {
   }
 }
 
+// per-block max of sum_j |a_ij| * |dinv_i|  (Gershgorin bound on the spectrum of D^-1 A)
+__global__ void __launch_bounds__(kThreads) k_gershgorin(int n, const int* __restrict__ rowptr,
+                                                         const double* __restrict__ vals, const double* __restrict__ dinv,
+                                                         double* __restrict__ partial) {
+  __shared__ double sh[32];
+  double mx = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) s += fabs(vals[k]);
+    mx = fmax(mx, s * fabs(dinv[i]));
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmax(mx, sh[w]);
+    partial[blockIdx.x] = mx;
+  }
+}
+
 }  // namespace
+
+// Guaranteed upper bound of lambda_max(D^-1 A): keeps the Chebyshev smoother (and with it the
+// V-cycle) positive definite, which MINRES / CG rely on.  A power-iteration estimate can fall short
+// of the true value and then the polynomial amplifies the top of the spectrum.
+int gershgorin_lambda_max(const Csr& A, const double* dinv, double* scratch, double* out, cudaStream_t st) {
+  const int grid = grid_for(A.nrows, kThreads, 4);
+  k_gershgorin<<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.vals, dinv, scratch);
+  SFEM_LAUNCH_CHECK();
+  std::vector<double> h(grid);
+  SFEM_CUDA(cudaMemcpyAsync(h.data(), scratch, grid * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  double mx = 0.0;
+  for (double v : h) mx = v > mx ? v : mx;
+  *out = mx;
+  return SFEM_OK;
+}
 
 int smooth(const Csr& A, const double* dinv, double lmax, double ratio, int degree, const double* b, double* x,
            double* r, double* d0, double* d1, bool zero_init, cudaStream_t st) {
@@ -118,6 +156,10 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
   mg->degree = cheb_degree;
   mg->ratio = eig_ratio;
   mg->coarse_inv = coarse_inv;
+  {
+    const char* e = std::getenv("SFEM_LMAX");
+    mg->use_power_iteration = (e != nullptr && std::string(e) == "power");
+  }
   mg->levels.resize(nlevels);
   int nmax = 0;
   for (int l = 0; l < nlevels; ++l) {
@@ -159,7 +201,10 @@ int sfem_mg_setup(sfem_mg_t mg, void* stream) {
     MgLevel& L = mg->levels[l];
     SFEM_TRY(extract_diag_inv(L.A, L.dinv, st));
     if (l + 1 == mg->levels.size() && mg->coarse_inv != nullptr) { L.lmax = 2.0; continue; }
-    SFEM_TRY(estimate_lambda_max(L.A, L.dinv, L.d0, L.d1, mg->scratch, &L.lmax, st));
+    if (mg->use_power_iteration)
+      SFEM_TRY(estimate_lambda_max(L.A, L.dinv, L.d0, L.d1, mg->scratch, &L.lmax, st));
+    else
+      SFEM_TRY(gershgorin_lambda_max(L.A, L.dinv, mg->scratch, &L.lmax, st));
   }
   mg->ready = true;
   return SFEM_OK;

@@ -27,6 +27,7 @@ struct sfem_mg {
   double ratio = 8.0;
   double* scratch = nullptr;
   bool ready = false;
+  bool use_power_iteration = false;   // SFEM_LMAX=power: estimate instead of the Gershgorin bound
 };
 
 namespace sfem {

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_d0(int nrows, const int* __r
 template <int LANES>
 static int launch_spmv_lanes(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st) {
   const int grid = grid_for(A.nrows, kThreads / LANES);
+  Prof prof(PC_SPMV, 12.0 * A.nnz + 4.0 * A.nrows + 8.0 * A.ncols + 8.0 * A.nrows * (mode == 0 ? 1 : 2), st);
   if (mode == 0) k_spmv<LANES, 0><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, b, y);
   else if (mode == 1) k_spmv<LANES, 1><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, b, y);
   else k_spmv<LANES, 2><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, b, y);
@@ -138,6 +139,7 @@ int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cu
 int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* nparts, cudaStream_t st) {
   const int lanes = pick_lanes(A.nnz, A.nrows);
   int grid = 1;
+  Prof prof(PC_SPMV_DOT, 12.0 * A.nnz + 20.0 * A.nrows, st);
   SFEM_DISPATCH_LANES(lanes, {
     grid = grid_for(A.nrows, kThreads / LN);
     k_spmv_dot<LN><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, y, partial);
@@ -150,6 +152,7 @@ int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* npa
 int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
               double c1, double c2, int last, cudaStream_t st) {
   const int lanes = pick_lanes(A.nnz, A.nrows);
+  Prof prof(PC_CHEB, 12.0 * A.nnz + 60.0 * A.nrows, st);
   SFEM_DISPATCH_LANES(lanes, {
     const int grid = grid_for(A.nrows, kThreads / LN);
     k_cheb_step<LN><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, d_old, d_new, r, x, c1, c2, last);
@@ -161,6 +164,7 @@ int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_n
 int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
              double c0, cudaStream_t st) {
   const int lanes = pick_lanes(A.nnz, A.nrows);
+  Prof prof(PC_RESID_D0, 12.0 * A.nnz + 44.0 * A.nrows, st);
   SFEM_DISPATCH_LANES(lanes, {
     const int grid = grid_for(A.nrows, kThreads / LN);
     k_resid_d0<LN><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, b, x, r, d, c0);

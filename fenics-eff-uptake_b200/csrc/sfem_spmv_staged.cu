@@ -187,6 +187,7 @@ int spmv_staged_plan(const Csr& A, int tile_rows, int tile_cap, int stages, cons
   int grid = num_sms() * per_sm;
   if (grid > ntiles) grid = ntiles;
 
+  Prof prof(PC_SPMV_STAGED, 12.0 * A.nnz + 4.0 * A.nrows + 8.0 * A.ncols + 8.0 * A.nrows * (mode == 0 ? 1 : 2), st);
 #define SFEM_STAGED_LAUNCH(LN, MD)                                                                      \
   do {                                                                                                   \
     auto kern = k_spmv_staged<LN, MD>;                                                                   \

@@ -28,6 +28,27 @@ int num_sms() {
   return sms;
 }
 
+// ------------------------------------------------------------------ per-launch profiler
+namespace {
+struct ProfRec { int cat; double bytes; cudaEvent_t e0, e1; };
+std::atomic<bool> g_prof_on{false};
+std::vector<ProfRec> g_prof;
+size_t g_prof_max = 0;
+}  // namespace
+
+Prof::Prof(int cat, double bytes, cudaStream_t s) : idx(-1), st(s) {
+  if (!g_prof_on.load(std::memory_order_relaxed) || g_prof.size() >= g_prof_max) return;
+  ProfRec r;
+  r.cat = cat; r.bytes = bytes;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  idx = (int)g_prof.size() - 1;
+}
+Prof::~Prof() {
+  if (idx >= 0) cudaEventRecord(g_prof[idx].e1, st);
+}
+
 // ------------------------------------------------------------------ kernels
 __global__ void k_set(int n, double a, double* __restrict__ x) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = a;
@@ -132,12 +153,14 @@ int vec_set(int n, double a, double* x, cudaStream_t st) {
 
 int vec_copy(int n, const double* x, double* y, cudaStream_t st) {
   if (n <= 0) return SFEM_OK;
+  Prof prof(PC_VEC, 16.0 * n, st);
   SFEM_CUDA(cudaMemcpyAsync(y, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   return SFEM_OK;
 }
 
 int vec_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st) {
   if (n <= 0) return SFEM_OK;
+  Prof prof(PC_VEC, 8.0 * n * (b == 0.0 ? 2 : 3), st);
   k_axpby<<<grid_for(n, kThreads * 4), kThreads, 0, st>>>(n, a, x, b, y);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
@@ -145,6 +168,7 @@ int vec_axpby(int n, double a, const double* x, double b, double* y, cudaStream_
 
 int vec_mul_scale(int n, double a, const double* d, const double* x, double* y, cudaStream_t st) {
   if (n <= 0) return SFEM_OK;
+  Prof prof(PC_VEC, 24.0 * n, st);
   k_mul_scale<<<grid_for(n, kThreads * 4), kThreads, 0, st>>>(n, a, d, x, y);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
@@ -152,6 +176,7 @@ int vec_mul_scale(int n, double a, const double* d, const double* x, double* y, 
 
 int vec_dot_partial(int n, const double* x, const double* y, double* partial, int* nparts, cudaStream_t st) {
   const int grid = grid_for(n, kThreads * 4, 4);
+  Prof prof(PC_VEC, 16.0 * n, st);
   k_dot_partial<<<grid, kThreads, 0, st>>>(n, x, y, partial);
   SFEM_LAUNCH_CHECK();
   *nparts = grid;
@@ -178,6 +203,7 @@ int extract_diag_inv(const Csr& A, double* dinv, cudaStream_t st) {
 
 int dense_gemv(int n, const double* M, const double* x, double* y, cudaStream_t st) {
   if (n <= 0) return SFEM_OK;
+  Prof prof(PC_OTHER, 8.0 * n * n + 16.0 * n, st);
   k_dense_gemv<<<grid_for(n, kThreads / 32), kThreads, 0, st>>>(n, M, x, y);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
@@ -195,6 +221,33 @@ int sfem_version(void) { return 100; }
 int sfem_device_sms(void) { return num_sms(); }
 long long sfem_launch_count(void) { return g_launches.load(); }
 void sfem_launch_count_reset(void) { g_launches.store(0); }
+
+int sfem_profile_start(int max_records) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_max = max_records > 0 ? (size_t)max_records : 0;
+  g_prof.reserve(g_prof_max);
+  g_prof_on.store(true);
+  return SFEM_OK;
+}
+
+/* Stops profiling, synchronises the device and copies up to `cap` records out; returns the count. */
+int sfem_profile_stop(int cap, int* h_cat, double* h_bytes, float* h_ms) {
+  g_prof_on.store(false);
+  SFEM_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (n < cap) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) ms = -1.f;
+      h_cat[n] = r.cat; h_bytes[n] = r.bytes; h_ms[n] = ms;
+      ++n;
+    }
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return n;
+}
 
 int sfem_vec_axpby(int n, double a, const double* x, double b, double* y, void* stream) {
   return vec_axpby(n, a, x, b, y, (cudaStream_t)stream);

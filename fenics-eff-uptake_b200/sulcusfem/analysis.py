@@ -1,0 +1,233 @@
+"""Flux / mass / mu_eff metrics with the reference's function names and result schema.
+
+Mirrors reference ``analysis.py``: ``compute_flux_metrics`` (:640), ``compute_mass_metrics`` (:677),
+``compute_concentration_profiles`` (:884), ``compute_mu_eff_arc/_enh/_sim/_sim_mouth`` (:948-1031),
+``compute_mu_eff_metrics`` (:1033).  Where the reference issues ~38 separate dolfin ``assemble``
+calls (each a full mesh loop), this module evaluates *all* facet and cell integrals of a run in two
+kernel launches (``sfem_facet_functionals`` / ``sfem_cell_functionals``) and then only fills the
+nested dictionaries the study drivers index.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.integrate import quad
+
+from .fem import Constant, evaluate_expression
+from . import dofmap as dm
+from .hostmesh import MARKERS  # noqa: F401
+
+_G = {'left': 0, 'right': 1, 'top': 2, 'bottom': 3, 'bottom_left': 4, 'sulcus': 5, 'bottom_right': 6,
+      'y0_ext': 7, 'mouth': 8}
+_DIFF, _ADV, _UPT, _C, _LEN, _EL1, _QIN, _QOUT = range(8)
+
+
+def _plan(mesh_results, domain_type):
+    mesh = mesh_results['mesh']
+    cache = getattr(mesh, '_sfem_cache', None)
+    if cache is None:
+        cache = {}
+        setattr(mesh, '_sfem_cache', cache)
+    key = ('functionals', domain_type)
+    if key not in cache:
+        from .device import FunctionalPlan
+        cache[key] = FunctionalPlan(mesh, mesh_results, domain_type)
+    return cache[key]
+
+
+def evaluate_functionals(c, u, mesh_results, domain_type, D_val, mu_val):
+    """All facet + cell integrals of one run (cached on ``c``): returns (F[groups,8], M[markers,2])."""
+    key = (id(u), float(D_val), id(mu_val) if not np.isscalar(mu_val) else float(mu_val), domain_type)
+    cached = getattr(c, '_functionals', None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    plan = _plan(mesh_results, domain_type)
+    cd = c.device_components()[0]
+    ux = uy = None
+    if u is not None and np.any(u.values):
+        ux, uy = u.device_components()
+    mu_const, mu_nodal = 0.0, None
+    if np.isscalar(mu_val) or isinstance(mu_val, Constant):
+        mu_const = float(mu_val)
+    elif mu_val is not None:
+        mesh = mesh_results['mesh']
+        X = dm.p2_dof_coordinates(mesh)
+        vals = np.zeros(len(X))
+        bottom = np.flatnonzero(X[:, 1] <= 0.0)           # only dofs of facets on the floor are read
+        vals[bottom] = evaluate_expression(mu_val, X[bottom])
+        mu_nodal = plan.ctx.up(vals, np.float64)
+    F, M = plan.evaluate(cd, ux, uy, D=float(D_val), mu_const=mu_const, mu_nodal=mu_nodal)
+    c._functionals = (key, F, M)
+    c._functionals_any = (F, M)
+    return F, M
+
+
+def _pf(F, g):
+    d, a = float(F[g, _DIFF]), float(F[g, _ADV])
+    return {'diffusive': d, 'advective': a, 'total': float(d + a)}
+
+
+# ====================================================================== flux metrics
+def compute_physical_flux_boundary(c, u, mesh_results, measures, boundary_marker, D_val):
+    domain_type = 'sulcus' if 'domain_markers' in mesh_results else 'rectangular'
+    F, _ = evaluate_functionals(c, u, mesh_results, domain_type, D_val, 0.0)
+    return _pf(F, int(boundary_marker) - 1)
+
+
+def compute_sulcus_segment_fluxes(c, u, mesh_results, measures, D_val, _F=None):
+    """Segment, mouth and y=0 fluxes of the sulcus mesh (reference analysis.py:181-298)."""
+    F = _F if _F is not None else evaluate_functionals(c, u, mesh_results, 'sulcus', D_val, 0.0)[0]
+    fl = {name: _pf(F, _G[name]) for name in ('bottom_left', 'sulcus', 'bottom_right')}
+    m = _G['mouth']
+    fl['sulcus_opening'] = _pf(F, m)
+    L_sig = float(F[m, _LEN])
+    fl['sulcus_opening_extra'] = {
+        'E_L1': float(F[m, _EL1]), 'E_avg': float(F[m, _EL1] / L_sig) if L_sig else float('nan'),
+        'Q_in': float(F[m, _QIN]), 'Q_out': float(F[m, _QOUT]),
+        'net_check': float(F[m, _QIN] - F[m, _QOUT]), 'length': L_sig}
+    e = _G['y0_ext']
+    jd, ja = float(F[e, _DIFF] + F[m, _DIFF]), float(F[e, _ADV] + F[m, _ADV])
+    fl['y0_flux'] = {'diffusive': jd, 'advective': ja, 'total': float(jd + ja)}
+
+    def sum_fields(keys):
+        return {nm: float(sum(fl[k][nm] for k in keys)) for nm in ('diffusive', 'advective', 'total')}
+    fl['bottom_combined'] = sum_fields(['bottom_left', 'sulcus', 'bottom_right'])
+    fl['y0_combined'] = sum_fields(['bottom_left', 'bottom_right', 'sulcus_opening'])
+    diff_val = abs(fl['y0_flux']['total'] - fl['y0_combined']['total'])
+    if diff_val > 1e-10:
+        print(f"⚠️ y0_flux vs y0_combined differ by {diff_val:.3e}")
+    return fl
+
+
+def compute_flux_metrics(c, u, mesh_results, domain_type, measures, D_val, mu_val):
+    """Reference analysis.py:640-675: same nested dictionary."""
+    F, _ = evaluate_functionals(c, u, mesh_results, domain_type, D_val, mu_val)
+    out = {'physical_flux': {nm: _pf(F, _G[nm]) for nm in ('left', 'right', 'top', 'bottom')},
+           'uptake_flux': float(F[_G['bottom'], _UPT])}
+    if domain_type == 'sulcus':
+        bl, su, br = (float(F[_G[k], _UPT]) for k in ('bottom_left', 'sulcus', 'bottom_right'))
+        out['sulcus_specific'] = {
+            'physical_flux': compute_sulcus_segment_fluxes(c, u, mesh_results, measures, D_val, _F=F),
+            'uptake_flux': {'bottom_left': bl, 'sulcus': su, 'bottom_right': br, 'total': bl + su + br}}
+    return out
+
+
+def compute_uptake_flux_bottom(c, measures, mu_val):
+    F, _ = c._functionals_any
+    return float(F[_G['bottom'], _UPT])
+
+
+# ====================================================================== mass metrics
+def compute_mass_metrics(c, measures, domain_type):
+    """Reference analysis.py:677-719."""
+    cached = getattr(c, '_functionals_any', None)
+    if cached is None:
+        mesh = c.function_space().mesh()
+        mr = {'mesh': mesh}
+        mr.update(getattr(mesh, '_sfem_markers', {}))
+        _, M = evaluate_functionals(c, None, mr, domain_type, 1.0, 0.0)
+    else:
+        M = cached[1]
+    if domain_type == 'sulcus':
+        sm, sa = float(M[1, 0]), float(M[1, 1])
+        rm, ra = float(M[2, 0]), float(M[2, 1])
+        tm, ta = sm + rm, sa + ra
+        return {'total_mass': tm, 'sulcus_mass': sm, 'rectangle_mass': rm, 'total_area': ta, 'sulcus_area': sa,
+                'rectangle_area': ra,
+                'average_concentration': {'total': tm / ta if ta > 0 else None,
+                                          'sulcus_region': sm / sa if sa > 0 else None,
+                                          'rectangle_region': rm / ra if ra > 0 else None}}
+    tm, ta = float(M[0, 0]), float(M[0, 1])
+    return {'total_mass': tm, 'total_area': ta, 'average_concentration': ta and tm / ta or 0.0}
+
+
+def compute_velocity_metrics(u, mesh_results, params):
+    """Line / sample statistics of |u| (reference analysis.py:721-830).  The reference's sampling is
+    unseeded random point evaluation for plots (out of scope); the no-advection branch
+    returns {} exactly like the reference (:733-734)."""
+    if u is None or not np.any(u.values):
+        return {}
+    n2 = len(u.values) // 2
+    speed = np.hypot(u.values[:n2], u.values[n2:])
+    return {'max_velocity_global': float(speed.max()), 'avg_velocity_global': float(speed.mean())}
+
+
+# ====================================================================== mu_eff
+def compute_concentration_profiles(results):
+    """Line integrals of c along y=0 with the channel-side trace on the mouth (analysis.py:884-946)."""
+    F, _ = results['c']._functionals_any
+    e, m = _G['y0_ext'], _G['mouth']
+    C_ext, C_m, L_ext, L_m = (float(F[e, _C]), float(F[m, _C]), float(F[e, _LEN]), float(F[m, _LEN]))
+    tot_L = L_ext + L_m
+    return {'C_y0_ext': C_ext, 'C_mouth': C_m, 'C_y0_total': C_ext + C_m,
+            'lengths': {'L_y0_ext': L_ext, 'L_mouth': L_m, 'L_y0_total': tot_L},
+            'means': {'mean_y0_ext': C_ext / L_ext if L_ext > 0 else np.nan,
+                      'mean_mouth': C_m / L_m if L_m > 0 else np.nan,
+                      'mean_y0_total': (C_ext + C_m) / tot_L if tot_L > 0 else np.nan}}
+
+
+def compute_mu_eff_arc(results):
+    """mu (1 + (L_sulcus - w)/L) with the arc length by adaptive quadrature (analysis.py:948-970)."""
+    p = results['params']
+    L, h, w, mu = float(p.L), float(p.sulci_h), float(p.sulci_w), float(p.mu)
+    if w <= 0 or h <= 0 or L <= 0:
+        return None
+    val, _ = quad(lambda s: np.sqrt(1.0 + (np.pi * h / w * np.cos(np.pi * s)) ** 2), 0.0, 1.0,
+                  epsabs=1e-10, epsrel=1e-10, limit=200)
+    return float(mu * (1.0 + (w * float(val) - w) / L))
+
+
+def compute_mu_eff_enh(results, kappa=10.0):
+    """analysis.py:972-985."""
+    p = results['params']
+    L, h, w, mu = float(p.L), float(p.sulci_h), float(p.sulci_w), float(p.mu)
+    if L <= 0 or mu < 0 or w <= 0:
+        return None
+    f = 1.0 / np.sqrt(1.0 + kappa * mu * (h ** 2) / w)
+    return float(mu * ((L - w) / L + (w / L) * f))
+
+
+def _flux_total(results, keys):
+    pf = results.get('flux_metrics', {}).get('sulcus_specific', {}).get('physical_flux', {})
+    for k in keys:
+        if k in pf and 'total' in pf[k]:
+            return float(pf[k]['total'])
+    return None
+
+
+def compute_mu_eff_sim(results, conc=None):
+    conc = conc if conc is not None else compute_concentration_profiles(results)
+    C_y0 = conc['C_y0_total']
+    J = _flux_total(results, ('y0_flux', 'y0_combined'))
+    if not np.isfinite(C_y0) or C_y0 <= 0.0 or J is None:
+        return None
+    return float(J / C_y0)
+
+
+def compute_mu_eff_sim_mouth(results, conc=None):
+    conc = conc if conc is not None else compute_concentration_profiles(results)
+    C_s = conc['C_mouth']
+    J = _flux_total(results, ('opening', 'mouth', 'y0_opening', 'y0_mouth', 'sulcus_opening'))
+    if not np.isfinite(C_s) or C_s <= 0.0 or J is None:
+        return None
+    return float(J / C_s)
+
+
+def compute_mu_eff_metrics(results, kappa=10.0):
+    """Reference analysis.py:1033-1097: same report dictionary."""
+    mu = float(results['params'].mu)
+    conc = compute_concentration_profiles(results)
+    arc, enh = compute_mu_eff_arc(results), compute_mu_eff_enh(results, kappa=kappa)
+    sim, opn = compute_mu_eff_sim(results, conc=conc), compute_mu_eff_sim_mouth(results, conc=conc)
+
+    def ratio(x, y):
+        return float(x / y) if (x is not None and y not in (None, 0.0)) else None
+
+    def pct(approx, truth):
+        return None if (truth in (None, 0.0) or approx is None) else float(abs(approx - truth) / abs(truth) * 100.0)
+    return {'mu_eff_arc': arc, 'mu_eff_enh': enh, 'mu_eff_sim': sim, 'mu_eff_open': opn,
+            'ratios': {'arc': ratio(arc, mu), 'enh': ratio(enh, mu), 'sim': ratio(sim, mu), 'open': ratio(opn, mu)},
+            'errors_vs_sim': {'arc': pct(arc, sim), 'enh': pct(enh, sim), 'open': pct(opn, sim)},
+            'audit': {'concentrations': {k: conc[k] for k in ('C_y0_ext', 'C_mouth', 'C_y0_total')},
+                      'lengths': conc.get('lengths', {}), 'means': conc.get('means', {}),
+                      'fluxes': {'J_y0_total': _flux_total(results, ('y0_flux', 'y0_combined')),
+                                 'J_sigma_mouth': _flux_total(results, ('opening', 'mouth', 'y0_opening', 'y0_mouth', 'sulcus_opening'))}}}

@@ -30,6 +30,8 @@ SIGNATURES = {
     'sfem_device_sms': (_i, []),
     'sfem_launch_count': (C.c_longlong, []),
     'sfem_launch_count_reset': (None, []),
+    'sfem_profile_start': (_i, [_i]),
+    'sfem_profile_stop': (_i, [_i, C.POINTER(_i), C.POINTER(_d), C.POINTER(C.c_float)]),
     'sfem_spmv_csr_f64': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _i, _p]),
     'sfem_spmv_csr_f64_staged': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     'sfem_elem_p2_advdiff': (_i, [_i, _p, _p, _d, _p, _p, _p, _p]),

@@ -64,6 +64,11 @@ class Context:
 P = capi.ptr
 
 
+def _arr(m):
+    """numpy view of a marker container (MeshMarkers, dolfin MeshFunction or plain array)."""
+    return np.asarray(m.array() if hasattr(m, "array") else m)
+
+
 class DeviceCsr:
     """CSR matrix in HBM (int32 indices, FP64 values); arrays padded for the staged SpMV."""
     PAD = 16
@@ -445,7 +450,7 @@ class FunctionalPlan:
         self.ctx = ctx or Context.get()
         ctx = self.ctx
         self.mesh, self.domain_type = mesh, domain_type
-        bc = markers['bc_markers'].values
+        bc = _arr(markers['bc_markers'])
         ent_cell, ent_loc, ptr = [], [], [0]
 
         def add(facets, cells, locs):
@@ -455,9 +460,9 @@ class FunctionalPlan:
         for mid in (1, 2, 3, 4):
             add(*dm.boundary_facets(mesh, bc, mid))
         if domain_type == 'sulcus':
-            bs = markers['bottom_segment_markers'].values
-            y0 = markers['y0_markers'].values
-            dmk = markers['domain_markers'].values
+            bs = _arr(markers['bottom_segment_markers'])
+            y0 = _arr(markers['y0_markers'])
+            dmk = _arr(markers['domain_markers'])
             for mid in (5, 6, 7):
                 add(*dm.boundary_facets(mesh, bs, mid))
             add(*dm.boundary_facets(mesh, y0, 10))
@@ -481,7 +486,7 @@ class FunctionalPlan:
         self.geo = ctx.up(cell_geometry(mesh), np.float64)
         self.celldofs = ctx.up(np.ascontiguousarray(dm.p2_cell_dofs(mesh).T), np.int32)
         if domain_type == 'sulcus':
-            self.cell_marker = ctx.up(markers['domain_markers'].values, np.int32)
+            self.cell_marker = ctx.up(_arr(markers['domain_markers']), np.int32)
             self.nmarkers = 3
         else:
             self.cell_marker = None

@@ -38,6 +38,11 @@ MARKERS = {                    # mesh.py:43-47 / analysis.py:17-21
 }
 
 
+class _CallableInt(int):
+    def __call__(self):
+        return int(self)
+
+
 class HostMesh:
     """2-D triangle mesh with dolfin-style ordered cells and derived connectivity."""
 
@@ -86,17 +91,19 @@ class HostMesh:
         self.edge_on_boundary = ~two
 
     # ------------------------------------------------------------------ sizes
+    # plain ints that can also be *called* like the dolfin methods (simulation.py:245-246 uses
+    # mesh.num_vertices() / mesh.num_cells())
     @property
     def num_vertices(self) -> int:
-        return int(self.coords.shape[0])
+        return _CallableInt(self.coords.shape[0])
 
     @property
     def num_cells(self) -> int:
-        return int(self.cells.shape[0])
+        return _CallableInt(self.cells.shape[0])
 
     @property
     def num_edges(self) -> int:
-        return int(self.edges.shape[0])
+        return _CallableInt(self.edges.shape[0])
 
     num_facets = num_edges
 
@@ -151,7 +158,7 @@ class MeshMarkers:
 
 
 def _near(a, b, eps):
-    return np.abs(a - b) <= eps           # dolfin::near
+    return (b - eps <= a) & (a <= b + eps)    # dolfin::near = between(x, (x0-eps, x0+eps))
 
 
 def boundary_predicates(width, height, xL, xR) -> Dict[str, Callable]:
@@ -356,7 +363,7 @@ def write_dolfin_xml(mesh: HostMesh, path: str):
         f.write('  <mesh celltype="triangle" dim="2">\n')
         f.write(f'    <vertices size="{mesh.num_vertices}">\n')
         for i, (x, y) in enumerate(mesh.coords):
-            f.write(f'      <vertex index="{i}" x="{x!r}" y="{y!r}" />\n')
+            f.write(f'      <vertex index="{i}" x="{float(x)!r}" y="{float(y)!r}" />\n')
         f.write(f'    </vertices>\n    <cells size="{mesh.num_cells}">\n')
         for i, (a, b, c) in enumerate(mesh.cells):
             f.write(f'      <triangle index="{i}" v0="{a}" v1="{b}" v2="{c}" />\n')

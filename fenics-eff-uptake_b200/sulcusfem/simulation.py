@@ -1,0 +1,116 @@
+"""``run_simulation`` with the reference's signature and ``results`` schema (simulation.py:270-349).
+
+Flow: mesh -> velocity (Stokes or zero) -> concentration -> post-processing.  The reference's
+plotting, ParaView export and JSON dump (simulation.py:91-92,137-138,165,235-268) are presentation
+layers outside the hot path and are not reproduced; everything the study drivers read from the
+returned dictionary is there.  Meshes (and with them patterns, gather maps and the
+multigrid hierarchy on the device) are cached per geometry so a mu-sweep on one geometry reuses
+them, where the reference re-runs Gmsh for every case.
+"""
+from __future__ import annotations
+
+import time
+
+from .analysis import (compute_flux_metrics, compute_mass_metrics, compute_mu_eff_metrics,
+                       compute_velocity_metrics)
+from .fem import Constant, FunctionSpace, MixedElement, VectorFunctionSpace
+from .mesh import MeshGenerator, setup_rectangular_measures, setup_sulcus_measures
+from .solvers import (advdiff_solver, advdiff_solver_variable_mu, pure_diffusion_solver,
+                      pure_diffusion_solver_variable_mu, stokes_solver, stokes_solver_no_adv)
+
+_MESH_CACHE = {}
+MESH_OPTIONS = {'mesher': 'delaunay', 'uniform_refinements': 0}
+
+
+def _simulation_generate_mesh(params, domain_type, mesh_dir=None, paraview_dir=None):
+    print("\n Generating mesh...")
+    mp = params.get_mesh_generator_params()
+    key = (domain_type, mp['width'], mp['height'], mp['sulcus_depth'], mp['sulcus_width'], mp['mesh_size'],
+           mp['refinement_factor'], MESH_OPTIONS['mesher'], MESH_OPTIONS['uniform_refinements'])
+    if key not in _MESH_CACHE:
+        mp['output_dir'] = mesh_dir
+        mp['domain_type'] = domain_type
+        _MESH_CACHE[key] = MeshGenerator(**mp, **MESH_OPTIONS).generate_mesh()
+    mesh_results = _MESH_CACHE[key]
+    if mesh_results:
+        info = mesh_results['mesh_info']
+        print("✓ Mesh generated successfully!")
+        print(f"      • Vertices: {info['num_vertices']:,}")
+        print(f"      • Elements: {info['num_cells']:,}")
+        print(f"      • h_min: {info['hmin']:.6f}")
+        print(f"      • h_max: {info['hmax']:.6f}")
+        return mesh_results
+    print("✗ Mesh generation failed!")
+    return None
+
+
+def _simulation_generate_vel(mode, domain_type, params, mesh_results, paraview_dir=None):
+    print("\n Generating velocity field...")
+    mesh = mesh_results['mesh']
+    V = VectorFunctionSpace(mesh, "P", 2)
+    Q = FunctionSpace(mesh, "P", 1)
+    W = FunctionSpace(mesh, MixedElement([V.ufl_element(), Q.ufl_element()]))
+    if mode == 'no-adv':
+        return stokes_solver_no_adv(V, Q)
+    cache = mesh_results.setdefault('_stokes_solution', {})
+    key = (float(params.L), float(params.H))
+    if key not in cache:                       # Stokes depends on the geometry only, not on Pe or mu
+        cache[key] = stokes_solver(mesh_results, W, params.L, params.H, domain_type)
+    return cache[key]
+
+
+def _simulation_generate_conc(u, mode, domain_type, params, mesh_results, paraview_dir=None, mu_variable=False):
+    print("\n Generating concentration field...")
+    mesh = mesh_results['mesh']
+    C = FunctionSpace(mesh, "CG", 2)
+    D_const = Constant(params.D)
+    mu_val = params.mu
+    if isinstance(mu_val, (int, float)):
+        mu_val = Constant(mu_val)
+    if mode == 'no-adv':
+        if mu_variable:
+            return pure_diffusion_solver_variable_mu(mesh_results, C, D_const, mu_val, domain_type)
+        return pure_diffusion_solver(mesh_results, C, D_const, mu_val, domain_type)
+    if mu_variable:
+        return advdiff_solver_variable_mu(mesh_results, u, C, D_const, mu_val, domain_type)
+    return advdiff_solver(mesh_results, u, C, D_const, mu_val, domain_type)
+
+
+def _simulation_post_process(domain_type, params, mesh_results, c, u, p):
+    print("\n Analysing results...")
+    mesh = mesh_results['mesh']
+    bc_markers = mesh_results['bc_markers']
+    if domain_type == 'sulcus':
+        ds_bc, ds_bottom, dS_bottom, ds_y0, dS_y0, dx_dom = setup_sulcus_measures(
+            mesh, bc_markers, mesh_results['bottom_segment_markers'], mesh_results['y0_markers'],
+            mesh_results['domain_markers'])
+        measures = {'ds_bc': ds_bc, 'ds_bottom': ds_bottom, 'dS_bottom': dS_bottom, 'ds_y0': ds_y0, 'dS_y0': dS_y0,
+                    'dx_domain_sulc': dx_dom}
+    else:
+        ds_bc, dx_dom = setup_rectangular_measures(mesh, bc_markers)
+        measures = {'ds_bc': ds_bc, 'dx_domain_rect': dx_dom}
+    flux_metrics = compute_flux_metrics(c, u, mesh_results, domain_type, measures, params.D, params.mu)
+    mass_metrics = compute_mass_metrics(c, measures, domain_type)
+    vel_metrics = compute_velocity_metrics(u, mesh_results, params)
+    results = {'c': c, 'u': u, 'p': p, 'mass_metrics': mass_metrics, 'flux_metrics': flux_metrics,
+               'vel_metrics': vel_metrics, 'params': params, 'mesh_results': mesh_results, 'measures': measures}
+    if domain_type == 'sulcus':
+        results['mu_eff_comparison'] = compute_mu_eff_metrics(results)
+    return results
+
+
+def run_simulation(mode, study_type, config_name, domain_type, params, mu_variable=False):
+    """Run one case; same arguments and result dictionary as the reference's ``run_simulation``."""
+    start_time = time.time()
+    valid_modes = ['adv-diff', 'no-adv', 'no-uptake']
+    if mode not in valid_modes:
+        raise ValueError(f"Invalid mode '{mode}'. Must be one of: {valid_modes}")
+    valid_domain_types = ['sulcus', 'rectangular']
+    if domain_type not in valid_domain_types:
+        raise ValueError(f"Invalid domain type '{domain_type}'. Must be one of: {valid_domain_types}")
+    mesh_results = _simulation_generate_mesh(params, domain_type)
+    u, p = _simulation_generate_vel(mode, domain_type, params, mesh_results)
+    c = _simulation_generate_conc(u, mode, domain_type, params, mesh_results, mu_variable=mu_variable)
+    results = _simulation_post_process(domain_type, params, mesh_results, c, u, p)
+    print(f"\n✓ Simulation completed in {time.time() - start_time:.1f}s")
+    return results

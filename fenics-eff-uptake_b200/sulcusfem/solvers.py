@@ -1,0 +1,234 @@
+"""The six solver entry points of the reference's ``solvers.py``, served by the B200 path.
+
+Signatures, argument meaning, printed diagnostics and error behaviour follow the reference
+(``solvers.py:16,59,113,176,237,308``) so ``simulation.run_simulation`` and the study drivers call
+them unchanged.  Inputs are duck-typed: ``mesh_results['mesh']`` is a :class:`HostMesh`,
+``mesh_results['bc_markers']`` anything with ``.array()``; ``C`` / ``W`` / ``V`` / ``Q`` are
+``fem.FunctionSpace`` objects (only the mesh and element are consulted); ``D`` / ``mu`` are
+``Constant`` or floats; ``mu_function`` is any object with ``eval(values, x)`` (e.g.
+``StepUptakeOpen``); ``u`` is a P2-vector ``Function``.
+
+What the reference hands to dolfin's ``solve(a == L, u, bcs)`` (assemble -> ``DirichletBC.apply`` ->
+sparse LU) runs here as: element/facet kernels + gather into the CSR pattern, Dirichlet kernel,
+then multigrid-preconditioned CG (pure diffusion), FGMRES (advection-diffusion) or MINRES
+(Taylor-Hood Stokes) to a relative residual of ``RTOL`` -- all on the device through the C ABI of
+``libsulcusfem.so``.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import dofmap as dm
+from .fem import Constant, Function, FunctionSpace, VectorFunctionSpace, evaluate_expression
+
+RTOL = 1e-13            # Krylov relative residual target (LU-level; fields match the oracle to 1e-10)
+STOKES_RTOL = 1e-14
+_CACHE_ATTR = '_sfem_cache'
+
+
+def _cache(mesh):
+    c = getattr(mesh, _CACHE_ATTR, None)
+    if c is None:
+        c = {}
+        setattr(mesh, _CACHE_ATTR, c)
+    return c
+
+
+def _markers_array(m):
+    return np.asarray(m.array() if hasattr(m, 'array') else m)
+
+
+def _hierarchy(mesh):
+    c = _cache(mesh)
+    if 'hierarchy' not in c:
+        from .hierarchy import build_hierarchy
+        c['hierarchy'] = build_hierarchy(mesh)
+    return c['hierarchy']
+
+
+def scalar_problem(mesh, bc_markers, robin_id=4):
+    """Cached device problem (patterns, gather maps, multigrid hierarchy) of one mesh."""
+    from .device import ScalarProblem
+    c = _cache(mesh)
+    key = ('scalar', int(robin_id))
+    if key not in c:
+        c[key] = ScalarProblem(mesh, _markers_array(bc_markers), dirichlet_ids=(1, 2), robin_id=robin_id,
+                               hierarchy=_hierarchy(mesh))
+    return c[key]
+
+
+def stokes_problem(mesh, bc_markers):
+    from .device import StokesProblem
+    c = _cache(mesh)
+    if 'stokes' not in c:
+        c['stokes'] = StokesProblem(mesh, _markers_array(bc_markers), hierarchy=_hierarchy(mesh))
+    return c['stokes']
+
+
+def _check_space(C, kind):
+    if not isinstance(C, FunctionSpace) or C.kind != kind:
+        raise ValueError(f"expected a {kind} function space")
+    return C.mesh()
+
+
+def _velocity_components(u, mesh):
+    if u is None:
+        return None, None
+    if isinstance(u, Constant):
+        v = u.values()
+        if np.all(v == 0.0):
+            return None, None
+        from .device import Context
+        ctx = Context.get()
+        n2 = dm.p2_num_dofs(mesh)
+        return ctx.up(np.full(n2, v[0]), np.float64), ctx.up(np.full(n2, v[1]), np.float64)
+    if u.function_space().kind != 'P2v':
+        raise ValueError("velocity must be a P2 vector Function")
+    if not np.any(u.values):
+        return None, None
+    return u.device_components()
+
+
+def _mu_nodal(mu_function, prob):
+    """P2 interpolant of mu at the dofs of the Robin boundary cells' facets (App. A.3)."""
+    lev = prob.fine
+    X = dm.p2_dof_coordinates(prob.mesh)
+    facet_dofs = np.unique(dm.p2_facet_dofs(prob.mesh, lev.robin_facets).ravel()) if lev.nf else np.zeros(0, dtype=np.int64)
+    vals = np.zeros(lev.n)
+    if len(facet_dofs):
+        vals[facet_dofs] = evaluate_expression(mu_function, X[facet_dofs])
+    mean = float(vals[facet_dofs].mean()) if len(facet_dofs) else 0.0
+    return prob.ctx.up(vals, np.float64), vals, mean
+
+
+def _solve_scalar(mesh_results, C, D, u, mu=None, mu_function=None, clamp=False, bottom_id=4):
+    mesh = _check_space(C, 'P2')
+    prob = scalar_problem(mesh, mesh_results['bc_markers'], bottom_id)
+    ux, uy = _velocity_components(u, mesh)
+    kw = dict(mu_const=0.0)
+    mu_host = None
+    if mu_function is not None:
+        mu_dev, mu_host, mean = _mu_nodal(mu_function, prob)
+        kw = dict(mu_nodal=mu_dev, clamp=clamp, coarse_mu=max(mean, 0.0))
+    elif mu is not None:
+        kw = dict(mu_const=float(mu))
+    prob.assemble(float(D), ux, uy, bc_values={1: 1.0, 2: 0.0}, **kw)
+    method = 'cg' if ux is None else 'fgmres'
+    x = prob.solve(method, rtol=RTOL)
+    if not prob.last_info['converged']:
+        raise RuntimeError(f"Krylov solver did not converge: {prob.last_info}")
+    return prob, x
+
+
+def _post(prob, x, fix_nonfinite):
+    import ctypes as C
+    from . import capi
+    stats = (C.c_double * 6)()
+    capi.check(prob.ctx.lib.sfem_postprocess_concentration(prob.n, capi.ptr(x), int(fix_nonfinite), stats, prob.ctx.stream),
+               'sfem_postprocess_concentration')
+    return {'nonfinite': int(stats[0]), 'negative': int(stats[1]), 'min': stats[2], 'max': stats[3], 'mean': stats[4],
+            'clamped': bool(stats[5])}
+
+
+def _to_function(C, prob, x):
+    f = Function(C, x.cpu().numpy())
+    f._dev = (x.clone(),)
+    f.solver_info = dict(prob.last_info)
+    return f
+
+
+# ====================================================================== advection-diffusion
+def advdiff_solver(mesh_results, u, C, D, mu, mesh_type="sulcus"):
+    """Steady advection-diffusion with constant Robin uptake (reference solvers.py:16-57)."""
+    prob, x = _solve_scalar(mesh_results, C, D, u, mu=mu)
+    return _to_function(C, prob, x)
+
+
+def advdiff_solver_variable_mu(mesh_results, u, C, D, mu_function, mesh_type="sulcus"):
+    """Advection-diffusion with a spatially varying Robin coefficient mu(x) (solvers.py:59-107)."""
+    prob, x = _solve_scalar(mesh_results, C, D, u, mu_function=mu_function, clamp=False)
+    st = _post(prob, x, fix_nonfinite=True)
+    if st['nonfinite']:
+        print(f"WARNING: {st['nonfinite']} non-finite concentration entries; clamping to 0.")
+    if st['negative']:
+        if st['clamped']:
+            print("✓ Clamped tiny negative values to 0 (numerical noise).")
+            st = _post(prob, x, fix_nonfinite=False)
+        else:
+            print(f"WARNING: {st['negative']} negative values; most negative {st['min']:.3e}")
+    print(f"Solution stats: min={st['min']:.6e}, max={st['max']:.6e}, mean={st['mean']:.6e}")
+    return _to_function(C, prob, x)
+
+
+# ====================================================================== diffusion only
+def pure_diffusion_solver(mesh_results, C, D, mu, mesh_type="sulcus"):
+    """Steady diffusion with constant Robin uptake (reference solvers.py:113-174)."""
+    prob, x = _solve_scalar(mesh_results, C, D, None, mu=mu)
+    st = _post(prob, x, fix_nonfinite=False)
+    if st['negative'] > 0:
+        if st['clamped']:
+            st = _post(prob, x, fix_nonfinite=False)
+        else:
+            print(f"WARNING: {st['negative']} negative concentration values found!")
+            print(f"  Most negative: {st['min']:.6e}")
+            print(f"  Min: {st['min']:.6e}, Max: {st['max']:.6e}")
+            print("  Check: mesh quality, boundary conditions, solver settings")
+    else:
+        print("✓ All concentration values are non-negative")
+    print(f"Solution stats: min={st['min']:.6e}, max={st['max']:.6e}, mean={st['mean']:.6e}")
+    return _to_function(C, prob, x)
+
+
+def pure_diffusion_solver_variable_mu(mesh_results, C, D, mu_function, mesh_type="rectangular", bottom_id=4, u=None):
+    """Diffusion (optionally advected by ``u``) with mu(x) clamped to >= 0 at the quadrature points
+    (reference solvers.py:176-231)."""
+    prob, x = _solve_scalar(mesh_results, C, D, u, mu_function=mu_function, clamp=True, bottom_id=bottom_id)
+    st = _post(prob, x, fix_nonfinite=False)
+    if st['negative'] > 0:
+        if st['clamped']:
+            st = _post(prob, x, fix_nonfinite=False)
+        else:
+            print(f"WARNING: {st['negative']} negative concentration values found!")
+            print(f"  Most negative: {st['min']:.6e}")
+            print("  Check: mesh quality, BCs, solver settings")
+    print(f"Solution stats: min={st['min']:.6e}, max={st['max']:.6e}, mean={st['mean']:.6e}")
+    return _to_function(C, prob, x)
+
+
+# ====================================================================== Stokes
+def stokes_solver(mesh_results, W, L_domain, H, mesh_type="sulcus"):
+    """Taylor-Hood Stokes flow driven by a Poiseuille inlet (reference solvers.py:237-306).
+
+    Inlet ``(4y(H-y), 0)`` on id 1, no-slip on ids 4 and 3 (applied in that order), natural outflow
+    on id 2.  The reference's "pointwise" pressure pin matches no dof, so the
+    pressure level is fixed by the outflow condition alone -- same here.
+    """
+    unique_vals = np.unique(_markers_array(mesh_results['bc_markers']))
+    print(f"Boundary markers present: {unique_vals}")
+    try:
+        mesh = _check_space(W, 'TH')
+        bm = _markers_array(mesh_results['bc_markers'])
+        prob = stokes_problem(mesh, bm)
+        X = dm.p2_dof_coordinates(mesh)
+        d1 = dm.dirichlet_dofs_p2(mesh, bm, 1)
+        print(f"Trying pressure constraint at outlet center: ({L_domain}, {H/2})")
+        prob.set_bcs({1: (4.0 * X[d1, 1] * (H - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+        prob.assemble(bc_mode=1)
+        ux, uy, p = prob.solve(rtol=STOKES_RTOL)
+        if not np.isfinite(prob.last_info['relres']) or prob.last_info['relres'] > 1e-9:
+            raise RuntimeError(f"MINRES stalled: {prob.last_info}")
+        n2 = prob.n2
+        u = Function(VectorFunctionSpace(mesh, 'P', 2), prob.x[:2 * n2].cpu().numpy())
+        u._dev = (ux.clone(), uy.clone())
+        pf = Function(FunctionSpace(mesh, 'P', 1), p.cpu().numpy())
+        u.solver_info = pf.solver_info = dict(prob.last_info)
+        print(f"✓ Stokes solver completed using outlet point constraint for {mesh_type} mesh")
+        return u, pf
+    except Exception as e:
+        print(f"Outlet point constraint failed: {e}")
+        raise RuntimeError("Unable to solve Stokes system.")
+
+
+def stokes_solver_no_adv(V, Q):
+    """Zero velocity / pressure fields for the no-advection mode (reference solvers.py:308-316)."""
+    return Function(V), Function(Q)

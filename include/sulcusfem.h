@@ -37,6 +37,13 @@ int sfem_device_sms(void);
 long long sfem_launch_count(void);
 void sfem_launch_count_reset(void);
 
+/* Per-launch timing for bench.py's roofline: between start and stop every instrumented launch is
+ * bracketed by CUDA events on its stream.  stop() synchronises the device and returns the number of
+ * records copied: category (0 spmv, 1 spmv+dot, 2 chebyshev step, 3 residual+d0, 4 element kernels,
+ * 5 gather, 6 vector ops, 7 other, 8 staged spmv), algorithmic bytes, milliseconds. */
+int sfem_profile_start(int max_records);
+int sfem_profile_stop(int cap, int* h_cat, double* h_bytes, float* h_ms);
+
 /* ------------------------------------------------------------------ sparse mat-vec ---------- */
 /* y = A x (mode 0), y = b - A x (mode 1), y += A x (mode 2).  FP64 values, int32 indices.
  * replaces: PETSc MatMult inside solve(a == L, ...)  solvers.py:55,84,151,213,298

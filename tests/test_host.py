@@ -1,0 +1,188 @@
+"""CPU: host-side logic (meshes, markers, DOF maps, sparsity, gather maps, hierarchy, front-end objects)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import cpu_oracle as co
+from sulcusfem import dofmap as dm
+from sulcusfem import hierarchy as hy
+from sulcusfem import hostmesh as hm
+from sulcusfem.unstructured import mesh_domain
+
+
+def _mesh_ok(m, area):
+    assert np.all(np.abs(m.signed_areas()) > 0)
+    assert abs(np.abs(m.signed_areas()).sum() - area) < 2e-3 * area
+    # Euler characteristic of a disc
+    assert m.num_vertices - m.num_edges + m.num_cells == 1
+    assert np.all(np.diff(m.cells.astype(np.int64), axis=1) > 0)          # ascending vertex ids per cell
+
+
+@pytest.mark.parametrize("w,d", [(0.5, 1.0), (0.25, 0.25), (1.0, 0.2), (0.3, 1.0)])
+def test_sulcus_meshers(w, d):
+    area = 10.0 + 2 * w * d / np.pi
+    for m in (hm.sulcus_mesh(10.0, 1.0, w, d, 0.1), mesh_domain(10.0, 1.0, w, d, 0.1, 'sulcus')):
+        _mesh_ok(m, area)
+        mk = hm.build_markers(m, 10.0, 1.0, 5 - w / 2, 5 + w / 2, 'sulcus')
+        bc = mk['bc_markers'].values
+        # every exterior facet carries exactly one of the ids 1..4 and no interior facet does
+        assert np.all(bc[m.edge_on_boundary] > 0) and np.all(bc[~m.edge_on_boundary] == 0)
+        L = np.linalg.norm(m.coords[m.edges[:, 0]] - m.coords[m.edges[:, 1]], axis=1)
+        assert abs(L[bc == 1].sum() - 1.0) < 1e-12 and abs(L[bc == 2].sum() - 1.0) < 1e-12
+        assert abs(L[bc == 3].sum() - 10.0) < 1e-12
+        y0 = mk['y0_markers'].values
+        assert abs(L[(y0 == 10) & m.edge_on_boundary].sum() - (10.0 - w)) < 1e-12
+        assert abs(L[(y0 == 10) & ~m.edge_on_boundary].sum() - w) < 1e-12      # mouth edges on y=0
+        bs = mk['bottom_segment_markers'].values
+        # 'sulcus' needs y < -eps at all three points: the two curve facets touching the corners stay 0
+        curve = (bc == 4) & (y0 != 10)
+        assert curve.sum() - (bs == 6).sum() == 2
+        dmk = mk['domain_markers'].values
+        a = np.abs(m.signed_areas())
+        assert abs(a[dmk == 2].sum() - 10.0) < 1e-9
+
+
+def test_rectangle_mesh_and_refine_numbering():
+    m = hm.rectangle_mesh(10.0, 1.0, 20, 4)
+    _mesh_ok(m, 10.0)
+    f = hm.refine(m)
+    _mesh_ok(f, 10.0)
+    assert f.num_vertices == m.num_vertices + m.num_edges and f.num_cells == 4 * m.num_cells
+    assert np.array_equal(f.coords[:m.num_vertices], m.coords)
+    assert np.allclose(f.coords[m.num_vertices:], m.edge_midpoints())
+    # P2 nodes of the coarse mesh = P1 nodes of the refined mesh, same numbering
+    assert np.allclose(dm.p2_dof_coordinates(m), f.coords)
+
+
+def test_refine_projects_curved_boundary():
+    m = hm.sulcus_mesh(10.0, 1.0, 0.5, 1.0, 0.2)
+    f = hm.refine(m, project_curved_boundary=True)
+    g = m.geometry
+    bnd = np.unique(f.edges[f.edge_on_boundary].ravel())
+    p = f.coords[bnd]
+    on_floor = p[:, 1] < -1e-12
+    assert np.allclose(p[on_floor, 1], hm.sulcus_floor(p[on_floor, 0], g['xL'], g['w'], g['d']), atol=1e-12)
+
+
+def test_dofmaps_and_patterns_match_oracle_bit_exact():
+    m = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.2, 'sulcus')
+    om = co.Mesh(m.coords, m.cells)
+    assert np.array_equal(m.edges, om.edges) and np.array_equal(m.cell_edges, om.cell_edges)
+    assert np.array_equal(dm.p2_cell_dofs(m), om.p2_cell_dofs())
+    assert np.array_equal(dm.th_cell_dofs(m), om.th_cell_dofs())
+    assert np.array_equal(dm.p2_dof_coordinates(m), om.p2_dof_coords())
+    for cd, n in ((dm.p2_cell_dofs(m), om.n_p2), (dm.th_cell_dofs(m), 2 * om.n_p2 + om.nv), (dm.p1_cell_dofs(m), om.nv)):
+        pat = dm.build_pattern(n, n, [(cd, cd)])
+        ip, ix = co.clique_pattern(cd, n)
+        assert np.array_equal(pat.rowptr, ip) and np.array_equal(pat.cols, ix)
+    # marker parity (vectorised host code vs per-facet oracle loop)
+    mk = hm.build_markers(m, 10.0, 1.0, 4.75, 5.25, 'sulcus')
+    for key, names in (('bc_markers', ['left', 'right', 'top', 'bottom']),
+                       ('bottom_segment_markers', ['bottom_left', 'bottom_right', 'sulcus', 'sulcus_opening']),
+                       ('y0_markers', ['y0_line'])):
+        assert np.array_equal(mk[key].values, co.mark_facets(om, 10.0, 1.0, 4.75, 5.25, names))
+    assert np.array_equal(mk['domain_markers'].values, co.cell_markers(om))
+    d_or, _ = co.concentration_bcs(om, mk['bc_markers'].values)
+    d_host = np.union1d(dm.dirichlet_dofs_p2(m, mk['bc_markers'].values, 1), dm.dirichlet_dofs_p2(m, mk['bc_markers'].values, 2))
+    assert np.array_equal(d_or, d_host)
+
+
+def test_gather_map_reproduces_assembly():
+    """The slot -> contributions map, applied to oracle element matrices, gives the oracle matrix."""
+    m = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.25, 'sulcus')
+    om = co.Mesh(m.coords, m.cells)
+    mk = hm.build_markers(m, 10.0, 1.0, 4.75, 5.25, 'sulcus')
+    bm = mk['bc_markers'].values
+    cd = dm.p2_cell_dofs(m)
+    f, _, _ = dm.boundary_facets(m, bm, 4)
+    fd = dm.p2_facet_dofs(m, f)
+    pat = dm.build_pattern(om.n_p2, om.n_p2, [(cd, cd), (fd, fd)])
+    lam, w = co.triangle_rule(2)
+    G = np.einsum('qia,cad->cqid', co.p2_dbasis(lam), om.glam)
+    Ke = np.einsum('q,cqid,cqjd,c->cij', w, G, G, np.abs(om.det))
+    # facet mass with the trace basis [va, vb, mid]
+    t, wt = co.interval_rule(4)
+    phi = np.stack([(1 - t) * (1 - 2 * t), t * (2 * t - 1), 4 * t * (1 - t)], axis=1)
+    L = np.linalg.norm(m.coords[m.edges[f, 0]] - m.coords[m.edges[f, 1]], axis=1)
+    Fe = np.einsum('q,qi,qj,f->fij', wt, phi, phi, L) * 0.7
+    E = np.concatenate([Ke.ravel(), Fe.ravel()])
+    assert pat.family_base == [0, Ke.size] and pat.buffer_len == E.size
+    vals = np.add.reduceat(E[pat.contrib_code], pat.contrib_ptr[:-1])
+    A = sp.csr_matrix((vals, pat.cols, pat.rowptr), shape=(om.n_p2, om.n_p2))
+    ref = co.assemble_p2_stiffness(om) + co.assemble_p2_robin(om, f, mu_const=0.7)
+    assert abs(A - ref).max() < 1e-13
+    # contributions of a slot are ordered by (family, cell)
+    for s in range(0, pat.nnz, 97):
+        c = pat.contrib_code[pat.contrib_ptr[s]:pat.contrib_ptr[s + 1]]
+        assert np.all(np.diff(c) > 0)
+
+
+def test_hierarchy_transfers():
+    fine = hm.refine(mesh_domain(10.0, 1.0, 0.5, 1.0, 0.2, 'sulcus'))
+    H = hy.build_hierarchy(fine, coarsest_vertices=150)
+    assert len(H.meshes) >= 3 and H.meshes[1] is fine.parent
+    sizes = [dm.p2_num_dofs(fine)] + [m.num_vertices for m in H.meshes]
+    for l, T in enumerate(H.transfers):
+        assert (T.n_fine, T.n_coarse) == (sizes[l], sizes[l + 1])
+        P = sp.csr_matrix((T.vals, T.cols, T.rowptr), shape=(T.n_fine, T.n_coarse))
+        R = sp.csr_matrix((T.t_vals, T.t_cols, T.t_rowptr), shape=(T.n_coarse, T.n_fine))
+        assert abs(P.T - R).max() == 0.0
+        assert np.allclose(np.asarray(P.sum(axis=1)).ravel(), 1.0)          # partition of unity
+        # prolongation reproduces linear functions (exactly for nested, up to the curved boundary otherwise)
+        Xc = H.meshes[l].coords
+        Xf = dm.p2_dof_coordinates(H.meshes[0]) if l == 0 else H.meshes[l - 1].coords
+        lin = lambda X: 2.0 + 0.3 * X[:, 0] - 1.7 * X[:, 1]
+        err = np.abs(P @ lin(Xc) - lin(Xf))
+        if T.nested and l == 0:
+            assert err.max() < 1e-12
+        else:
+            assert np.median(err) < 1e-12 and np.quantile(err, 0.9) < 0.05   # only nodes near the curved floor differ
+    assert H.transfers[0].nested and H.transfers[1].nested and not H.transfers[-1].nested
+
+
+def test_locate_points_and_function_eval():
+    from sulcusfem.fem import Function, FunctionSpace, VectorFunctionSpace
+    m = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.2, 'sulcus')
+    V = FunctionSpace(m, 'CG', 2)
+    X = V.tabulate_dof_coordinates()
+    quad = lambda x, y: 1.0 + x - 2 * y + 0.5 * x * y - 0.25 * y * y
+    f = Function(V, quad(X[:, 0], X[:, 1]))
+    for p in ((0.3, 0.4), (5.0, -0.5), (9.99, 0.999), (5.0, 0.0)):
+        assert abs(f(p) - quad(*p)) < 1e-12
+    with pytest.raises(RuntimeError):
+        f((5.0, -3.0))
+    f.set_allow_extrapolation(True)
+    f((5.0, -1.05))
+    W = VectorFunctionSpace(m, 'P', 2)
+    u = Function(W, np.concatenate([X[:, 1] * (1 - X[:, 1]), 0 * X[:, 0]]))
+    assert np.allclose(u((2.0, 0.25)), [0.1875, 0.0])
+    v = f.vector()
+    a = v.get_local(); a[:] = 3.0; v.set_local(a); v.apply('insert')
+    assert f((1.0, 0.5)) == pytest.approx(3.0)
+    assert m.num_vertices() == m.num_vertices and isinstance(m.hmin(), float)
+
+
+def test_mesh_generator_interface(tmp_path):
+    from sulcusfem.mesh import MeshGenerator
+    from sulcusfem.parameters import Parameters
+    p = Parameters(mode='no-adv', mesh_size_dim=0.2)
+    p.validate(); p.nondim()
+    kw = p.get_mesh_generator_params()
+    kw['domain_type'] = 'sulcus'
+    res = MeshGenerator(**kw).generate_mesh()
+    assert set(res) == {'mesh', 'bc_markers', 'bottom_segment_markers', 'y0_markers', 'domain_markers', 'mesh_info'}
+    assert set(np.unique(res['bc_markers'].array())) == {0, 1, 2, 3, 4}
+    kw['domain_type'] = 'rectangular'
+    res2 = MeshGenerator(**kw).generate_mesh()
+    assert set(res2) == {'mesh', 'bc_markers', 'mesh_info'}
+    with pytest.raises(ValueError):
+        MeshGenerator(10, 1, 1.0, 0.5, -0.1, 1, 'sulcus')
+    with pytest.raises(ValueError):
+        MeshGenerator(10, 1, 1.0, 0.5, 0.1, 1, 'triangle')
+    # round trip through the dolfin-XML format the reference writes
+    path = str(tmp_path / 'm.xml')
+    hm.write_dolfin_xml(res['mesh'], path)
+    back = hm.read_dolfin_xml(path)
+    assert np.array_equal(back.cells, res['mesh'].cells) and np.array_equal(back.coords, res['mesh'].coords)
+    res3 = MeshGenerator(10.0, 1.0, 1.0, 0.5, 0.2, 1, 'sulcus', mesh_file=path).generate_mesh()
+    assert np.array_equal(res3['bc_markers'].array(), res['bc_markers'].array())
