@@ -15,6 +15,15 @@ int sfem_spmv_csr_f64(int nrows, int nnz, const int* rowptr, const int* cols, co
   return spmv(A, x, b, y, mode, (cudaStream_t)stream);
 }
 
+int sfem_spmv_csr_f64_nb(int nrows, int ncols, int nnz, const int* rowptr, const int* cols, const double* vals,
+                         const double* x, const double* b, double* y, int mode, int nb, void* stream) {
+  if (nrows < 0 || ncols < 0 || nnz < 0 || mode < 0 || mode > 2) { set_error("spmv: bad arguments"); return SFEM_ERR_ARG; }
+  Csr A;
+  A.nrows = nrows; A.ncols = ncols; A.nnz = nnz;
+  A.rowptr = rowptr; A.cols = cols; A.vals = vals;
+  return spmv(A, x, b, y, mode, (cudaStream_t)stream, nb);
+}
+
 int sfem_spmv_csr_f64_staged(int nrows, int nnz, const int* rowptr, const int* cols, const double* vals,
                              const double* x, const double* b, double* y, int mode, int tile_rows, int tile_cap,
                              int stages, void* stream) {

@@ -264,6 +264,26 @@ __global__ void __launch_bounds__(kThreads) k_gather(int nnz, const int* __restr
   }
 }
 
+// dst[i] = src[slot[i]]  (copy a sub-block of an assembled CSR into its own CSR, e.g. K / B / B^T of
+// the Taylor-Hood matrix)
+__global__ void __launch_bounds__(kThreads) k_extract(int n, const int* __restrict__ slot, const double* __restrict__ src,
+                                                      double* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[slot[i]];
+}
+
+// blocked [c][n] <-> interleaved [n][c] layouts of a two-component nodal field
+__global__ void k_interleave2(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    reinterpret_cast<double2*>(out)[i] = make_double2(a[i], b[i]);
+}
+__global__ void k_deinterleave2(int n, const double* __restrict__ in, double* __restrict__ a, double* __restrict__ b) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double2 v = reinterpret_cast<const double2*>(in)[i];
+    a[i] = v.x;
+    b[i] = v.y;
+  }
+}
+
 template <int LANES>
 __global__ void __launch_bounds__(kThreads) k_dirichlet(int n, const int* __restrict__ rowptr, const int* __restrict__ cols,
                                                         double* __restrict__ vals, double* __restrict__ rhs,
@@ -368,6 +388,28 @@ int sfem_gather_csr(int nnz, const int* contrib_ptr, const int* contrib_code, co
   if (nnz <= 0) return SFEM_OK;
   Prof prof(PC_GATHER, (double)nnz * 12.0, (cudaStream_t)stream);   // + 12 B per contribution, unknown here
   k_gather<<<grid_for(nnz, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(nnz, contrib_ptr, contrib_code, E, vals);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_csr_extract(int n, const int* slot, const double* src_vals, double* dst_vals, void* stream) {
+  if (n <= 0) return SFEM_OK;
+  Prof prof(PC_GATHER, (double)n * 20.0, (cudaStream_t)stream);
+  k_extract<<<grid_for(n, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(n, slot, src_vals, dst_vals);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_vec_interleave2(int n, const double* a, const double* b, double* out, void* stream) {
+  if (n <= 0) return SFEM_OK;
+  k_interleave2<<<grid_for(n, kThreads * 2), kThreads, 0, (cudaStream_t)stream>>>(n, a, b, out);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_vec_deinterleave2(int n, const double* in, double* a, double* b, void* stream) {
+  if (n <= 0) return SFEM_OK;
+  k_deinterleave2<<<grid_for(n, kThreads * 2), kThreads, 0, (cudaStream_t)stream>>>(n, in, a, b);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

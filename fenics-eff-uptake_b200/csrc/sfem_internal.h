@@ -18,13 +18,18 @@ struct Csr {
   int stages = 3;
 };
 
-// sfem_spmv.cu
-int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st);
-int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* nparts, cudaStream_t st);
+// sfem_spmv.cu  (nb = number of interleaved right-hand sides, 1 or 2)
+int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st, int nb = 1);
+int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* nparts, cudaStream_t st, int nb = 1,
+             const double* dotx = nullptr);   // partial sums of <dotx, y>, dotx defaults to x
+// Chebyshev coefficients are read from device memory: c12 -> {c1, c2}, c0 -> {c0}
 int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
-              double c1, double c2, int last, cudaStream_t st);
+              const double* c12, int last, cudaStream_t st, int nb = 1);
 int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
-             double c0, cudaStream_t st);
+             const double* c0, cudaStream_t st, int nb = 1);
+// y_u = K z_u + BT z_p (interleaved velocity), partial sums of <z_u, y_u>
+int stokes_apply_u(const Csr& K, const Csr& BT, const double* zu, const double* zp, double* yu, double* partial,
+                   int* nparts, cudaStream_t st);
 // sfem_spmv_staged.cu
 int spmv_staged_plan(const Csr& A, int tile_rows, int tile_cap, int stages, const double* x, const double* b,
                      double* y, int mode, cudaStream_t st);
@@ -35,8 +40,9 @@ int vec_copy(int n, const double* x, double* y, cudaStream_t st);
 int vec_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st);
 int vec_mul_scale(int n, double a, const double* d, const double* x, double* y, cudaStream_t st);   // y = a d.*x
 int vec_dot_partial(int n, const double* x, const double* y, double* partial, int* nparts, cudaStream_t st);
+int vec_sum_partials(const double* partial, int n, double* out, cudaStream_t st);   // out[0] = sum, one block
 int vec_dot_host(int n, const double* x, const double* y, double* scratch, double* h_out, cudaStream_t st);
 int extract_diag_inv(const Csr& A, double* dinv, cudaStream_t st);
-int dense_gemv(int n, const double* M, const double* x, double* y, cudaStream_t st);
+int dense_gemv(int n, const double* M, const double* x, double* y, cudaStream_t st, int nb = 1);
 
 }  // namespace sfem

@@ -7,6 +7,11 @@
 //     r0 = b - A x0,  d0 = D^-1 r0 / theta
 //     x_{i+1} = x_i + d_i;  r_{i+1} = r_i - A d_i;  d_{i+1} = rho_{i+1} rho_i d_i + (2 rho_{i+1}/delta) D^-1 r_{i+1}
 // Each step after the first is ONE kernel (SpMV fused with all vector updates, ping-pong d).
+// lmax is the Gershgorin bound of D^-1 A -- a guaranteed upper bound keeps the smoother (and with
+// it the V-cycle) positive definite, which MINRES / CG rely on -- computed on the device; the
+// coefficients stay in device memory, so set-up never synchronises with the host and captured
+// CUDA graphs of a cycle stay valid when the operator is re-assembled.
+// With nb = 2 a cycle carries two interleaved right-hand sides (see sfem_spmv.cu).
 #include "sfem_mg.h"
 
 #include <cmath>
@@ -18,20 +23,16 @@ namespace sfem {
 
 namespace {
 
-__global__ void k_cheb_init0(int n, const double* __restrict__ dinv, const double* __restrict__ b,
-                             double* __restrict__ r, double* __restrict__ d, double* __restrict__ x, double c0) {
+// n = rows * nb entries; dinv is per row
+__global__ void k_cheb_init0(int n, int nb, const double* __restrict__ dinv, const double* __restrict__ b,
+                             double* __restrict__ r, double* __restrict__ d, double* __restrict__ x,
+                             const double* __restrict__ coef) {
+  const double c0 = coef[1];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double bi = b[i];
     r[i] = bi;
-    d[i] = c0 * dinv[i] * bi;
+    d[i] = c0 * dinv[nb == 2 ? (i >> 1) : i] * bi;
     x[i] = 0.0;
-  }
-}
-
-__global__ void k_fill_pseudo(int n, double* __restrict__ v) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double t = (double)i * 0.6180339887498949;
-    v[i] = 0.25 + (t - floor(t));
   }
 }
 
@@ -55,43 +56,61 @@ __global__ void __launch_bounds__(kThreads) k_gershgorin(int n, const int* __res
   }
 }
 
-}  // namespace
-
-// Guaranteed upper bound of lambda_max(D^-1 A): keeps the Chebyshev smoother (and with it the
-// V-cycle) positive definite, which MINRES / CG rely on.  A power-iteration estimate can fall short
-// of the true value and then the polynomial amplifies the top of the spectrum.
-int gershgorin_lambda_max(const Csr& A, const double* dinv, double* scratch, double* out, cudaStream_t st) {
-  const int grid = grid_for(A.nrows, kThreads, 4);
-  k_gershgorin<<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.vals, dinv, scratch);
-  SFEM_LAUNCH_CHECK();
-  std::vector<double> h(grid);
-  SFEM_CUDA(cudaMemcpyAsync(h.data(), scratch, grid * sizeof(double), cudaMemcpyDeviceToHost, st));
-  SFEM_CUDA(cudaStreamSynchronize(st));
-  double mx = 0.0;
-  for (double v : h) mx = v > mx ? v : mx;
-  *out = mx;
-  return SFEM_OK;
-}
-
-int smooth(const Csr& A, const double* dinv, double lmax, double ratio, int degree, const double* b, double* x,
-           double* r, double* d0, double* d1, bool zero_init, cudaStream_t st) {
-  const int n = A.nrows;
+__global__ void k_cheb_coef(const double* __restrict__ partial, int np, double fixed_lmax, double ratio, int degree,
+                            double* __restrict__ coef) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double lmax = fixed_lmax;
+  if (np > 0) {
+    lmax = 0.0;
+    for (int i = 0; i < np; ++i) lmax = fmax(lmax, partial[i]);
+    if (!(lmax > 0.0)) lmax = 2.0;
+  }
   const double lmin = lmax / ratio;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double rho = 1.0 / sigma;
+  coef[0] = lmax;
+  coef[1] = 1.0 / theta;
+  for (int i = 0; i + 1 < degree; ++i) {
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    coef[2 + 2 * i] = rho_new * rho;
+    coef[3 + 2 * i] = 2.0 * rho_new / delta;
+    rho = rho_new;
+  }
+}
+
+constexpr int kCoarseFallbackDegree = 12;
+
+}  // namespace
+
+int cheb_setup(const Csr* A, const double* dinv, double fixed_lmax, double ratio, int degree, double* scratch,
+               double* coef, cudaStream_t st) {
+  if (degree < 1 || degree > kMaxChebDegree) { set_error("chebyshev degree out of range"); return SFEM_ERR_ARG; }
+  int np = 0;
+  if (A != nullptr) {
+    np = grid_for(A->nrows, kThreads, 4);
+    k_gershgorin<<<np, kThreads, 0, st>>>(A->nrows, A->rowptr, A->vals, dinv, scratch);
+    SFEM_LAUNCH_CHECK();
+  }
+  k_cheb_coef<<<1, 32, 0, st>>>(scratch, np, fixed_lmax, ratio, degree, coef);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int smooth(const Csr& A, const double* dinv, const double* coef, int degree, const double* b, double* x,
+           double* r, double* d0, double* d1, bool zero_init, cudaStream_t st, int nb) {
+  const int n = A.nrows * nb;
   if (zero_init) {
-    k_cheb_init0<<<grid_for(n, kThreads * 2), kThreads, 0, st>>>(n, dinv, b, r, d0, x, 1.0 / theta);
+    { Prof prof(PC_VEC, 32.0 * n + 8.0 * A.nrows, st);
+    k_cheb_init0<<<grid_for(n, kThreads * 2), kThreads, 0, st>>>(n, nb, dinv, b, r, d0, x, coef); }
     SFEM_LAUNCH_CHECK();
   } else {
-    SFEM_TRY(resid_d0(A, dinv, b, x, r, d0, 1.0 / theta, st));
+    SFEM_TRY(resid_d0(A, dinv, b, x, r, d0, coef + 1, st, nb));
   }
   if (degree <= 1) return vec_axpby(n, 1.0, d0, 1.0, x, st);
   double* dold = d0;
   double* dnew = d1;
   for (int i = 0; i < degree - 1; ++i) {
-    const double rho_new = 1.0 / (2.0 * sigma - rho);
-    SFEM_TRY(cheb_step(A, dinv, dold, dnew, r, x, rho_new * rho, 2.0 * rho_new / delta, i == degree - 2, st));
-    rho = rho_new;
+    SFEM_TRY(cheb_step(A, dinv, dold, dnew, r, x, coef + 2 + 2 * i, i == degree - 2, st, nb));
     double* t = dold; dold = dnew; dnew = t;
   }
   return SFEM_OK;
@@ -100,39 +119,19 @@ int smooth(const Csr& A, const double* dinv, double lmax, double ratio, int degr
 int mg_vcycle_level(sfem_mg* mg, int l, const double* b, double* x, cudaStream_t st) {
   MgLevel& L = mg->levels[l];
   const int last = (int)mg->levels.size() - 1;
+  const int nb = mg->nb;
   if (l == last) {
-    if (mg->coarse_inv != nullptr) return dense_gemv(L.A.nrows, mg->coarse_inv, b, x, st);
+    if (mg->coarse_inv != nullptr) return dense_gemv(L.A.nrows, mg->coarse_inv, b, x, st, nb);
     // no dense inverse given: a long smoothing sweep stands in for the coarse solve
-    return smooth(L.A, L.dinv, L.lmax, 30.0, 12, b, x, L.r, L.d0, L.d1, true, st);
+    return smooth(L.A, L.dinv, L.coef, kCoarseFallbackDegree, b, x, L.r, L.d0, L.d1, true, st, nb);
   }
-  SFEM_TRY(smooth(L.A, L.dinv, L.lmax, mg->ratio, mg->degree, b, x, L.r, L.d0, L.d1, true, st));
-  SFEM_TRY(spmv(L.A, x, b, L.r, 1, st));
+  SFEM_TRY(smooth(L.A, L.dinv, L.coef, mg->degree, b, x, L.r, L.d0, L.d1, true, st, nb));
+  SFEM_TRY(spmv(L.A, x, b, L.r, 1, st, nb));
   MgLevel& C = mg->levels[l + 1];
-  SFEM_TRY(spmv(L.R, L.r, nullptr, C.b, 0, st));
+  SFEM_TRY(spmv(L.R, L.r, nullptr, C.b, 0, st, nb));
   SFEM_TRY(mg_vcycle_level(mg, l + 1, C.b, C.x, st));
-  SFEM_TRY(spmv(L.P, C.x, nullptr, x, 2, st));
-  SFEM_TRY(smooth(L.A, L.dinv, L.lmax, mg->ratio, mg->degree, b, x, L.r, L.d0, L.d1, false, st));
-  return SFEM_OK;
-}
-
-int estimate_lambda_max(const Csr& A, const double* dinv, double* v, double* w, double* scratch, double* out,
-                        cudaStream_t st) {
-  const int n = A.nrows;
-  k_fill_pseudo<<<grid_for(n, kThreads * 2), kThreads, 0, st>>>(n, v);
-  SFEM_LAUNCH_CHECK();
-  double lam = 1.0, nv = 0.0;
-  SFEM_TRY(vec_dot_host(n, v, v, scratch, &nv, st));
-  for (int it = 0; it < 12; ++it) {
-    SFEM_TRY(spmv(A, v, nullptr, w, 0, st));
-    SFEM_TRY(vec_mul_scale(n, 1.0, dinv, w, w, st));
-    double nw = 0.0;
-    SFEM_TRY(vec_dot_host(n, w, w, scratch, &nw, st));
-    if (!(nw > 0.0) || !(nv > 0.0)) break;
-    lam = std::sqrt(nw / nv);
-    SFEM_TRY(vec_axpby(n, 1.0 / std::sqrt(nw), w, 0.0, v, st));
-    nv = 1.0;
-  }
-  *out = 1.1 * lam;
+  SFEM_TRY(spmv(L.P, C.x, nullptr, x, 2, st, nb));
+  SFEM_TRY(smooth(L.A, L.dinv, L.coef, mg->degree, b, x, L.r, L.d0, L.d1, false, st, nb));
   return SFEM_OK;
 }
 
@@ -147,25 +146,20 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
                          const int* h_P_nnz,
                          const int* const* h_P_rowptr, const int* const* h_P_cols, const double* const* h_P_vals,
                          const int* const* h_R_rowptr, const int* const* h_R_cols, const double* const* h_R_vals,
-                         const double* coarse_inv, int cheb_degree, double eig_ratio) {
-  if (nlevels < 1 || cheb_degree < 1 || !(eig_ratio > 1.0)) {
+                         const double* coarse_inv, int cheb_degree, double eig_ratio, int nb) {
+  if (nlevels < 1 || cheb_degree < 1 || cheb_degree > kMaxChebDegree || !(eig_ratio > 1.0) || (nb != 1 && nb != 2)) {
     set_error("sfem_mg_create: bad arguments");
     return nullptr;
   }
   sfem_mg* mg = new sfem_mg();
   mg->degree = cheb_degree;
   mg->ratio = eig_ratio;
+  mg->nb = nb;
   mg->coarse_inv = coarse_inv;
-  {
-    const char* e = std::getenv("SFEM_LMAX");
-    mg->use_power_iteration = (e != nullptr && std::string(e) == "power");
-  }
   mg->levels.resize(nlevels);
-  int nmax = 0;
   for (int l = 0; l < nlevels; ++l) {
     MgLevel& L = mg->levels[l];
     const int n = h_n[l];
-    if (n > nmax) nmax = n;
     L.A.nrows = L.A.ncols = n;
     L.A.nnz = h_A_nnz[l];
     L.A.rowptr = h_A_rowptr[l]; L.A.cols = h_A_cols[l]; L.A.vals = h_A_vals[l];
@@ -176,9 +170,10 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
       L.R.nrows = nc; L.R.ncols = n; L.R.nnz = h_P_nnz[l];
       L.R.rowptr = h_R_rowptr[l]; L.R.cols = h_R_cols[l]; L.R.vals = h_R_vals[l];
     }
-    const size_t bytes = (size_t)n * sizeof(double);
-    bool ok = cudaMalloc(&L.dinv, bytes) == cudaSuccess && cudaMalloc(&L.r, bytes) == cudaSuccess &&
-              cudaMalloc(&L.d0, bytes) == cudaSuccess && cudaMalloc(&L.d1, bytes) == cudaSuccess;
+    const size_t bytes = (size_t)n * nb * sizeof(double);
+    bool ok = cudaMalloc(&L.dinv, (size_t)n * sizeof(double)) == cudaSuccess && cudaMalloc(&L.r, bytes) == cudaSuccess &&
+              cudaMalloc(&L.d0, bytes) == cudaSuccess && cudaMalloc(&L.d1, bytes) == cudaSuccess &&
+              cudaMalloc(&L.coef, kChebCoefLen * sizeof(double)) == cudaSuccess;
     if (ok && l > 0) ok = cudaMalloc(&L.x, bytes) == cudaSuccess && cudaMalloc(&L.b, bytes) == cudaSuccess;
     if (!ok) {
       set_error("sfem_mg_create: device allocation failed");
@@ -197,14 +192,16 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
 int sfem_mg_setup(sfem_mg_t mg, void* stream) {
   if (!mg) { set_error("null mg handle"); return SFEM_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
-  for (size_t l = 0; l < mg->levels.size(); ++l) {
+  const size_t nl = mg->levels.size();
+  for (size_t l = 0; l < nl; ++l) {
     MgLevel& L = mg->levels[l];
     SFEM_TRY(extract_diag_inv(L.A, L.dinv, st));
-    if (l + 1 == mg->levels.size() && mg->coarse_inv != nullptr) { L.lmax = 2.0; continue; }
-    if (mg->use_power_iteration)
-      SFEM_TRY(estimate_lambda_max(L.A, L.dinv, L.d0, L.d1, mg->scratch, &L.lmax, st));
-    else
-      SFEM_TRY(gershgorin_lambda_max(L.A, L.dinv, mg->scratch, &L.lmax, st));
+    if (l + 1 == nl) {
+      if (mg->coarse_inv == nullptr)
+        SFEM_TRY(cheb_setup(&L.A, L.dinv, 0.0, 30.0, kCoarseFallbackDegree, mg->scratch, L.coef, st));
+      continue;
+    }
+    SFEM_TRY(cheb_setup(&L.A, L.dinv, 0.0, mg->ratio, mg->degree, mg->scratch, L.coef, st));
   }
   mg->ready = true;
   return SFEM_OK;
@@ -217,14 +214,20 @@ int sfem_mg_vcycle(sfem_mg_t mg, const double* b, double* x, void* stream) {
 
 int sfem_mg_lambda_max(sfem_mg_t mg, double* h_out) {
   if (!mg) { set_error("null mg handle"); return SFEM_ERR_ARG; }
-  for (size_t l = 0; l < mg->levels.size(); ++l) h_out[l] = mg->levels[l].lmax;
+  SFEM_CUDA(cudaDeviceSynchronize());
+  for (size_t l = 0; l < mg->levels.size(); ++l) {
+    h_out[l] = 2.0;
+    const bool dense_coarse = (l + 1 == mg->levels.size()) && mg->coarse_inv != nullptr;
+    if (!dense_coarse && mg->ready)
+      SFEM_CUDA(cudaMemcpy(&h_out[l], mg->levels[l].coef, sizeof(double), cudaMemcpyDeviceToHost));
+  }
   return SFEM_OK;
 }
 
 void sfem_mg_destroy(sfem_mg_t mg) {
   if (!mg) return;
   for (MgLevel& L : mg->levels) {
-    cudaFree(L.dinv); cudaFree(L.r); cudaFree(L.d0); cudaFree(L.d1); cudaFree(L.x); cudaFree(L.b);
+    cudaFree(L.dinv); cudaFree(L.r); cudaFree(L.d0); cudaFree(L.d1); cudaFree(L.x); cudaFree(L.b); cudaFree(L.coef);
   }
   cudaFree(mg->scratch);
   delete mg;

@@ -7,6 +7,9 @@
 
 namespace sfem {
 
+constexpr int kMaxChebDegree = 16;
+constexpr int kChebCoefLen = 2 + 2 * kMaxChebDegree;   // [lmax, 1/theta, (c1, c2) per step]
+
 struct MgLevel {
   Csr A, P, R;
   double* dinv = nullptr;
@@ -15,7 +18,7 @@ struct MgLevel {
   double* r = nullptr;
   double* d0 = nullptr;
   double* d1 = nullptr;
-  double lmax = 2.0;
+  double* coef = nullptr;  // device: Chebyshev coefficients of this level (written by sfem_mg_setup)
 };
 
 }  // namespace sfem
@@ -24,16 +27,20 @@ struct sfem_mg {
   std::vector<sfem::MgLevel> levels;
   const double* coarse_inv = nullptr;
   int degree = 2;
+  int nb = 1;                         // interleaved right-hand sides per V-cycle (1 or 2)
   double ratio = 8.0;
   double* scratch = nullptr;
   bool ready = false;
-  bool use_power_iteration = false;   // SFEM_LMAX=power: estimate instead of the Gershgorin bound
 };
 
 namespace sfem {
-int smooth(const Csr& A, const double* dinv, double lmax, double ratio, int degree, const double* b, double* x,
-           double* r, double* d0, double* d1, bool zero_init, cudaStream_t st);
+// Chebyshev-Jacobi sweep of `degree` steps on D^-1 A; coefficients are read from device memory
+// (coef, layout above) so that captured graphs stay valid when the operator values change.
+int smooth(const Csr& A, const double* dinv, const double* coef, int degree, const double* b, double* x,
+           double* r, double* d0, double* d1, bool zero_init, cudaStream_t st, int nb = 1);
+// coef <- coefficients for the window [lmax/ratio, lmax]; lmax = Gershgorin bound of D^-1 A when A is
+// given (scratch: kMaxPartials doubles), else fixed_lmax.  No host synchronisation.
+int cheb_setup(const Csr* A, const double* dinv, double fixed_lmax, double ratio, int degree, double* scratch,
+               double* coef, cudaStream_t st);
 int mg_vcycle_level(sfem_mg* mg, int l, const double* b, double* x, cudaStream_t st);
-int estimate_lambda_max(const Csr& A, const double* dinv, double* v, double* w, double* scratch, double* out,
-                        cudaStream_t st);
 }  // namespace sfem

@@ -1,0 +1,367 @@
+// Taylor-Hood Stokes solver (reference solvers.py:237-306: what dolfin's solve() hands to sparse LU).
+//
+// Unknowns: [ velocity, interleaved (ux_0, uy_0, ux_1, uy_1, ...) | pressure ].  The operator is kept
+// in block form
+//        [ K   0   Bx^T ]
+//    A = [ 0   K   By^T ]          K : scalar P2 stiffness (same for both components, read ONCE per
+//        [ Bx  By  0    ]              apply with the two components as interleaved right-hand sides)
+// whose values are copied out of the assembled Taylor-Hood CSR (dolfin clique pattern, Dirichlet rows
+// and columns eliminated), i.e. it is the assembled matrix minus its structural zeros.
+//
+// Preconditioned MINRES with the block-diagonal SPD preconditioner
+//    M^-1 = diag( V-cycle(K) [both components in one 2-RHS cycle],  S^-1 ),
+//    S^-1 = Cheb_4(Mp) + Z C Z^T,
+// Mp = P1 pressure mass matrix (4 Chebyshev-Jacobi steps ~ exact), Z = 1-D hat functions in x over the
+// channel and C >= 0 a small dense matrix built on the host from the lubrication (Reynolds) operator:
+// it lifts the O((H/L)^2) eigenvalues of the long-channel Schur complement that would otherwise
+// cost MINRES ~60% more iterations.  C = 0 (nz = 0) gives the classical mass-matrix preconditioner.
+//
+// The iteration body is a fixed launch sequence with all recurrence scalars in device memory; it is
+// captured into two CUDA graphs (even / odd buffer parity) and replayed.  The host polls the
+// residual estimate one iteration late, so the device never waits for the host.
+#include "sfem_mg.h"
+#include "sfem_graph.h"
+
+#include <cmath>
+#include <vector>
+
+namespace sfem {
+
+namespace {
+
+// S: 0 gamma_prev, 1 gamma, 3 delta, 4 eta, 5 c_prev, 6 c, 7 s_prev, 8 s, 9 a1, 10 a2, 11 a3,
+//    12 xcoef, 13 gamma1, 14 delta/gamma, 15 gamma/gamma_prev, 16 1/gamma (of the current z)
+__global__ void k_sm_init(const double* __restrict__ partial, int np, double* __restrict__ S) {
+  __shared__ double sh[33];
+  const double t = block_sum_array(partial, np, sh);
+  if (threadIdx.x == 0) {
+    const double gamma = sqrt(fabs(t));
+    S[0] = 1.0; S[1] = gamma; S[2] = 0.0; S[3] = 0.0; S[4] = gamma;
+    S[5] = 1.0; S[6] = 1.0; S[7] = 0.0; S[8] = 0.0; S[13] = gamma;
+    S[16] = (gamma > 0.0) ? 1.0 / gamma : 0.0;
+  }
+}
+
+__global__ void k_sm_delta(const double* __restrict__ pu, int npu, const double* __restrict__ pp, int npp,
+                           double* __restrict__ S) {
+  __shared__ double sh[33];
+  const double du = block_sum_array(pu, npu, sh);
+  const double dp = block_sum_array(pp, npp, sh);
+  if (threadIdx.x == 0) {
+    const double gamma = S[1];
+    const double invg = (gamma > 0.0) ? 1.0 / gamma : 0.0;
+    const double delta = (du + dp) * invg * invg;
+    S[3] = delta;
+    S[14] = delta * invg;
+    S[15] = gamma / S[0];
+    S[16] = invg;
+  }
+}
+
+// v_prev <- Az/gamma - (delta/gamma) v - (gamma/gamma_prev) v_prev     (then v_prev is the new v)
+__global__ void k_sm_vnext(int n, const double* __restrict__ S, const double* __restrict__ Az,
+                           const double* __restrict__ v, double* __restrict__ v_prev) {
+  const double invg = S[16], a = S[14], b = S[15];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    v_prev[i] = Az[i] * invg - a * v[i] - b * v_prev[i];
+}
+
+__global__ void k_sm_rot(const double* __restrict__ partial, int np, double* __restrict__ S) {
+  __shared__ double sh[33];
+  const double t = block_sum_array(partial, np, sh);
+  if (threadIdx.x == 0) {
+    const double gamma = S[1], delta = S[3], eta = S[4];
+    const double c_prev = S[5], c = S[6], s_prev = S[7], s = S[8];
+    const double gamma_next = sqrt(fabs(t));
+    const double a0 = c * delta - c_prev * s * gamma;
+    const double a1 = sqrt(a0 * a0 + gamma_next * gamma_next);
+    const double a2 = s * delta + c_prev * c * gamma;
+    const double a3 = s_prev * gamma;
+    const double c_next = a0 / a1, s_next = gamma_next / a1;
+    S[9] = a1; S[10] = a2; S[11] = a3;
+    S[12] = c_next * eta;
+    S[4] = -s_next * eta;
+    S[0] = gamma; S[1] = gamma_next;
+    S[5] = c; S[6] = c_next; S[7] = s; S[8] = s_next;
+  }
+}
+
+// w_prev <- (z/gamma - a3 w_prev - a2 w)/a1 ; x += xcoef w_prev        (then w_prev is the new w)
+__global__ void k_sm_wx(int n, const double* __restrict__ S, const double* __restrict__ z,
+                        const double* __restrict__ w, double* __restrict__ w_prev, double* __restrict__ x) {
+  const double invg = S[16], inv = 1.0 / S[9], a2 = S[10], a3 = S[11], xc = S[12];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double wn = (z[i] * invg - a3 * w_prev[i] - a2 * w[i]) * inv;
+    w_prev[i] = wn;
+    x[i] = fma(xc, wn, x[i]);
+  }
+}
+
+// out = a - b, partial sums of out.out
+__global__ void __launch_bounds__(kThreads) k_sub_norm(int n, const double* __restrict__ a, const double* __restrict__ b,
+                                                       double* __restrict__ out, double* __restrict__ partial) {
+  __shared__ double sh[33];
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double r = a[i] - b[i];
+    out[i] = r;
+    acc = fma(r, r, acc);
+  }
+  const double t = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+// ---- coarse pressure correction  z_p += Z C Z^T r_p
+// stage 1: partial[k][chunk] = sum over a chunk of row k of Z^T (CSR) of val * r[col]
+__global__ void __launch_bounds__(kThreads) k_zt_partial(const int* __restrict__ zt_rowptr, const int* __restrict__ zt_cols,
+                                                         const double* __restrict__ zt_vals, const double* __restrict__ r,
+                                                         int nchunks, double* __restrict__ partial) {
+  __shared__ double sh[33];
+  const int k = blockIdx.y;
+  const int s = zt_rowptr[k], e = zt_rowptr[k + 1];
+  const int len = e - s;
+  const int per = (len + nchunks - 1) / nchunks;
+  const int c0 = s + blockIdx.x * per;
+  const int c1 = min(e, c0 + per);
+  double acc = 0.0;
+  for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) acc = fma(zt_vals[i], r[zt_cols[i]], acc);
+  const double t = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[(size_t)k * nchunks + blockIdx.x] = t;
+}
+
+// stage 2 (one block): t = sum of partials per row; coef = C t
+__global__ void __launch_bounds__(kThreads) k_zt_coef(int nz, int nchunks, const double* __restrict__ partial,
+                                                      const double* __restrict__ Cc, double* __restrict__ coef) {
+  extern __shared__ double t[];
+  for (int k = threadIdx.x; k < nz; k += blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += partial[(size_t)k * nchunks + c];
+    t[k] = s;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nz; k += blockDim.x) {
+    double s = 0.0;
+    for (int j = 0; j < nz; ++j) s = fma(Cc[(size_t)k * nz + j], t[j], s);
+    coef[k] = s;
+  }
+}
+
+// stage 3: z[i] += w_i coef[idx_i] + (1 - w_i) coef[idx_i + 1]
+__global__ void k_z_apply(int nv, const int* __restrict__ zidx, const double* __restrict__ zw,
+                          const double* __restrict__ coef, double* __restrict__ z) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+    const int k = zidx[i];
+    const double w = zw[i];
+    z[i] += w * coef[k] + (1.0 - w) * coef[k + 1];
+  }
+}
+
+constexpr int kZtChunks = 16;
+
+}  // namespace
+
+}  // namespace sfem
+
+using namespace sfem;
+
+struct sfem_stokes {
+  int n2 = 0, nv = 0, n = 0;
+  Csr K, B, BT, Mp;
+  sfem_mg* mg = nullptr;
+  int nz = 0;
+  const int* zt_rowptr = nullptr; const int* zt_cols = nullptr; const double* zt_vals = nullptr;
+  const int* zidx = nullptr; const double* zw = nullptr; const double* Cc = nullptr;
+  // owned work space
+  double* buf = nullptr;
+  double *v[2] = {nullptr, nullptr}, *z[2] = {nullptr, nullptr}, *w[2] = {nullptr, nullptr};
+  double *Az = nullptr, *mp_dinv = nullptr, *mp_r = nullptr, *mp_d0 = nullptr, *mp_d1 = nullptr;
+  double *part_u = nullptr, *part_p = nullptr, *part = nullptr, *zt_part = nullptr, *zcoef = nullptr, *S = nullptr;
+  double* mp_coef = nullptr;
+  double* h_pin = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  WorkStream ws;
+  GraphExec iter[2];
+  const double* graph_x = nullptr;     // the x pointer baked into the graphs
+  int npu = 0, npp = 0;
+};
+
+namespace {
+
+int st_apply(sfem_stokes* h, const double* zin, double* y, cudaStream_t st) {
+  const size_t nu = 2 * (size_t)h->n2;
+  SFEM_TRY(stokes_apply_u(h->K, h->BT, zin, zin + nu, y, h->part_u, &h->npu, st));
+  SFEM_TRY(spmv_dot(h->B, zin, y + nu, h->part_p, &h->npp, st, 1, zin + nu));
+  return SFEM_OK;
+}
+
+int st_precond(sfem_stokes* h, const double* r, double* out, cudaStream_t st) {
+  const size_t nu = 2 * (size_t)h->n2;
+  SFEM_TRY(mg_vcycle_level(h->mg, 0, r, out, st));
+  // P1 mass matrix with Jacobi scaling has its spectrum in [1/2, 2]: 4 Chebyshev steps ~ exact solve
+  SFEM_TRY(smooth(h->Mp, h->mp_dinv, h->mp_coef, 4, r + nu, out + nu, h->mp_r, h->mp_d0, h->mp_d1, true, st));
+  if (h->nz > 0) {
+    dim3 grid(kZtChunks, h->nz);
+    k_zt_partial<<<grid, kThreads, 0, st>>>(h->zt_rowptr, h->zt_cols, h->zt_vals, r + nu, kZtChunks, h->zt_part);
+    SFEM_LAUNCH_CHECK();
+    k_zt_coef<<<1, kThreads, h->nz * sizeof(double), st>>>(h->nz, kZtChunks, h->zt_part, h->Cc, h->zcoef);
+    SFEM_LAUNCH_CHECK();
+    { Prof prof(PC_VEC, 28.0 * h->nv, st);
+    k_z_apply<<<grid_for(h->nv, kThreads * 2), kThreads, 0, st>>>(h->nv, h->zidx, h->zw, h->zcoef, out + nu); }
+    SFEM_LAUNCH_CHECK();
+  }
+  return SFEM_OK;
+}
+
+// one MINRES iteration with buffer parity q (z[q] holds the current unscaled z, v[q] the current v)
+int st_iteration(sfem_stokes* h, int q, double* x, cudaStream_t st) {
+  const int n = h->n;
+  const int gv = grid_for(n, kThreads * 4);
+  double* zc = h->z[q];     double* zn = h->z[q ^ 1];
+  double* vc = h->v[q];     double* vp = h->v[q ^ 1];
+  double* wc = h->w[q];     double* wp = h->w[q ^ 1];
+  SFEM_TRY(st_apply(h, zc, h->Az, st));
+  k_sm_delta<<<1, kThreads, 0, st>>>(h->part_u, h->npu, h->part_p, h->npp, h->S);
+  SFEM_LAUNCH_CHECK();
+  { Prof prof(PC_VEC, 32.0 * n, st);
+  k_sm_vnext<<<gv, kThreads, 0, st>>>(n, h->S, h->Az, vc, vp); }
+  SFEM_LAUNCH_CHECK();
+  SFEM_TRY(st_precond(h, vp, zn, st));                       // vp now holds v_{j+1}
+  int np = 0;
+  SFEM_TRY(vec_dot_partial(n, zn, vp, h->part, &np, st));
+  k_sm_rot<<<1, kThreads, 0, st>>>(h->part, np, h->S);
+  SFEM_LAUNCH_CHECK();
+  { Prof prof(PC_VEC, 48.0 * n, st);
+  k_sm_wx<<<gv, kThreads, 0, st>>>(n, h->S, zc, wc, wp, x); }
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+sfem_stokes_t sfem_stokes_create(int n2, int nv,
+                                 int K_nnz, const int* K_rowptr, const int* K_cols, const double* K_vals,
+                                 int B_nnz, const int* B_rowptr, const int* B_cols, const double* B_vals,
+                                 const int* BT_rowptr, const int* BT_cols, const double* BT_vals,
+                                 int Mp_nnz, const int* Mp_rowptr, const int* Mp_cols, const double* Mp_vals,
+                                 sfem_mg_t mg,
+                                 int nz, const int* zt_rowptr, const int* zt_cols, const double* zt_vals,
+                                 const int* zidx, const double* zw, const double* Cc) {
+  if (n2 <= 0 || nv <= 0 || !mg || mg->nb != 2 || mg->levels[0].A.nrows != n2 || nz < 0 || nz > 1024) {
+    set_error("sfem_stokes_create: bad arguments (the multigrid handle must be built with nb = 2 on the velocity block)");
+    return nullptr;
+  }
+  sfem_stokes* h = new sfem_stokes();
+  h->n2 = n2; h->nv = nv; h->n = 2 * n2 + nv;
+  h->K.nrows = h->K.ncols = n2; h->K.nnz = K_nnz; h->K.rowptr = K_rowptr; h->K.cols = K_cols; h->K.vals = K_vals;
+  h->B.nrows = nv; h->B.ncols = 2 * n2; h->B.nnz = B_nnz; h->B.rowptr = B_rowptr; h->B.cols = B_cols; h->B.vals = B_vals;
+  h->BT.nrows = 2 * n2; h->BT.ncols = nv; h->BT.nnz = B_nnz; h->BT.rowptr = BT_rowptr; h->BT.cols = BT_cols; h->BT.vals = BT_vals;
+  h->Mp.nrows = h->Mp.ncols = nv; h->Mp.nnz = Mp_nnz; h->Mp.rowptr = Mp_rowptr; h->Mp.cols = Mp_cols; h->Mp.vals = Mp_vals;
+  h->mg = mg;
+  h->nz = nz; h->zt_rowptr = zt_rowptr; h->zt_cols = zt_cols; h->zt_vals = zt_vals; h->zidx = zidx; h->zw = zw; h->Cc = Cc;
+  const size_t nn = (size_t)h->n;
+  const size_t total = 7 * nn + 4 * (size_t)nv + 3 * (size_t)kMaxPartials + (size_t)(nz + 1) * (kZtChunks + 1) + kChebCoefLen + 64;
+  if (cudaMalloc(&h->buf, total * sizeof(double)) != cudaSuccess || cudaMallocHost(&h->h_pin, 8 * sizeof(double)) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming) != cudaSuccess || h->ws.init() != SFEM_OK) {
+    set_error("sfem_stokes_create: allocation failed");
+    sfem_stokes_destroy(h);
+    return nullptr;
+  }
+  double* p = h->buf;
+  h->v[0] = p; p += nn; h->v[1] = p; p += nn; h->z[0] = p; p += nn; h->z[1] = p; p += nn;
+  h->w[0] = p; p += nn; h->w[1] = p; p += nn; h->Az = p; p += nn;
+  h->mp_dinv = p; p += nv; h->mp_r = p; p += nv; h->mp_d0 = p; p += nv; h->mp_d1 = p; p += nv;
+  h->part_u = p; p += kMaxPartials; h->part_p = p; p += kMaxPartials; h->part = p; p += kMaxPartials;
+  h->zt_part = p; p += (size_t)(nz + 1) * kZtChunks; h->zcoef = p; p += nz + 1; h->mp_coef = p; p += kChebCoefLen; h->S = p;
+  return h;
+}
+
+void sfem_stokes_destroy(sfem_stokes_t h) {
+  if (!h) return;
+  h->iter[0].reset(); h->iter[1].reset();
+  if (h->ev[0]) cudaEventDestroy(h->ev[0]);
+  if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  cudaFree(h->buf);
+  h->ws.destroy();
+  delete h;
+}
+
+int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, int maxit, double* h_info, void* stream) {
+  if (!h || !h->mg->ready) { set_error("stokes solve: handle / multigrid not set up"); return SFEM_ERR_ARG; }
+  cudaStream_t user = (cudaStream_t)stream;
+  SFEM_TRY(h->ws.fork(user));
+  cudaStream_t st = h->ws.s;
+  const int n = h->n;
+  const size_t nn = (size_t)n;
+  const int gv = grid_for(n, kThreads * 4, 4);
+  SFEM_TRY(extract_diag_inv(h->Mp, h->mp_dinv, st));
+  SFEM_TRY(cheb_setup(nullptr, nullptr, 2.0, 4.0, 4, h->part, h->mp_coef, st));
+  double bb = 0.0;
+  SFEM_TRY(vec_dot_host(n, b, b, h->part, &bb, st));
+  const double bnorm = std::sqrt(bb);
+  // v = b - A x ; z = M^-1 v ; gamma_1
+  SFEM_TRY(st_apply(h, x, h->Az, st));
+  k_sub_norm<<<gv, kThreads, 0, st>>>(n, b, h->Az, h->v[0], h->part);
+  SFEM_LAUNCH_CHECK();
+  SFEM_CUDA(cudaMemsetAsync(h->v[1], 0, nn * sizeof(double), st));
+  SFEM_CUDA(cudaMemsetAsync(h->w[0], 0, nn * sizeof(double), st));
+  SFEM_CUDA(cudaMemsetAsync(h->w[1], 0, nn * sizeof(double), st));
+  SFEM_TRY(st_precond(h, h->v[0], h->z[0], st));
+  int np = 0;
+  SFEM_TRY(vec_dot_partial(n, h->z[0], h->v[0], h->part, &np, st));
+  k_sm_init<<<1, kThreads, 0, st>>>(h->part, np, h->S);
+  SFEM_LAUNCH_CHECK();
+  double gamma1 = 0.0;
+  SFEM_CUDA(cudaMemcpyAsync(&gamma1, h->S + 13, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SFEM_CUDA(cudaStreamSynchronize(st));
+  int it = 0;
+  double eta = gamma1;
+  const bool use_graph = graphs_enabled();
+  if (gamma1 > 0.0 && maxit > 0) {
+    if (use_graph && (h->iter[0].exec == nullptr || h->graph_x != x)) {
+      for (int q = 0; q < 2; ++q) SFEM_TRY(graph_capture(st, h->iter[q], [&]() { return st_iteration(h, q, x, st); }));
+      h->graph_x = x;
+    }
+    const double target = rtol * gamma1;
+    bool done = false;
+    for (it = 1; it <= maxit && !done; ++it) {
+      const int q = (it - 1) & 1;
+      if (use_graph) SFEM_TRY(graph_launch(h->iter[q], st));
+      else SFEM_TRY(st_iteration(h, q, x, st));
+      SFEM_CUDA(cudaMemcpyAsync(h->h_pin + (it & 1), h->S + 4, sizeof(double), cudaMemcpyDeviceToHost, st));
+      SFEM_CUDA(cudaEventRecord(h->ev[it & 1], st));
+      if (it > 1) {                                      // poll the previous iteration (device keeps running)
+        SFEM_CUDA(cudaEventSynchronize(h->ev[(it - 1) & 1]));
+        eta = h->h_pin[(it - 1) & 1];
+        if (!(eta == eta)) { h->ws.join(user); set_error("minres: NaN residual"); return SFEM_ERR_NOCONV; }
+        if (std::fabs(eta) <= target) done = true;       // iteration `it` is already queued: keep its update
+      }
+    }
+    --it;
+    SFEM_CUDA(cudaEventSynchronize(h->ev[it & 1]));
+    eta = h->h_pin[it & 1];
+  }
+  // true residual
+  SFEM_TRY(st_apply(h, x, h->Az, st));
+  k_sub_norm<<<gv, kThreads, 0, st>>>(n, b, h->Az, h->Az, h->part);
+  SFEM_LAUNCH_CHECK();
+  double rr = 0.0;
+  {
+    double* out = h->part + kMaxPartials - 1;            // last slot of the partial array is free (gv < kMaxPartials)
+    // reuse the generic one-block sum
+    SFEM_TRY(vec_sum_partials(h->part, gv, out, st));
+    SFEM_CUDA(cudaMemcpyAsync(&rr, out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SFEM_CUDA(cudaStreamSynchronize(st));
+  }
+  SFEM_TRY(h->ws.join(user));
+  const double rel = (bnorm > 0.0) ? std::sqrt(rr) / bnorm : std::sqrt(rr);
+  h_info[0] = it; h_info[1] = rel;
+  h_info[2] = (gamma1 == 0.0 || std::fabs(eta) <= rtol * gamma1) ? 1.0 : 0.0;
+  h_info[3] = (gamma1 > 0.0) ? std::fabs(eta) / gamma1 : 0.0;
+  return SFEM_OK;
+}
+
+}  // extern "C"

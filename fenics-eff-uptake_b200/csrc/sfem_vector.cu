@@ -2,8 +2,10 @@
 // coarse-level gemv, concentration post-processing (solvers.py:86-105,154-173).
 #include "sfem_common.cuh"
 #include "sfem_internal.h"
+#include "sfem_graph.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -35,6 +37,16 @@ std::atomic<bool> g_prof_on{false};
 std::vector<ProfRec> g_prof;
 size_t g_prof_max = 0;
 }  // namespace
+
+bool profiling_active() { return g_prof_on.load(std::memory_order_relaxed); }
+bool graphs_enabled() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("SFEM_GRAPHS");
+    env = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return env == 1 && !profiling_active();
+}
 
 Prof::Prof(int cat, double bytes, cudaStream_t s) : idx(-1), st(s) {
   if (!g_prof_on.load(std::memory_order_relaxed) || g_prof.size() >= g_prof_max) return;
@@ -91,16 +103,26 @@ __global__ void k_diag_inv(int n, const int* __restrict__ rowptr, const int* __r
 }
 
 // y = M x for a small dense row-major matrix (coarsest multigrid level): one warp per row.
+template <int NB>
 __global__ void __launch_bounds__(kThreads) k_dense_gemv(int n, const double* __restrict__ M,
                                                          const double* __restrict__ x, double* __restrict__ y) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n; row += gridDim.x * warps_per_block) {
     const double* m = M + (size_t)row * n;
-    double acc = 0.0;
-    for (int j = lane; j < n; j += 32) acc = fma(m[j], x[j], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) y[row] = acc;
+    double acc[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) acc[c] = 0.0;
+    for (int j = lane; j < n; j += 32) {
+      const double mj = m[j];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] = fma(mj, x[(size_t)j * NB + c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      const double t = warp_sum(acc[c]);
+      if (lane == 0) y[(size_t)row * NB + c] = t;
+    }
   }
 }
 
@@ -183,6 +205,12 @@ int vec_dot_partial(int n, const double* x, const double* y, double* partial, in
   return SFEM_OK;
 }
 
+int vec_sum_partials(const double* partial, int n, double* out, cudaStream_t st) {
+  k_sum_partials<<<1, kThreads, 0, st>>>(partial, n, out);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
 // scratch: kMaxPartials + 1 doubles
 int vec_dot_host(int n, const double* x, const double* y, double* scratch, double* h_out, cudaStream_t st) {
   int np = 0;
@@ -201,10 +229,11 @@ int extract_diag_inv(const Csr& A, double* dinv, cudaStream_t st) {
   return SFEM_OK;
 }
 
-int dense_gemv(int n, const double* M, const double* x, double* y, cudaStream_t st) {
+int dense_gemv(int n, const double* M, const double* x, double* y, cudaStream_t st, int nb) {
   if (n <= 0) return SFEM_OK;
-  Prof prof(PC_OTHER, 8.0 * n * n + 16.0 * n, st);
-  k_dense_gemv<<<grid_for(n, kThreads / 32), kThreads, 0, st>>>(n, M, x, y);
+  Prof prof(PC_OTHER, 8.0 * n * n + 16.0 * n * nb, st);
+  if (nb == 2) k_dense_gemv<2><<<grid_for(n, kThreads / 32), kThreads, 0, st>>>(n, M, x, y);
+  else k_dense_gemv<1><<<grid_for(n, kThreads / 32), kThreads, 0, st>>>(n, M, x, y);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

@@ -33,6 +33,7 @@ SIGNATURES = {
     'sfem_profile_start': (_i, [_i]),
     'sfem_profile_stop': (_i, [_i, C.POINTER(_i), C.POINTER(_d), C.POINTER(C.c_float)]),
     'sfem_spmv_csr_f64': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _i, _p]),
+    'sfem_spmv_csr_f64_nb': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     'sfem_spmv_csr_f64_staged': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     'sfem_elem_p2_advdiff': (_i, [_i, _p, _p, _d, _p, _p, _p, _p]),
     'sfem_elem_p1_advdiff': (_i, [_i, _p, _p, _d, _p, _p, _i, _p, _p]),
@@ -42,6 +43,9 @@ SIGNATURES = {
     'sfem_facet_p1_robin': (_i, [_i, _p, _p, _d, _p, _i, _p, _p]),
     'sfem_gather_csr': (_i, [_i, _p, _p, _p, _p, _p]),
     'sfem_apply_dirichlet': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _i, _p]),
+    'sfem_csr_extract': (_i, [_i, _p, _p, _p, _p]),
+    'sfem_vec_interleave2': (_i, [_i, _p, _p, _p, _p]),
+    'sfem_vec_deinterleave2': (_i, [_i, _p, _p, _p, _p]),
     'sfem_vec_axpby': (_i, [_i, _d, _p, _d, _p, _p]),
     'sfem_vec_dot': (_i, [_i, _p, _p, C.POINTER(_d), _p]),
     'sfem_vec_set': (_i, [_i, _d, _p, _p]),
@@ -51,15 +55,17 @@ SIGNATURES = {
     'sfem_postprocess_concentration': (_i, [_i, _p, _i, C.POINTER(_d), _p]),
     'sfem_mg_create': (_p, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p),
                             C.POINTER(_i), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p),
-                            C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), _p, _i, _d]),
+                            C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), _p, _i, _d, _i]),
     'sfem_mg_setup': (_i, [_p, _p]),
     'sfem_mg_vcycle': (_i, [_p, _p, _p, _p]),
     'sfem_mg_lambda_max': (_i, [_p, C.POINTER(_d)]),
     'sfem_mg_destroy': (None, [_p]),
     'sfem_krylov_cg': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _d, _i, C.POINTER(_d), _p]),
     'sfem_krylov_fgmres': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _d, _i, _i, C.POINTER(_d), _p]),
-    'sfem_krylov_minres_stokes': (_i, [_i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _d, _i,
-                                       C.POINTER(_d), _p]),
+    'sfem_stokes_create': (_p, [_i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p,
+                                _i, _p, _p, _p, _p, _p, _p]),
+    'sfem_stokes_solve': (_i, [_p, _p, _p, _d, _i, C.POINTER(_d), _p]),
+    'sfem_stokes_destroy': (None, [_p]),
     'sfem_facet_functionals': (_i, [_i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _d, _d, _p, _p, _p]),
     'sfem_cell_functionals': (_i, [_i, _p, _p, _p, _i, _p, _p, _p]),
 }

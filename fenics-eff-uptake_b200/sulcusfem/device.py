@@ -96,11 +96,14 @@ class DeviceCsr:
         rpa = np.asarray(rowptr, dtype=np.int64)
         self.tile_cap = int(np.max(rpa[r1] - (rpa[r0] & ~3))) if self.nrows else 0
 
-    def spmv(self, x, y=None, b=None, mode=0, staged=False, stages=3):
+    def spmv(self, x, y=None, b=None, mode=0, staged=False, stages=3, nb=1):
         ctx = self.ctx
         if y is None:
-            y = ctx.empty(self.nrows)
-        if staged:
+            y = ctx.empty(self.nrows * nb)
+        if nb != 1 or self.nrows != self.ncols:
+            capi.check(ctx.lib.sfem_spmv_csr_f64_nb(self.nrows, self.ncols, self.nnz, P(self.rowptr), P(self.cols), P(self.vals),
+                                                    P(x), P(b), P(y), mode, nb, ctx.stream), 'sfem_spmv_csr_f64_nb')
+        elif staged:
             capi.check(ctx.lib.sfem_spmv_csr_f64_staged(self.nrows, self.nnz, P(self.rowptr), P(self.cols), P(self.vals_buf),
                                                         P(x), P(b), P(y), mode, self.tile_rows, self.tile_cap, stages,
                                                         ctx.stream), 'sfem_spmv_csr_f64_staged')
@@ -228,8 +231,9 @@ class Multigrid:
     """sfem_mg handle over [system level, P1 levels...]."""
 
     def __init__(self, ctx: Context, levels: List[ScalarLevel], transfers: List[DeviceTransfer],
-                 cheb_degree=2, eig_ratio=8.0):
+                 cheb_degree=2, eig_ratio=8.0, nb=1):
         self.ctx, self.levels, self.transfers = ctx, levels, transfers
+        self.nb = int(nb)
         nl = len(levels)
         self.coarse_inv = ctx.zeros(levels[-1].n ** 2) if nl > 1 else None
         IntArr, PtrArr = C.c_int * nl, C.c_void_p * nl
@@ -246,7 +250,7 @@ class Multigrid:
         k = self._keep
         self.handle = ctx.lib.sfem_mg_create(nl, k['n'], k['annz'], k['arp'], k['ac'], k['av'], k['pnnz'], k['prp'], k['pc'],
                                              k['pv'], k['rrp'], k['rc'], k['rv'], P(self.coarse_inv), int(cheb_degree),
-                                             float(eig_ratio))
+                                             float(eig_ratio), self.nb)
         if not self.handle:
             raise capi.SulcusFemError("sfem_mg_create failed: " + ctx.lib.sfem_last_error().decode())
 
@@ -259,7 +263,7 @@ class Multigrid:
         capi.check(ctx.lib.sfem_mg_setup(self.handle, ctx.stream), 'sfem_mg_setup')
 
     def vcycle(self, b, x=None):
-        x = self.ctx.empty(self.levels[0].n) if x is None else x
+        x = self.ctx.empty(self.levels[0].n * self.nb) if x is None else x
         capi.check(self.ctx.lib.sfem_mg_vcycle(self.handle, P(b), P(x), self.ctx.stream), 'sfem_mg_vcycle')
         return x
 
@@ -282,7 +286,7 @@ class ScalarProblem:
 
     def __init__(self, mesh: HostMesh, bc_markers: np.ndarray, dirichlet_ids=(1, 2), robin_id: Optional[int] = 4,
                  hierarchy: Optional[hy.Hierarchy] = None, ctx: Optional[Context] = None,
-                 cheb_degree=2, eig_ratio=8.0):
+                 cheb_degree=2, eig_ratio=8.0, nb=1):
         self.ctx = ctx or Context.get()
         self.mesh = mesh
         self.hierarchy = hierarchy or hy.build_hierarchy(mesh)
@@ -294,7 +298,7 @@ class ScalarProblem:
             self.levels.append(ScalarLevel(self.ctx, m, mk, 1, dirichlet_ids, robin_id))
         self.transfers = [DeviceTransfer(self.ctx, T, self.levels[l].bc_flag_host, self.levels[l + 1].bc_flag_host)
                           for l, T in enumerate(H.transfers)]
-        self.mg = Multigrid(self.ctx, self.levels, self.transfers, cheb_degree, eig_ratio)
+        self.mg = Multigrid(self.ctx, self.levels, self.transfers, cheb_degree, eig_ratio, nb)
         self.n = self.fine.n
         self.x = self.ctx.zeros(self.n)
         self.last_info = None
@@ -318,13 +322,16 @@ class ScalarProblem:
         return out
 
     def assemble(self, D, ux=None, uy=None, mu_const=0.0, mu_nodal=None, clamp=False, bc_values=None,
-                 bc_mode=1, robin=True, coarse_mu: Optional[float] = None):
-        """Assemble the system level (+ BCs) and rediscretise the multigrid levels."""
+                 bc_mode=1, robin=True, coarse_mu: Optional[float] = None, fine=True):
+        """Assemble the system level (+ BCs) and rediscretise the multigrid levels.  ``fine=False``:
+        the system-level values were written by the caller (Stokes: K extracted from the Taylor-Hood
+        matrix); only the coarse levels are assembled."""
         f = self.fine
-        f.set_bc_values(bc_values if bc_values is not None else {i: 0.0 for i in f.bc_dofs})
-        f.assemble(D, ux, uy, mu_const, mu_nodal, clamp, robin=robin)
-        f.rhs.zero_()
-        f.apply_bc(bc_mode)
+        if fine:
+            f.set_bc_values(bc_values if bc_values is not None else {i: 0.0 for i in f.bc_dofs})
+            f.assemble(D, ux, uy, mu_const, mu_nodal, clamp, robin=robin)
+            f.rhs.zero_()
+            f.apply_bc(bc_mode)
         self.bc_mode = bc_mode
         vel = self._coarse_velocity(ux, uy) if ux is not None else [(None, None)] * len(self.transfers)
         # coarse levels are preconditioner data only: a spatially varying mu is represented there by
@@ -361,41 +368,86 @@ class ScalarProblem:
 
 
 class StokesProblem:
-    """Taylor-Hood Stokes system (solvers.py:237-306) with MINRES + block-diagonal multigrid."""
+    """Taylor-Hood Stokes system (solvers.py:237-306): assembled with dolfin's clique pattern, solved in
+    block form (K shared by both velocity components, B, B^T) by ``sfem_stokes_solve``."""
 
     def __init__(self, mesh: HostMesh, bc_markers: np.ndarray, hierarchy: Optional[hy.Hierarchy] = None,
-                 ctx: Optional[Context] = None, velocity_ids=(1, 4, 3)):
+                 ctx: Optional[Context] = None, velocity_ids=(1, 4, 3), schur_correction=True):
         self.ctx = ctx or Context.get()
         ctx = self.ctx
         self.mesh = mesh
-        self.n2 = dm.p2_num_dofs(mesh)
-        self.nv = mesh.num_vertices
-        self.n = 2 * self.n2 + self.nv
+        self.n2 = n2 = dm.p2_num_dofs(mesh)
+        self.nv = nv = mesh.num_vertices
+        self.n = 2 * n2 + nv
         self.nc = mesh.num_cells
         cd = dm.th_cell_dofs(mesh)
         self.pattern = dm.build_pattern(self.n, self.n, [(cd, cd)])
-        self.A = DeviceCsr(ctx, self.n, self.n, self.pattern.rowptr, self.pattern.cols)
-        self.contrib_ptr = ctx.up(self.pattern.contrib_ptr, np.int32)
-        self.contrib_code = ctx.up(self.pattern.contrib_code, np.int32)
-        self.E = ctx.zeros(self.pattern.buffer_len)
+        pat = self.pattern
+        self.A = DeviceCsr(ctx, self.n, self.n, pat.rowptr, pat.cols)
+        self.contrib_ptr = ctx.up(pat.contrib_ptr, np.int32)
+        self.contrib_code = ctx.up(pat.contrib_code, np.int32)
+        self.E = ctx.zeros(pat.buffer_len)
         self.geo = ctx.up(cell_geometry(mesh), np.float64)
-        # velocity preconditioner: scalar stiffness hierarchy with the velocity Dirichlet set
+        # velocity block: scalar stiffness hierarchy with the velocity Dirichlet set, 2 interleaved RHS
         self.vel = ScalarProblem(mesh, bc_markers, dirichlet_ids=tuple(velocity_ids), robin_id=None,
-                                 hierarchy=hierarchy, ctx=ctx)
+                                 hierarchy=hierarchy, ctx=ctx, nb=2)
+        # ---- block views of the assembled matrix: slot maps TH CSR -> K / B / B^T (host, once)
+        rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(pat.rowptr.astype(np.int64)))
+        cols = pat.cols.astype(np.int64)
+        kslot = np.flatnonzero((rows < n2) & (cols < n2))
+        Kp = self.vel.fine.pattern
+        if len(kslot) != Kp.nnz or not np.array_equal(cols[kslot], Kp.cols):
+            raise capi.SulcusFemError("Taylor-Hood velocity block does not match the P2 scalar pattern")
+        self.k_slot = ctx.up(kslot, np.int32)
+
+        def sub_csr(sel, new_rows, new_cols, nrows, ncols):
+            slot = np.flatnonzero(sel)
+            r, c = new_rows[slot], new_cols[slot]
+            order = np.lexsort((c, r))
+            slot, r, c = slot[order], r[order], c[order]
+            rp = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=nrows))]).astype(np.int32)
+            return DeviceCsr(ctx, nrows, ncols, rp, c.astype(np.int32)), ctx.up(slot, np.int32)
+        il_rows = 2 * (rows % n2) + rows // n2          # interleaved velocity numbering (valid for rows < 2 n2)
+        il_cols = 2 * (cols % n2) + cols // n2
+        self.BT, self.bt_slot = sub_csr((rows < 2 * n2) & (cols >= 2 * n2), il_rows, cols - 2 * n2, 2 * n2, nv)
+        self.B, self.b_slot = sub_csr((rows >= 2 * n2) & (cols < 2 * n2), rows - 2 * n2, il_cols, nv, 2 * n2)
         # pressure mass matrix (P1)
         c1 = dm.p1_cell_dofs(mesh)
-        mp = dm.build_pattern(self.nv, self.nv, [(c1, c1)])
-        self.Mp = DeviceCsr(ctx, self.nv, self.nv, mp.rowptr, mp.cols)
+        mp = dm.build_pattern(nv, nv, [(c1, c1)])
+        self.Mp = DeviceCsr(ctx, nv, nv, mp.rowptr, mp.cols)
         self._mp = (ctx.up(mp.contrib_ptr, np.int32), ctx.up(mp.contrib_code, np.int32), ctx.zeros(mp.buffer_len))
+        # coarse pressure correction of the Schur-complement preconditioner (lubrication operator)
+        self.schur = None
+        nz = 0
+        zt = [None] * 6
+        if schur_correction:
+            from . import schur as sc
+            self.schur = sc.lubrication_correction(mesh, np.asarray(bc_markers))
+            if self.schur is not None:
+                q = self.schur
+                nz = q.nz
+                self._z = (ctx.up(q.zt_rowptr, np.int32), ctx.up(q.zt_cols, np.int32), ctx.up(q.zt_vals, np.float64),
+                           ctx.up(q.zidx, np.int32), ctx.up(q.zw, np.float64), ctx.up(q.C.ravel(), np.float64))
+                zt = [P(t) for t in self._z]
         # Dirichlet data on W.sub(0): both components on every velocity id
         self.bc_markers = bc_markers
         self.velocity_ids = tuple(velocity_ids)
         self.bc_flag_host = np.zeros(self.n, dtype=np.uint8)
         self.bc_flag = None
         self.bc_val = ctx.zeros(self.n)
-        self.rhs = ctx.zeros(self.n)
-        self.x = ctx.zeros(self.n)
+        self.rhs = ctx.zeros(self.n)            # blocked layout [ux | uy | p] (as assembled)
+        self.rhs_il = ctx.zeros(self.n)         # solver layout [u interleaved | p]
+        self.x_il = ctx.zeros(self.n)
+        self.x = ctx.zeros(self.n)              # blocked layout
         self.last_info = None
+        K = self.vel.fine.A
+        self.handle = ctx.lib.sfem_stokes_create(n2, nv, K.nnz, P(K.rowptr), P(K.cols), P(K.vals),
+                                                 self.B.nnz, P(self.B.rowptr), P(self.B.cols), P(self.B.vals),
+                                                 P(self.BT.rowptr), P(self.BT.cols), P(self.BT.vals),
+                                                 self.Mp.nnz, P(self.Mp.rowptr), P(self.Mp.cols), P(self.Mp.vals),
+                                                 self.vel.mg.handle, nz, *zt)
+        if not self.handle:
+            raise capi.SulcusFemError("sfem_stokes_create failed: " + ctx.lib.sfem_last_error().decode())
 
     def set_bcs(self, values_by_id):
         """values_by_id: ordered {id: (gx over dofs, gy over dofs)} -- later ids overwrite earlier."""
@@ -407,12 +459,22 @@ class StokesProblem:
             g[d + self.n2] = gy
             flag[d] = 1
             flag[d + self.n2] = 1
+        if not np.array_equal(flag[:self.n2], self.vel.fine.bc_flag_host) or \
+                not np.array_equal(flag[self.n2:2 * self.n2], self.vel.fine.bc_flag_host):
+            raise capi.SulcusFemError("velocity Dirichlet set differs from the preconditioner's")
         self.bc_flag_host = flag
         self.bc_flag = self.ctx.up(flag, np.uint8)
         self.bc_val.copy_(self.ctx.up(g, np.float64))
         return g
 
+    def _to_solver_layout(self, blocked, out):
+        n2, lib, ctx = self.n2, self.ctx.lib, self.ctx
+        capi.check(lib.sfem_vec_interleave2(n2, P(blocked[:n2]), P(blocked[n2:2 * n2]), P(out), ctx.stream), 'interleave')
+        out[2 * n2:].copy_(blocked[2 * n2:])
+
     def assemble(self, bc_mode=1):
+        """Assemble the Taylor-Hood matrix (+ Dirichlet); with ``bc_mode=1`` (symmetric elimination) also
+        refresh the block views and the preconditioner used by :meth:`solve`."""
         ctx, lib = self.ctx, self.ctx.lib
         capi.check(lib.sfem_elem_th_stokes(self.nc, P(self.geo), P(self.E), ctx.stream), 'sfem_elem_th_stokes')
         capi.check(lib.sfem_gather_csr(self.A.nnz, P(self.contrib_ptr), P(self.contrib_code), P(self.E), P(self.A.vals),
@@ -420,26 +482,44 @@ class StokesProblem:
         self.rhs.zero_()
         capi.check(lib.sfem_apply_dirichlet(self.n, self.A.nnz, P(self.A.rowptr), P(self.A.cols), P(self.A.vals), P(self.rhs),
                                             P(self.bc_flag), P(self.bc_val), bc_mode, ctx.stream), 'sfem_apply_dirichlet')
-        # preconditioner pieces
-        self.vel.assemble(1.0, robin=False)
+        self.bc_mode = bc_mode
+        if bc_mode != 1:
+            return
+        K = self.vel.fine.A
+        capi.check(lib.sfem_csr_extract(K.nnz, P(self.k_slot), P(self.A.vals), P(K.vals), ctx.stream), 'sfem_csr_extract')
+        capi.check(lib.sfem_csr_extract(self.B.nnz, P(self.b_slot), P(self.A.vals), P(self.B.vals), ctx.stream), 'sfem_csr_extract')
+        capi.check(lib.sfem_csr_extract(self.BT.nnz, P(self.bt_slot), P(self.A.vals), P(self.BT.vals), ctx.stream), 'sfem_csr_extract')
+        # preconditioner pieces: coarse velocity levels + pressure mass matrix
+        self.vel.assemble(1.0, robin=False, fine=False)
         cp, cc, E = self._mp
         capi.check(lib.sfem_elem_p1_mass(self.nc, P(self.geo), P(E), ctx.stream), 'sfem_elem_p1_mass')
         capi.check(lib.sfem_gather_csr(self.Mp.nnz, P(cp), P(cc), P(E), P(self.Mp.vals), ctx.stream), 'sfem_gather_csr')
 
     def solve(self, rtol=1e-14, maxit=2000):
-        ctx = self.ctx
+        ctx, lib = self.ctx, self.ctx.lib
         torch = _torch()
+        if getattr(self, 'bc_mode', None) != 1:
+            raise capi.SulcusFemError("StokesProblem.solve needs assemble(bc_mode=1)")
+        n2 = self.n2
+        self._to_solver_layout(self.rhs, self.rhs_il)
         self.x.copy_(self.bc_val * self.bc_flag.to(torch.float64))
+        self._to_solver_layout(self.x, self.x_il)
         info = (C.c_double * 4)()
-        A, Mp = self.A, self.Mp
-        rc = ctx.lib.sfem_krylov_minres_stokes(self.n2, self.nv, A.nnz, P(A.rowptr), P(A.cols), P(A.vals), self.vel.mg.handle,
-                                               Mp.nnz, P(Mp.rowptr), P(Mp.cols), P(Mp.vals), P(self.rhs), P(self.x),
-                                               float(rtol), int(maxit), info, ctx.stream)
-        capi.check(rc, 'sfem_krylov_minres_stokes')
+        rc = lib.sfem_stokes_solve(self.handle, P(self.rhs_il), P(self.x_il), float(rtol), int(maxit), info, ctx.stream)
+        capi.check(rc, 'sfem_stokes_solve')
         self.last_info = {'iterations': int(info[0]), 'relres': float(info[1]), 'converged': bool(info[2]),
                           'estimate': float(info[3]), 'method': 'minres'}
-        n2 = self.n2
+        capi.check(lib.sfem_vec_deinterleave2(n2, P(self.x_il), P(self.x[:n2]), P(self.x[n2:2 * n2]), ctx.stream), 'deinterleave')
+        self.x[2 * n2:].copy_(self.x_il[2 * n2:])
         return self.x[:n2], self.x[n2:2 * n2], self.x[2 * n2:]
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.ctx.lib.sfem_stokes_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 class FunctionalPlan:

@@ -50,6 +50,10 @@ int sfem_profile_stop(int cap, int* h_cat, double* h_bytes, float* h_ms);
  * (sub-warp-per-row vector kernel, grid-stride, grid = multiple of the SM count) */
 int sfem_spmv_csr_f64(int nrows, int nnz, const int* rowptr, const int* cols, const double* vals,
                       const double* x, const double* b, double* y, int mode, void* stream);
+/* Same for nb = 1 or 2 right-hand sides stored interleaved (x: [ncols][nb], y, b: [nrows][nb]); the
+ * matrix stream is read once for both.  Rectangular matrices allowed (multigrid transfers, B, B^T). */
+int sfem_spmv_csr_f64_nb(int nrows, int ncols, int nnz, const int* rowptr, const int* cols, const double* vals,
+                         const double* x, const double* b, double* y, int mode, int nb, void* stream);
 /* Shared-memory staged variant (modes 0 and 1): tiles of `tile_rows` consecutive rows (multiple of
  * 4) are streamed HBM -> shared memory by 1-D bulk async copies (TMA) through a `stages`-deep
  * mbarrier pipeline.  `tile_cap` = exact maximum over tiles of
@@ -99,6 +103,12 @@ int sfem_gather_csr(int nnz, const int* contrib_ptr, const int* contrib_code, co
  * replaces: DirichletBC::apply inside solve()  solvers.py:30-31,68-69,127-128,188-189,262-264 */
 int sfem_apply_dirichlet(int n, int nnz, const int* rowptr, const int* cols, double* vals, double* rhs,
                          const unsigned char* bc_flag, const double* bc_val, int mode, void* stream);
+/* dst_vals[i] = src_vals[slot[i]]: copies a sub-block of an assembled CSR (e.g. K, B, B^T of the
+ * Taylor-Hood matrix) into its own CSR; the slot map is built once on the host. */
+int sfem_csr_extract(int n, const int* slot, const double* src_vals, double* dst_vals, void* stream);
+/* blocked (a | b) <-> interleaved (a0,b0,a1,b1,...) layouts of a two-component nodal field */
+int sfem_vec_interleave2(int n, const double* a, const double* b, double* out, void* stream);
+int sfem_vec_deinterleave2(int n, const double* in, double* a, double* b, void* stream);
 
 /* ------------------------------------------------------------------ vectors ------------------ */
 int sfem_vec_axpby(int n, double a, const double* x, double b, double* y, void* stream);   /* y = a x + b y */
@@ -123,8 +133,10 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
                          const int* h_P_nnz,
                          const int* const* h_P_rowptr, const int* const* h_P_cols, const double* const* h_P_vals,
                          const int* const* h_R_rowptr, const int* const* h_R_cols, const double* const* h_R_vals,
-                         const double* coarse_inv, int cheb_degree, double eig_ratio);
-/* (re)compute D^-1 and lambda_max(D^-1 A) of every level from the current operator values */
+                         const double* coarse_inv, int cheb_degree, double eig_ratio, int nb);
+/* nb = 1 or 2: number of right-hand sides a V-cycle carries, stored interleaved ([dof][nb]).
+ * (re)compute D^-1, the Gershgorin bound of lambda_max(D^-1 A) and the Chebyshev coefficients of
+ * every level from the current operator values -- all on the device, no host synchronisation */
 int sfem_mg_setup(sfem_mg_t mg, void* stream);
 int sfem_mg_vcycle(sfem_mg_t mg, const double* b, double* x, void* stream);   /* x = M^-1 b */
 int sfem_mg_lambda_max(sfem_mg_t mg, double* h_out);                            /* per level, host */
@@ -139,12 +151,30 @@ int sfem_krylov_cg(int n, int nnz, const int* rowptr, const int* cols, const dou
 int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const double* vals, sfem_mg_t mg,
                        const double* b, double* x, double rtol, int restart, int maxit,
                        double* h_info, void* stream);
-/* Taylor-Hood saddle point [ux | uy | p] with n2 velocity dofs per component and nv pressure dofs:
- * MINRES with the block-diagonal preconditioner diag(MG, MG, Chebyshev(Mp)); mg acts on one
- * velocity component; Mp_* is the P1 pressure mass matrix. */
-int sfem_krylov_minres_stokes(int n2, int nv, int nnz, const int* rowptr, const int* cols, const double* vals,
-                              sfem_mg_t mg, int Mp_nnz, const int* Mp_rowptr, const int* Mp_cols, const double* Mp_vals,
-                              const double* b, double* x, double rtol, int maxit, double* h_info, void* stream);
+/* Taylor-Hood Stokes solver: preconditioned MINRES on the block form of the assembled matrix.
+ * Unknown / right-hand-side layout: [velocity interleaved (ux0,uy0,ux1,uy1,...) : 2*n2 | pressure : nv].
+ *   K   (n2 x n2)      scalar P2 stiffness block with the velocity Dirichlet rows/columns eliminated
+ *   B   (nv x 2*n2)    divergence block, columns in interleaved velocity numbering; BT its transpose
+ *   Mp  (nv x nv)      P1 pressure mass matrix (Schur-complement preconditioner, 4 Chebyshev steps)
+ *   mg                 multigrid handle on K created with nb = 2 (one V-cycle serves both components)
+ *   nz, zt_*, zidx, zw, Cc   optional coarse pressure correction  S^-1 += Z Cc Z^T  with Z the nz 1-D
+ *                      hat functions in x (zidx/zw: left hat index and weight per pressure dof;
+ *                      zt_*: CSR of Z^T), Cc (nz x nz, symmetric positive semi-definite); nz = 0: none
+ * All arrays are caller-owned device arrays that must stay valid for the life of the handle; the
+ * values may be rewritten between solves (re-assembly).  The iteration is replayed from CUDA graphs.
+ * replaces: the sparse LU of solve(a == L, U, bcs) in stokes_solver, solvers.py:298
+ * h_info[4] = {iterations, true relative residual, converged(1/0), preconditioned residual estimate} */
+typedef struct sfem_stokes* sfem_stokes_t;
+sfem_stokes_t sfem_stokes_create(int n2, int nv,
+                                 int K_nnz, const int* K_rowptr, const int* K_cols, const double* K_vals,
+                                 int B_nnz, const int* B_rowptr, const int* B_cols, const double* B_vals,
+                                 const int* BT_rowptr, const int* BT_cols, const double* BT_vals,
+                                 int Mp_nnz, const int* Mp_rowptr, const int* Mp_cols, const double* Mp_vals,
+                                 sfem_mg_t mg,
+                                 int nz, const int* zt_rowptr, const int* zt_cols, const double* zt_vals,
+                                 const int* zidx, const double* zw, const double* Cc);
+int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, int maxit, double* h_info, void* stream);
+void sfem_stokes_destroy(sfem_stokes_t h);
 
 /* ------------------------------------------------------------------ functionals -------------- */
 /* Facet functionals of analysis.py, all groups in one launch.

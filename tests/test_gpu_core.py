@@ -52,6 +52,51 @@ def test_spmv_variants(ctx):
         assert _rel(y2.cpu().numpy(), b + ref) < 1e-14
 
 
+def test_spmv_two_rhs_and_rectangular(ctx):
+    """nb = 2 interleaved right-hand sides (matrix read once) and rectangular operators."""
+    import torch
+    import scipy.sparse as sp
+    from sulcusfem.device import DeviceCsr
+    rng = np.random.default_rng(2)
+    for (m, n, dens) in ((1, 1, 1.0), (53, 31, 0.2), (3000, 4100, 0.004), (20011, 20011, 0.0005)):
+        A = sp.random(m, n, dens, random_state=5, format='csr')
+        if m > 100:
+            A = A.tolil(); A[3, :] = 0; A[9, :300] = -0.5; A = A.tocsr(); A.eliminate_zeros()
+        A.sort_indices()
+        dA = DeviceCsr(ctx, m, n, A.indptr, A.indices, A.data)
+        X = rng.random((n, 2)); B = rng.random((m, 2))
+        dX = torch.from_numpy(X.ravel().copy()).cuda(); dB = torch.from_numpy(B.ravel().copy()).cuda()
+        ref = A @ X
+        y = dA.spmv(dX, nb=2).cpu().numpy().reshape(m, 2)
+        assert _rel(y, ref) < 1e-14 or np.linalg.norm(ref) == 0
+        r = dA.spmv(dX, b=dB, mode=1, nb=2).cpu().numpy().reshape(m, 2)
+        assert _rel(r, B - ref) < 1e-13
+        y2 = dB.clone()
+        dA.spmv(dX, y=y2, mode=2, nb=2)
+        assert _rel(y2.cpu().numpy().reshape(m, 2), B + ref) < 1e-14
+        if m != n:
+            y1 = dA.spmv(torch.from_numpy(X[:, 0].copy()).cuda(), nb=1).cpu().numpy()
+            assert _rel(y1, ref[:, 0]) < 1e-14 or np.linalg.norm(ref) == 0
+
+
+def test_vcycle_two_rhs_equals_two_cycles(ctx, small):
+    """One nb = 2 V-cycle is bit-identical to two scalar V-cycles."""
+    import torch
+    from sulcusfem.device import ScalarProblem
+    mesh, mk, om = small
+    bm = mk['bc_markers'].values
+    p1 = ScalarProblem(mesh, bm, dirichlet_ids=(1, 4, 3), robin_id=None, ctx=ctx, nb=1)
+    p2 = ScalarProblem(mesh, bm, dirichlet_ids=(1, 4, 3), robin_id=None, hierarchy=p1.hierarchy, ctx=ctx, nb=2)
+    p1.assemble(1.0, robin=False)
+    p2.assemble(1.0, robin=False)
+    torch.manual_seed(1)
+    r = torch.rand(p1.n, 2, dtype=torch.float64, device=ctx.device)
+    za = p1.mg.vcycle(r[:, 0].contiguous()).cpu().numpy()
+    zb = p1.mg.vcycle(r[:, 1].contiguous()).cpu().numpy()
+    z2 = p2.mg.vcycle(r.reshape(-1).contiguous()).cpu().numpy().reshape(-1, 2)
+    assert np.array_equal(z2[:, 0], za) and np.array_equal(z2[:, 1], zb)
+
+
 def test_p2_assembly_matches_oracle(ctx, small):
     import torch
     from oracle import cpu_oracle as co
@@ -175,9 +220,37 @@ def test_stokes_solve_matches_lu(ctx, small):
     ux, uy, p = [t.cpu().numpy() for t in sp_.solve(rtol=1e-14)]
     rx, ry, rp, _, _ = co.solve_stokes(om, bm, 1.0)
     print('minres', sp_.last_info)
+    assert sp_.last_info['converged']
     un = np.linalg.norm(np.concatenate([rx, ry]))
     assert np.linalg.norm(np.concatenate([ux - rx, uy - ry])) / un < 1e-10
     assert _rel(p, rp) < 1e-9
+    # block views = the assembled matrix minus structural zeros: K, B, B^T reproduce A exactly
+    import scipy.sparse as sps
+    A = sp_.A.to_scipy()
+    n2, nv = sp_.n2, sp_.nv
+    K = sp_.vel.fine.A.to_scipy()
+    assert abs(K - A[:n2, :n2]).max() == 0.0 and abs(K - A[n2:2 * n2, n2:2 * n2]).max() == 0.0
+    perm = np.concatenate([2 * np.arange(n2), 2 * np.arange(n2) + 1])        # blocked -> interleaved position
+    B = sp_.B.to_scipy()
+    assert abs(B[:, perm] - A[2 * n2:, :2 * n2]).max() == 0.0
+    assert abs(sp_.BT.to_scipy() - B.T).max() == 0.0
+    # the graph-replayed iteration and the plain launch sequence give the same iterates
+    it_graph = sp_.last_info['iterations']
+    import os
+    x_graph = sp_.x.clone()
+    ctx.lib.sfem_profile_start(1)          # profiling on -> graphs bypassed
+    sp_.solve(rtol=1e-14)
+    ctx.lib.sfem_profile_stop(0, None, None, None)
+    assert sp_.last_info['iterations'] == it_graph
+    assert float((sp_.x - x_graph).abs().max()) == 0.0
+    # without the lubrication coarse correction: same solution, more iterations
+    sp0 = StokesProblem(mesh, bm, ctx=ctx, schur_correction=False)
+    sp0.set_bcs({1: (4 * X[d1, 1] * (1 - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+    sp0.assemble(bc_mode=1)
+    ux0, uy0, p0 = [t.cpu().numpy() for t in sp0.solve(rtol=1e-14)]
+    print('minres (mass-matrix Schur only)', sp0.last_info)
+    assert np.linalg.norm(np.concatenate([ux0 - rx, uy0 - ry])) / un < 1e-10
+    assert sp0.last_info['iterations'] > sp_.last_info['iterations']
 
 
 def test_functionals_match_oracle(ctx, small):

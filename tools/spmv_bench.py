@@ -1,0 +1,108 @@
+"""SpMV micro-benchmark: FP64 CSR SpMV on P2 / Taylor-Hood patterns of rect(r) meshes.
+
+    python tools/spmv_bench.py [--nx 2000 --ny 200] [--space p2|th] [--variants vector,staged:128:3 ...]
+                               [--iters 20] [--only NAME] [--out gpurun_out/spmv_bench.json]
+
+Every timed launch is preceded by an L2 flush (512 MiB memset) unless --no-flush; time = CUDA events
+on the launching stream; achieved = (12 nnz + 20 N) / t  (SURVEY 8(d) algorithmic bytes).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'fenics-eff-uptake_b200'))
+
+import numpy as np  # noqa: E402
+
+
+def build_matrix(nx, ny, space):
+    from sulcusfem import hostmesh as hm, dofmap as dm
+    mesh = hm.rectangle_mesh(10.0, 1.0, nx, ny)
+    if space == 'p2':
+        cd = dm.p2_cell_dofs(mesh)
+        n = dm.p2_num_dofs(mesh)
+    else:
+        cd = dm.th_cell_dofs(mesh)
+        n = dm.th_num_dofs(mesh)
+    pat = dm.build_pattern(n, n, [(cd, cd)])
+    return n, pat.rowptr, pat.cols
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--nx', type=int, default=2000)
+    ap.add_argument('--ny', type=int, default=200)
+    ap.add_argument('--space', default='p2')
+    ap.add_argument('--variants', default='vector,staged:64:3,staged:128:3,staged:128:4,staged:256:3,staged:256:4')
+    ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--no-flush', action='store_true')
+    ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'spmv_bench.json'))
+    args = ap.parse_args()
+    import torch
+    from sulcusfem.device import Context, DeviceCsr
+    ctx = Context.get()
+    n, rowptr, cols = build_matrix(args.nx, args.ny, args.space)
+    nnz = len(cols)
+    rng = np.random.default_rng(0)
+    vals = rng.random(nnz)
+    torch.manual_seed(0)
+    x = torch.rand(n, dtype=torch.float64, device=ctx.device)
+    y = torch.empty(n, dtype=torch.float64, device=ctx.device)
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
+    bytes_alg = 12.0 * nnz + 20.0 * n
+    peak = 6449.4
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peak = float(json.load(f)['hbm_gbs'])
+    except Exception:
+        pass
+    ref = None
+    results = []
+    for v in args.variants.split(','):
+        parts = v.split(':')
+        staged = parts[0] == 'staged'
+        tile_rows = int(parts[1]) if len(parts) > 1 else 128
+        stages = int(parts[2]) if len(parts) > 2 else 3
+        if len(parts) > 3:
+            os.environ['SFEM_STAGED_CTAS_PER_SM'] = parts[3]
+        else:
+            os.environ.pop('SFEM_STAGED_CTAS_PER_SM', None)
+        A = DeviceCsr(ctx, n, n, rowptr, cols, vals, tile_rows=tile_rows)
+        for _ in range(3):
+            A.spmv(x, y, staged=staged, stages=stages)
+        torch.cuda.synchronize()
+        got = y.clone()
+        if ref is None:
+            import scipy.sparse as sp
+            M = sp.csr_matrix((vals, cols, rowptr), shape=(n, n))
+            ref = torch.from_numpy(M @ x.cpu().numpy()).to(ctx.device)
+        err = float((got - ref).norm() / ref.norm())
+        ms = []
+        for _ in range(args.iters):
+            if not args.no_flush:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            A.spmv(x, y, staged=staged, stages=stages)
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        ms = np.array(ms)
+        r = {"variant": v, "space": args.space, "n": n, "nnz": nnz, "ms_med": float(np.median(ms)), "ms_min": float(ms.min()),
+             "gbs_med": bytes_alg / 1e9 / (float(np.median(ms)) / 1e3), "gbs_best": bytes_alg / 1e9 / (float(ms.min()) / 1e3),
+             "rel_err": err, "flush": not args.no_flush}
+        r["frac_of_measured_peak"] = r["gbs_med"] / peak
+        results.append(r)
+        print(json.dumps(r), flush=True)
+        del A
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, 'a') as f:
+        for r in results:
+            f.write(json.dumps(r) + "\n")
+
+
+if __name__ == '__main__':
+    main()
