@@ -249,6 +249,7 @@ int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cu
   if (A.nrows <= 0) return SFEM_OK;
   if (mode == 1 && b == nullptr) { set_error("spmv mode 1 needs b"); return SFEM_ERR_ARG; }
   if (nb != 1 && nb != 2) { set_error("spmv: nb must be 1 or 2"); return SFEM_ERR_ARG; }
+  if (nb == 2 && (reinterpret_cast<uintptr_t>(x) & 15u)) { set_error("spmv: nb = 2 needs a 16-byte aligned x"); return SFEM_ERR_ARG; }
   if (nb == 1 && A.tile_cap > 0 && mode != 2)
     return spmv_staged_plan(A, A.tile_rows, A.tile_cap, A.stages, x, b, y, mode, st);
   const int lanes = lanes_for(A, nb);

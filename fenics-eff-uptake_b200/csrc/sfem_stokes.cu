@@ -260,7 +260,7 @@ sfem_stokes_t sfem_stokes_create(int n2, int nv,
   h->Mp.nrows = h->Mp.ncols = nv; h->Mp.nnz = Mp_nnz; h->Mp.rowptr = Mp_rowptr; h->Mp.cols = Mp_cols; h->Mp.vals = Mp_vals;
   h->mg = mg;
   h->nz = nz; h->zt_rowptr = zt_rowptr; h->zt_cols = zt_cols; h->zt_vals = zt_vals; h->zidx = zidx; h->zw = zw; h->Cc = Cc;
-  const size_t nn = (size_t)h->n;
+  const size_t nn = ((size_t)h->n + 1) & ~(size_t)1;     // even stride: velocity parts are read as double2
   const size_t total = 7 * nn + 4 * (size_t)nv + 3 * (size_t)kMaxPartials + (size_t)(nz + 1) * (kZtChunks + 1) + kChebCoefLen + 64;
   if (cudaMalloc(&h->buf, total * sizeof(double)) != cudaSuccess || cudaMallocHost(&h->h_pin, 8 * sizeof(double)) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -291,6 +291,10 @@ void sfem_stokes_destroy(sfem_stokes_t h) {
 
 int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, int maxit, double* h_info, void* stream) {
   if (!h || !h->mg->ready) { set_error("stokes solve: handle / multigrid not set up"); return SFEM_ERR_ARG; }
+  if ((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15u) {
+    set_error("stokes solve: b and x must be 16-byte aligned (interleaved velocity is read as double2)");
+    return SFEM_ERR_ARG;
+  }
   cudaStream_t user = (cudaStream_t)stream;
   SFEM_TRY(h->ws.fork(user));
   cudaStream_t st = h->ws.s;
