@@ -24,15 +24,16 @@ int sfem_spmv_csr_f64_nb(int nrows, int ncols, int nnz, const int* rowptr, const
   return spmv(A, x, b, y, mode, (cudaStream_t)stream, nb);
 }
 
-int sfem_spmv_csr_f64_staged(int nrows, int nnz, const int* rowptr, const int* cols, const double* vals,
-                             const double* x, const double* b, double* y, int mode, int tile_rows, int tile_cap,
-                             int stages, void* stream) {
-  if (nrows < 0 || nnz < 0 || mode < 0 || mode > 1) { set_error("staged spmv: bad arguments"); return SFEM_ERR_ARG; }
+int sfem_spmv_csr_f64_staged(int nrows, int ncols, int nnz, const int* rowptr, const int* cols, const double* vals,
+                             const double* x, const double* b, double* y, int mode, int nb, void* stream) {
+  if (nrows < 0 || nnz < 0 || mode < 0 || mode > 2 || (nb != 1 && nb != 2)) { set_error("staged spmv: bad arguments"); return SFEM_ERR_ARG; }
   if (mode == 1 && b == nullptr) { set_error("staged spmv: mode 1 needs b"); return SFEM_ERR_ARG; }
   Csr A;
-  A.nrows = nrows; A.ncols = nrows; A.nnz = nnz;
+  A.nrows = nrows; A.ncols = ncols; A.nnz = nnz;
   A.rowptr = rowptr; A.cols = cols; A.vals = vals;
-  return spmv_staged_plan(A, tile_rows, tile_cap, stages, x, b, y, mode, (cudaStream_t)stream);
+  const int r = staged_spmv(A, x, b, y, mode, nb, (cudaStream_t)stream);
+  if (r == 0) { set_error("staged spmv: no tile plan registered for this matrix (or fewer tiles than SFEM_STAGED_MIN_TILES)"); return SFEM_ERR_ARG; }
+  return r < 0 ? r : SFEM_OK;
 }
 
 }  // extern "C"

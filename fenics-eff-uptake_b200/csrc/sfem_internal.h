@@ -11,17 +11,12 @@ struct Csr {
   const int* rowptr = nullptr;
   const int* cols = nullptr;
   const double* vals = nullptr;
-  // shared-memory staged SpMV plan (0 = use the vector kernel): rows per tile, exact max nnz of a
-  // tile (from the host copy of rowptr) and pipeline depth
-  int tile_rows = 0;
-  int tile_cap = 0;
-  int stages = 3;
 };
 
 // sfem_spmv.cu  (nb = number of interleaved right-hand sides, 1 or 2)
 int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st, int nb = 1);
 int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* nparts, cudaStream_t st, int nb = 1,
-             const double* dotx = nullptr);   // partial sums of <dotx, y>, dotx defaults to x
+             const double* dotx = nullptr, int mode = 0);   // partial sums of <dotx, y>; mode 2: y += A x first
 // Chebyshev coefficients are read from device memory: c12 -> {c1, c2}, c0 -> {c0}
 int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
               const double* c12, int last, cudaStream_t st, int nb = 1);
@@ -30,9 +25,15 @@ int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x,
 // y_u = K z_u + BT z_p (interleaved velocity), partial sums of <z_u, y_u>
 int stokes_apply_u(const Csr& K, const Csr& BT, const double* zu, const double* zp, double* yu, double* partial,
                    int* nparts, cudaStream_t st);
-// sfem_spmv_staged.cu
-int spmv_staged_plan(const Csr& A, int tile_rows, int tile_cap, int stages, const double* x, const double* b,
-                     double* y, int mode, cudaStream_t st);
+// sfem_spmv_staged.cu: TMA-staged engine; each returns 1 when it took the launch (a tile plan is registered for
+// A.rowptr and the matrix is large enough), 0 when the caller should use the vector engine, < 0 on error
+int staged_spmv(const Csr& A, const double* x, const double* b, double* y, int mode, int nb, cudaStream_t st);
+int staged_spmv_dot(const Csr& A, const double* x, const double* dx, double* y, double* partial, int* nparts, int mode,
+                    int nb, cudaStream_t st);
+int staged_cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
+                     const double* c12, int last, int nb, cudaStream_t st);
+int staged_resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
+                    const double* c0, int nb, cudaStream_t st);
 
 // sfem_vector.cu
 int vec_set(int n, double a, double* x, cudaStream_t st);

@@ -16,201 +16,169 @@
 // mbarrier, multi-buffered, then reduced from shared memory.  See sfem_spmv_staged.cu.
 #include "sfem_common.cuh"
 #include "sfem_internal.h"
+#include "sfem_spmv_epi.cuh"
+
+#include <cstdlib>
 
 namespace sfem {
 
+// ------------------------------------------------------------------ pipelined row engine
+// A warp owns kThreads/LANES... rows per pass: LANES lanes per row, UNROLL entries per lane and pass.
+// Per row the dependent chain is  rowptr -> (cols, vals) -> gather x -> reduce -> epilogue loads;
+// executed naively that is three exposed memory latencies per row group and the kernel is
+// latency-bound (measured 3.6 TB/s on B200).  The engine software-pipelines it: while the gathers
+// of row group i are in flight it already holds the (cols, vals) of group i+1 in registers and has
+// the rowptr entries of group i+2 and the epilogue operands of group i+1 requested.
 template <int NB>
 struct Acc {
   double v[NB];
 };
 
+constexpr int kUnroll = 4;
+constexpr int kSpmvBlocksPerSm = 4;   // matches __launch_bounds__(kThreads, 4): one resident wave, persistent grid-stride
+
 template <int NB>
-__device__ __forceinline__ void gather_fma(const double* __restrict__ x, int col, double a, Acc<NB>& acc);
+struct XVal;
 template <>
-__device__ __forceinline__ void gather_fma<1>(const double* __restrict__ x, int col, double a, Acc<1>& acc) {
-  acc.v[0] = fma(a, __ldg(x + col), acc.v[0]);
-}
+struct XVal<1> {
+  double a;
+  __device__ __forceinline__ void load(const double* __restrict__ x, int col, bool ok) { a = ok ? __ldg(x + col) : 0.0; }
+  __device__ __forceinline__ void fma_into(double v, Acc<1>& acc) const { acc.v[0] = fma(v, a, acc.v[0]); }
+};
 template <>
-__device__ __forceinline__ void gather_fma<2>(const double* __restrict__ x, int col, double a, Acc<2>& acc) {
-  const double2 xv = __ldg(reinterpret_cast<const double2*>(x) + col);
-  acc.v[0] = fma(a, xv.x, acc.v[0]);
-  acc.v[1] = fma(a, xv.y, acc.v[1]);
+struct XVal<2> {
+  double2 a;
+  __device__ __forceinline__ void load(const double* __restrict__ x, int col, bool ok) {
+    a = ok ? __ldg(reinterpret_cast<const double2*>(x) + col) : make_double2(0.0, 0.0);
+  }
+  __device__ __forceinline__ void fma_into(double v, Acc<2>& acc) const {
+    acc.v[0] = fma(v, a.x, acc.v[0]);
+    acc.v[1] = fma(v, a.y, acc.v[1]);
+  }
+};
+
+template <int LANES>
+__device__ __forceinline__ void load_pass(const int* __restrict__ cols, const double* __restrict__ vals, int k, int e,
+                                          int (&cc)[kUnroll], double (&vv)[kUnroll]) {
+#pragma unroll
+  for (int j = 0; j < kUnroll; ++j) {
+    const int kk = k + j * LANES;
+    const bool ok = kk < e;
+    cc[j] = ok ? __ldcs(cols + kk) : -1;
+    vv[j] = ok ? __ldcs(vals + kk) : 0.0;
+  }
 }
 
-// Dot of CSR row `row` with the NB interleaved vectors in x by LANES cooperating lanes; every lane
-// of the group gets the sums.  All 32 lanes of the warp must call this (invalid rows: valid=false).
-template <int LANES, int NB>
-__device__ __forceinline__ Acc<NB> csr_row_dot_nb(const int* __restrict__ rowptr, const int* __restrict__ cols,
-                                                  const double* __restrict__ vals, const double* __restrict__ x,
-                                                  int row, bool valid, int lane) {
-  Acc<NB> a0, a1;
-#pragma unroll
-  for (int c = 0; c < NB; ++c) { a0.v[c] = 0.0; a1.v[c] = 0.0; }
-  if (valid) {
-    const int s = rowptr[row], e = rowptr[row + 1];
-    int k = s + lane;
-    for (; k + LANES < e; k += 2 * LANES) {
-      const int c0 = __ldcs(cols + k), c1 = __ldcs(cols + k + LANES);
-      const double v0 = __ldcs(vals + k), v1 = __ldcs(vals + k + LANES);
-      gather_fma<NB>(x, c0, v0, a0);
-      gather_fma<NB>(x, c1, v1, a1);
-    }
-    if (k < e) gather_fma<NB>(x, __ldcs(cols + k), __ldcs(vals + k), a0);
-  }
-#pragma unroll
-  for (int c = 0; c < NB; ++c) {
-    double t = a0.v[c] + a1.v[c];
-#pragma unroll
-    for (int o = LANES >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    a0.v[c] = t;
-  }
-  return a0;
-}
-
-// MODE 0: y = A x;  1: y = b - A x;  2: y += A x
-template <int LANES, int NB, int MODE>
-__global__ void __launch_bounds__(kThreads) k_spmv(int nrows, const int* __restrict__ rowptr,
-                                                   const int* __restrict__ cols, const double* __restrict__ vals,
-                                                   const double* __restrict__ x, const double* __restrict__ b,
-                                                   double* __restrict__ y) {
+// Epi: struct with   Pre pre(int row, int lane, bool active)   (loads issued early)
+//                    void fin(int row, int lane, double value, const Pre&)   (called for lane < NB of valid rows)
+template <int LANES, int NB, class Epi>
+__device__ __forceinline__ void row_engine(int nrows, const int* __restrict__ rowptr, const int* __restrict__ cols,
+                                           const double* __restrict__ vals, const double* __restrict__ x, Epi& epi) {
   constexpr int ROWS = kThreads / LANES;
   const int lane = threadIdx.x % LANES;
   const int sub = threadIdx.x / LANES;
-  for (long long base = (long long)blockIdx.x * ROWS; base < nrows; base += (long long)gridDim.x * ROWS) {
-    const int row = (int)base + sub;
-    const bool valid = row < nrows;
-    const Acc<NB> s = csr_row_dot_nb<LANES, NB>(rowptr, cols, vals, x, row, valid, lane);
-    if (valid && lane < NB) {
-      const double sv = (NB == 2 && lane == 1) ? s.v[NB - 1] : s.v[0];
-      const size_t i = (size_t)row * NB + lane;
-      if (MODE == 0) y[i] = sv;
-      else if (MODE == 1) y[i] = b[i] - sv;
-      else y[i] += sv;
+  const long long stride = (long long)gridDim.x * ROWS;
+  long long base = (long long)blockIdx.x * ROWS;
+  if (base >= nrows) return;
+  // prologue: row group 0 fully fetched, rowptr of group 1 requested
+  long long row = base + sub;
+  bool valid = row < nrows;
+  int s = 0, e = 0;
+  if (valid) { s = rowptr[row]; e = rowptr[row + 1]; }
+  int cc[kUnroll];
+  double vv[kUnroll];
+  load_pass<LANES>(cols, vals, s + lane, e, cc, vv);
+  typename Epi::Pre pre = epi.pre((int)row, lane, valid && lane < NB);
+  long long nrow = row + stride;
+  bool nvalid = nrow < nrows;
+  int ns = 0, ne = 0;
+  if (nvalid) { ns = rowptr[nrow]; ne = rowptr[nrow + 1]; }
+  for (; base < nrows; base += stride) {
+    // rowptr of the group after next
+    const long long nnrow = nrow + stride;
+    const bool nnvalid = nnrow < nrows;
+    int nns = 0, nne = 0;
+    if (nnvalid) { nns = rowptr[nnrow]; nne = rowptr[nnrow + 1]; }
+    // gathers of the current group (first pass)
+    XVal<NB> xv[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) xv[j].load(x, cc[j], cc[j] >= 0);
+    // (cols, vals) and epilogue operands of the next group
+    int ncc[kUnroll];
+    double nvv[kUnroll];
+    load_pass<LANES>(cols, vals, ns + lane, ne, ncc, nvv);
+    typename Epi::Pre npre = epi.pre((int)nrow, lane, nvalid && lane < NB);
+    Acc<NB> a0, a1;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) { a0.v[c] = 0.0; a1.v[c] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) xv[j].fma_into(vv[j], (j & 1) ? a1 : a0);
+    // rows longer than one pass (rare for FEM patterns)
+    for (int k = s + lane + kUnroll * LANES; k < e; k += kUnroll * LANES) {
+      load_pass<LANES>(cols, vals, k, e, cc, vv);
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) xv[j].load(x, cc[j], cc[j] >= 0);
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) xv[j].fma_into(vv[j], (j & 1) ? a1 : a0);
     }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      double t = a0.v[c] + a1.v[c];
+#pragma unroll
+      for (int o = LANES >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      a0.v[c] = t;
+    }
+    if (valid && lane < NB) epi.fin((int)row, lane, (NB == 2 && lane == 1) ? a0.v[NB - 1] : a0.v[0], pre);
+    // rotate the pipeline
+    row = nrow; valid = nvalid; s = ns; e = ne;
+    nrow = nnrow; nvalid = nnvalid; ns = nns; ne = nne;
+    pre = npre;
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) { cc[j] = ncc[j]; vv[j] = nvv[j]; }
   }
 }
 
-// y = A x and partial sums of <dx, y> (CG: dx = x, p.Ap); one partial per block.
-template <int LANES, int NB>
-__global__ void __launch_bounds__(kThreads) k_spmv_dot(int nrows, const int* __restrict__ rowptr,
+// ------------------------------------------------------------------ kernels
+template <int LANES, int NB, int MODE>
+__global__ void __launch_bounds__(kThreads, 4) k_spmv(int nrows, const int* __restrict__ rowptr,
+                                                   const int* __restrict__ cols, const double* __restrict__ vals,
+                                                   const double* __restrict__ x, const double* __restrict__ b,
+                                                   double* __restrict__ y) {
+  EpiStore<NB, MODE> epi{b, y};
+  row_engine<LANES, NB>(nrows, rowptr, cols, vals, x, epi);
+}
+
+// y = A x (MODE 0) or y += A x (MODE 2) and partial sums of <dx, y>; one partial per block.
+template <int LANES, int NB, int MODE>
+__global__ void __launch_bounds__(kThreads, 4) k_spmv_dot(int nrows, const int* __restrict__ rowptr,
                                                        const int* __restrict__ cols, const double* __restrict__ vals,
                                                        const double* __restrict__ x, const double* __restrict__ dx,
                                                        double* __restrict__ y, double* __restrict__ partial) {
   __shared__ double sh[33];
-  constexpr int ROWS = kThreads / LANES;
-  const int lane = threadIdx.x % LANES;
-  const int sub = threadIdx.x / LANES;
-  double acc = 0.0;
-  for (long long base = (long long)blockIdx.x * ROWS; base < nrows; base += (long long)gridDim.x * ROWS) {
-    const int row = (int)base + sub;
-    const bool valid = row < nrows;
-    const Acc<NB> s = csr_row_dot_nb<LANES, NB>(rowptr, cols, vals, x, row, valid, lane);
-    if (valid && lane < NB) {
-      const double sv = (NB == 2 && lane == 1) ? s.v[NB - 1] : s.v[0];
-      const size_t i = (size_t)row * NB + lane;
-      y[i] = sv;
-      acc = fma(dx[i], sv, acc);
-    }
-  }
-  const double t = block_sum(acc, sh);
+  EpiDot<NB, MODE> epi{dx, y, 0.0};
+  row_engine<LANES, NB>(nrows, rowptr, cols, vals, x, epi);
+  const double t = block_sum(epi.acc, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
-// One fused Chebyshev-Jacobi step (see sfem_mg.cu):
-//   t = (A d_old)_i;  r_i -= t;  x_i += d_old_i (+ d_new_i when LAST);
-//   d_new_i = c1 d_old_i + c2 dinv_i r_i
 template <int LANES, int NB>
-__global__ void __launch_bounds__(kThreads) k_cheb_step(int nrows, const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(kThreads, 4) k_cheb_step(int nrows, const int* __restrict__ rowptr,
                                                         const int* __restrict__ cols, const double* __restrict__ vals,
                                                         const double* __restrict__ dinv, const double* __restrict__ d_old,
                                                         double* __restrict__ d_new, double* __restrict__ r,
                                                         double* __restrict__ x, const double* __restrict__ c12, int last) {
-  const double c1 = c12[0], c2 = c12[1];
-  constexpr int ROWS = kThreads / LANES;
-  const int lane = threadIdx.x % LANES;
-  const int sub = threadIdx.x / LANES;
-  for (long long base = (long long)blockIdx.x * ROWS; base < nrows; base += (long long)gridDim.x * ROWS) {
-    const int row = (int)base + sub;
-    const bool valid = row < nrows;
-    const Acc<NB> s = csr_row_dot_nb<LANES, NB>(rowptr, cols, vals, d_old, row, valid, lane);
-    if (valid && lane < NB) {
-      const double t = (NB == 2 && lane == 1) ? s.v[NB - 1] : s.v[0];
-      const size_t i = (size_t)row * NB + lane;
-      const double rn = r[i] - t;
-      const double dold = d_old[i];
-      const double dn = c1 * dold + c2 * dinv[row] * rn;
-      r[i] = rn;
-      d_new[i] = dn;
-      x[i] += last ? (dold + dn) : dold;
-    }
-  }
+  EpiCheb<NB> epi{dinv, d_old, d_new, r, x, c12[0], c12[1], last};
+  row_engine<LANES, NB>(nrows, rowptr, cols, vals, d_old, epi);
 }
 
-// r = b - A x ; d = c0 * dinv * r      (start of a smoothing sweep with a non-zero iterate)
 template <int LANES, int NB>
-__global__ void __launch_bounds__(kThreads) k_resid_d0(int nrows, const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(kThreads, 4) k_resid_d0(int nrows, const int* __restrict__ rowptr,
                                                        const int* __restrict__ cols, const double* __restrict__ vals,
                                                        const double* __restrict__ dinv, const double* __restrict__ b,
                                                        const double* __restrict__ x, double* __restrict__ r,
                                                        double* __restrict__ d, const double* __restrict__ c0p) {
-  const double c0 = c0p[0];
-  constexpr int ROWS = kThreads / LANES;
-  const int lane = threadIdx.x % LANES;
-  const int sub = threadIdx.x / LANES;
-  for (long long base = (long long)blockIdx.x * ROWS; base < nrows; base += (long long)gridDim.x * ROWS) {
-    const int row = (int)base + sub;
-    const bool valid = row < nrows;
-    const Acc<NB> s = csr_row_dot_nb<LANES, NB>(rowptr, cols, vals, x, row, valid, lane);
-    if (valid && lane < NB) {
-      const double sv = (NB == 2 && lane == 1) ? s.v[NB - 1] : s.v[0];
-      const size_t i = (size_t)row * NB + lane;
-      const double rr = b[i] - sv;
-      r[i] = rr;
-      d[i] = c0 * dinv[row] * rr;
-    }
-  }
-}
-
-// Taylor-Hood velocity rows of  y = A z  in block form (both components of dof `row` at once):
-//   y_u[row] = K[row,:] z_u  +  BT[2 row + c, :] z_p ,  plus partial sums of <z_u, y_u>.
-// K is the scalar P2 stiffness (Dirichlet rows = identity), BT the (interleaved-row) transpose of
-// the divergence block.
-template <int LANES>
-__global__ void __launch_bounds__(kThreads) k_stokes_apply_u(int n2, const int* __restrict__ k_rowptr,
-                                                             const int* __restrict__ k_cols, const double* __restrict__ k_vals,
-                                                             const int* __restrict__ bt_rowptr, const int* __restrict__ bt_cols,
-                                                             const double* __restrict__ bt_vals,
-                                                             const double* __restrict__ zu, const double* __restrict__ zp,
-                                                             double* __restrict__ yu, double* __restrict__ partial) {
-  __shared__ double sh[33];
-  constexpr int ROWS = kThreads / LANES;
-  const int lane = threadIdx.x % LANES;
-  const int sub = threadIdx.x / LANES;
-  double acc = 0.0;
-  for (long long base = (long long)blockIdx.x * ROWS; base < n2; base += (long long)gridDim.x * ROWS) {
-    const int row = (int)base + sub;
-    const bool valid = row < n2;
-    Acc<2> s = csr_row_dot_nb<LANES, 2>(k_rowptr, k_cols, k_vals, zu, row, valid, lane);
-    double t0 = 0.0, t1 = 0.0;
-    if (valid) {
-      const int s0 = bt_rowptr[2 * row], s1 = bt_rowptr[2 * row + 1], s2 = bt_rowptr[2 * row + 2];
-      for (int k = s0 + lane; k < s1; k += LANES) t0 = fma(__ldcs(bt_vals + k), __ldg(zp + __ldcs(bt_cols + k)), t0);
-      for (int k = s1 + lane; k < s2; k += LANES) t1 = fma(__ldcs(bt_vals + k), __ldg(zp + __ldcs(bt_cols + k)), t1);
-    }
-#pragma unroll
-    for (int o = LANES >> 1; o > 0; o >>= 1) {
-      t0 += __shfl_xor_sync(0xffffffffu, t0, o);
-      t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-    }
-    if (valid && lane < 2) {
-      const double sv = (lane == 1) ? (s.v[1] + t1) : (s.v[0] + t0);
-      const size_t i = (size_t)row * 2 + lane;
-      yu[i] = sv;
-      acc = fma(zu[i], sv, acc);
-    }
-  }
-  const double t = block_sum(acc, sh);
-  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+  EpiResidD0<NB> epi{dinv, b, r, d, c0p[0]};
+  row_engine<LANES, NB>(nrows, rowptr, cols, vals, x, epi);
 }
 
 #define SFEM_DISPATCH_LANES(L, ...)       \
@@ -225,7 +193,13 @@ __global__ void __launch_bounds__(kThreads) k_stokes_apply_u(int n2, const int* 
 
 // with NB = 2 the two result lanes need LANES >= 2
 static inline int lanes_for(const Csr& A, int nb) {
-  int l = pick_lanes(A.nnz, A.nrows);
+  // 4 entries per lane and pass: the smallest lane group that covers an average row in one pass
+  static int forced = -1;
+  if (forced < 0) { const char* e = std::getenv("SFEM_LANES"); forced = e ? std::atoi(e) : 0; }
+  const double avg = A.nrows > 0 ? (double)A.nnz / A.nrows : 1.0;
+  int l = 1;
+  while (l < 32 && 4.0 * l < avg) l <<= 1;
+  if (forced > 0) l = forced;
   if (l < nb) l = nb;
   return l;
 }
@@ -236,7 +210,7 @@ static inline double spmv_bytes(const Csr& A, int nb, int vec_passes) {
 
 template <int LANES, int NB>
 static int launch_spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st) {
-  const int grid = grid_for(A.nrows, kThreads / LANES);
+  const int grid = grid_for(A.nrows, kThreads / LANES, kSpmvBlocksPerSm);
   Prof prof(PC_SPMV, spmv_bytes(A, NB, mode == 0 ? 1 : 2), st);
   if (mode == 0) k_spmv<LANES, NB, 0><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, b, y);
   else if (mode == 1) k_spmv<LANES, NB, 1><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, b, y);
@@ -250,8 +224,7 @@ int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cu
   if (mode == 1 && b == nullptr) { set_error("spmv mode 1 needs b"); return SFEM_ERR_ARG; }
   if (nb != 1 && nb != 2) { set_error("spmv: nb must be 1 or 2"); return SFEM_ERR_ARG; }
   if (nb == 2 && (reinterpret_cast<uintptr_t>(x) & 15u)) { set_error("spmv: nb = 2 needs a 16-byte aligned x"); return SFEM_ERR_ARG; }
-  if (nb == 1 && A.tile_cap > 0 && mode != 2)
-    return spmv_staged_plan(A, A.tile_rows, A.tile_cap, A.stages, x, b, y, mode, st);
+  { const int took = staged_spmv(A, x, b, y, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   if (nb == 1) {
     SFEM_DISPATCH_LANES(lanes, return (launch_spmv<LN, 1>(A, x, b, y, mode, st)));
@@ -262,21 +235,25 @@ int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cu
 }
 
 int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* nparts, cudaStream_t st, int nb,
-             const double* dotx) {
+             const double* dotx, int mode) {
   if (dotx == nullptr) dotx = x;
+  if (mode != 0 && mode != 2) { set_error("spmv_dot: mode must be 0 or 2"); return SFEM_ERR_ARG; }
+  { const int took = staged_spmv_dot(A, x, dotx, y, partial, nparts, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   int grid = 1;
   Prof prof(PC_SPMV_DOT, spmv_bytes(A, nb, 2), st);
   if (nb == 1) {
     SFEM_DISPATCH_LANES(lanes, {
-      grid = grid_for(A.nrows, kThreads / LN);
-      k_spmv_dot<LN, 1><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, dotx, y, partial);
+      grid = grid_for(A.nrows, kThreads / LN, kSpmvBlocksPerSm);
+      if (mode == 0) k_spmv_dot<LN, 1, 0><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, dotx, y, partial);
+      else k_spmv_dot<LN, 1, 2><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, dotx, y, partial);
     });
   } else {
     SFEM_DISPATCH_LANES(lanes, {
       constexpr int L2 = LN < 2 ? 2 : LN;
-      grid = grid_for(A.nrows, kThreads / L2);
-      k_spmv_dot<L2, 2><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, dotx, y, partial);
+      grid = grid_for(A.nrows, kThreads / L2, kSpmvBlocksPerSm);
+      if (mode == 0) k_spmv_dot<L2, 2, 0><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, dotx, y, partial);
+      else k_spmv_dot<L2, 2, 2><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, x, dotx, y, partial);
     });
   }
   SFEM_LAUNCH_CHECK();
@@ -286,17 +263,18 @@ int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* npa
 
 int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
               const double* c12, int last, cudaStream_t st, int nb) {
+  { const int took = staged_cheb_step(A, dinv, d_old, d_new, r, x, c12, last, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   Prof prof(PC_CHEB, 12.0 * A.nnz + 12.0 * A.nrows + 48.0 * nb * A.nrows, st);
   if (nb == 1) {
     SFEM_DISPATCH_LANES(lanes, {
-      const int grid = grid_for(A.nrows, kThreads / LN);
+      const int grid = grid_for(A.nrows, kThreads / LN, kSpmvBlocksPerSm);
       k_cheb_step<LN, 1><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, d_old, d_new, r, x, c12, last);
     });
   } else {
     SFEM_DISPATCH_LANES(lanes, {
       constexpr int L2 = LN < 2 ? 2 : LN;
-      const int grid = grid_for(A.nrows, kThreads / L2);
+      const int grid = grid_for(A.nrows, kThreads / L2, kSpmvBlocksPerSm);
       k_cheb_step<L2, 2><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, d_old, d_new, r, x, c12, last);
     });
   }
@@ -306,17 +284,18 @@ int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_n
 
 int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
              const double* c0, cudaStream_t st, int nb) {
+  { const int took = staged_resid_d0(A, dinv, b, x, r, d, c0, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   Prof prof(PC_RESID_D0, 12.0 * A.nnz + 12.0 * A.nrows + 32.0 * nb * A.nrows, st);
   if (nb == 1) {
     SFEM_DISPATCH_LANES(lanes, {
-      const int grid = grid_for(A.nrows, kThreads / LN);
+      const int grid = grid_for(A.nrows, kThreads / LN, kSpmvBlocksPerSm);
       k_resid_d0<LN, 1><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, b, x, r, d, c0);
     });
   } else {
     SFEM_DISPATCH_LANES(lanes, {
       constexpr int L2 = LN < 2 ? 2 : LN;
-      const int grid = grid_for(A.nrows, kThreads / L2);
+      const int grid = grid_for(A.nrows, kThreads / L2, kSpmvBlocksPerSm);
       k_resid_d0<L2, 2><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, b, x, r, d, c0);
     });
   }
@@ -324,21 +303,11 @@ int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x,
   return SFEM_OK;
 }
 
+// y_u = K z_u (both components, matrix read once) ; y_u += BT z_p with the partial sums of <z_u, y_u>
 int stokes_apply_u(const Csr& K, const Csr& BT, const double* zu, const double* zp, double* yu, double* partial,
                    int* nparts, cudaStream_t st) {
-  int lanes = pick_lanes(K.nnz + BT.nnz / 2, K.nrows);
-  if (lanes < 2) lanes = 2;
-  int grid = 1;
-  Prof prof(PC_SPMV_DOT, 12.0 * (K.nnz + BT.nnz) + 12.0 * K.nrows + 8.0 * (2.0 * K.nrows * 3 + BT.ncols), st);
-  SFEM_DISPATCH_LANES(lanes, {
-    constexpr int L2 = LN < 2 ? 2 : LN;
-    grid = grid_for(K.nrows, kThreads / L2);
-    k_stokes_apply_u<L2><<<grid, kThreads, 0, st>>>(K.nrows, K.rowptr, K.cols, K.vals, BT.rowptr, BT.cols, BT.vals, zu, zp,
-                                                    yu, partial);
-  });
-  SFEM_LAUNCH_CHECK();
-  *nparts = grid;
-  return SFEM_OK;
+  SFEM_TRY(spmv(K, zu, nullptr, yu, 0, st, 2));
+  return spmv_dot(BT, zp, yu, partial, nparts, st, 1, zu, 2);
 }
 
 }  // namespace sfem

@@ -34,7 +34,11 @@ SIGNATURES = {
     'sfem_profile_stop': (_i, [_i, C.POINTER(_i), C.POINTER(_d), C.POINTER(C.c_float)]),
     'sfem_spmv_csr_f64': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _i, _p]),
     'sfem_spmv_csr_f64_nb': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
-    'sfem_spmv_csr_f64_staged': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    'sfem_staged_plan': (_i, [_i, _p, _i, _i, _p]),
+    'sfem_staged_register': (_i, [_p, _i, _p, _i, _i, _i]),
+    'sfem_staged_unregister': (None, [_p]),
+    'sfem_staged_set_min_tiles': (_i, [_i]),
+    'sfem_spmv_csr_f64_staged': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     'sfem_elem_p2_advdiff': (_i, [_i, _p, _p, _d, _p, _p, _p, _p]),
     'sfem_elem_p1_advdiff': (_i, [_i, _p, _p, _d, _p, _p, _i, _p, _p]),
     'sfem_elem_th_stokes': (_i, [_i, _p, _p, _p]),

@@ -70,10 +70,13 @@ def _arr(m):
 
 
 class DeviceCsr:
-    """CSR matrix in HBM (int32 indices, FP64 values); arrays padded for the staged SpMV."""
+    """CSR matrix in HBM (int32 indices, FP64 values), padded for the TMA-staged SpMV engine, with its
+    tile plan registered in the library (keyed by the device address of rowptr)."""
     PAD = 16
+    STAGED_CAP = 768             # entries per tile (one shared-memory stage)
+    STAGED_ROWS = 64             # rows per tile (64: 128 consumer threads per CTA, 128: 256)
 
-    def __init__(self, ctx: Context, nrows, ncols, rowptr, cols, vals=None, tile_rows=128):
+    def __init__(self, ctx: Context, nrows, ncols, rowptr, cols, vals=None, staged=True):
         torch = _torch()
         self.ctx = ctx
         self.nrows, self.ncols = int(nrows), int(ncols)
@@ -89,27 +92,35 @@ class DeviceCsr:
         self.vals = self.vals_buf[:self.nnz]
         if vals is not None:
             self.vals.copy_(ctx.up(vals, np.float64))
-        # staged-SpMV plan: exact max nnz of a tile (with the 16-byte rounding of the span start)
-        self.tile_rows = int(tile_rows)
-        r0 = np.arange(0, self.nrows, self.tile_rows)
-        r1 = np.minimum(r0 + self.tile_rows, self.nrows)
-        rpa = np.asarray(rowptr, dtype=np.int64)
-        self.tile_cap = int(np.max(rpa[r1] - (rpa[r0] & ~3))) if self.nrows else 0
+        self.tile_row = None
+        self.ntiles = 0
+        if staged and self.nrows > 0:
+            tr = np.zeros(self.nrows + 1, dtype=np.int32)
+            nt = ctx.lib.sfem_staged_plan(self.nrows, rp.ctypes.data_as(C.c_void_p), self.STAGED_CAP, self.STAGED_ROWS,
+                                          tr.ctypes.data_as(C.c_void_p))
+            if nt > 0:
+                self.ntiles = int(nt)
+                self.tile_row = ctx.up(tr[:nt + 1], np.int32)
+                capi.check(ctx.lib.sfem_staged_register(P(self.rowptr), self.nrows, P(self.tile_row), self.ntiles,
+                                                        self.STAGED_CAP, self.STAGED_ROWS), 'sfem_staged_register')
 
-    def spmv(self, x, y=None, b=None, mode=0, staged=False, stages=3, nb=1):
+    def __del__(self):
+        try:
+            if getattr(self, 'tile_row', None) is not None:
+                self.ctx.lib.sfem_staged_unregister(P(self.rowptr))
+                self.tile_row = None
+        except Exception:
+            pass
+
+    def spmv(self, x, y=None, b=None, mode=0, staged=False, nb=1):
+        """y = A x (0), b - A x (1), y += A x (2).  ``staged=True`` insists on the TMA-staged engine (error
+        if the matrix is too small / has no plan); otherwise the library picks the engine."""
         ctx = self.ctx
         if y is None:
             y = ctx.empty(self.nrows * nb)
-        if nb != 1 or self.nrows != self.ncols:
-            capi.check(ctx.lib.sfem_spmv_csr_f64_nb(self.nrows, self.ncols, self.nnz, P(self.rowptr), P(self.cols), P(self.vals),
-                                                    P(x), P(b), P(y), mode, nb, ctx.stream), 'sfem_spmv_csr_f64_nb')
-        elif staged:
-            capi.check(ctx.lib.sfem_spmv_csr_f64_staged(self.nrows, self.nnz, P(self.rowptr), P(self.cols), P(self.vals_buf),
-                                                        P(x), P(b), P(y), mode, self.tile_rows, self.tile_cap, stages,
-                                                        ctx.stream), 'sfem_spmv_csr_f64_staged')
-        else:
-            capi.check(ctx.lib.sfem_spmv_csr_f64(self.nrows, self.nnz, P(self.rowptr), P(self.cols), P(self.vals),
-                                                 P(x), P(b), P(y), mode, ctx.stream), 'sfem_spmv_csr_f64')
+        fn = ctx.lib.sfem_spmv_csr_f64_staged if staged else ctx.lib.sfem_spmv_csr_f64_nb
+        capi.check(fn(self.nrows, self.ncols, self.nnz, P(self.rowptr), P(self.cols), P(self.vals_buf),
+                      P(x), P(b), P(y), mode, nb, ctx.stream), 'sfem_spmv_csr_f64')
         return y
 
     def to_scipy(self):

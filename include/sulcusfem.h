@@ -54,14 +54,22 @@ int sfem_spmv_csr_f64(int nrows, int nnz, const int* rowptr, const int* cols, co
  * matrix stream is read once for both.  Rectangular matrices allowed (multigrid transfers, B, B^T). */
 int sfem_spmv_csr_f64_nb(int nrows, int ncols, int nnz, const int* rowptr, const int* cols, const double* vals,
                          const double* x, const double* b, double* y, int mode, int nb, void* stream);
-/* Shared-memory staged variant (modes 0 and 1): tiles of `tile_rows` consecutive rows (multiple of
- * 4) are streamed HBM -> shared memory by 1-D bulk async copies (TMA) through a `stages`-deep
- * mbarrier pipeline.  `tile_cap` = exact maximum over tiles of
- * rowptr[min(r0+tile_rows,nrows)] - (rowptr[r0] & ~3)  (the host has rowptr).  rowptr / cols / vals
- * must be 16-byte aligned and allocated with >= 4 elements of padding past their logical end. */
-int sfem_spmv_csr_f64_staged(int nrows, int nnz, const int* rowptr, const int* cols, const double* vals,
-                             const double* x, const double* b, double* y, int mode,
-                             int tile_rows, int tile_cap, int stages, void* stream);
+/* TMA-staged engine.  A tile plan is attached to a matrix by the DEVICE address of its rowptr array;
+ * once registered, every SpMV-family launch on that matrix (this call, the multigrid smoother, the
+ * Krylov drivers) streams the matrix HBM -> shared memory with bulk async copies and reduces rows
+ * from shared memory.  rowptr / cols / vals must be 16-byte aligned and readable >= 8 elements past
+ * their logical end.
+ *   sfem_staged_plan      HOST helper: greedy tiles of consecutive rows with <= cap_nnz entries and
+ *                         <= max_rows rows (64: 128 consumer threads per CTA, 128: 256); h_tile_row has room for nrows+1 ints; returns ntiles or -1
+ *   sfem_staged_register  tile_row: DEVICE copy of the plan, kept alive by the caller until unregister
+ *   sfem_spmv_csr_f64_staged  like sfem_spmv_csr_f64_nb but fails if the matrix has no usable plan */
+int sfem_staged_plan(int nrows, const int* h_rowptr, int cap_nnz, int max_rows, int* h_tile_row);
+int sfem_staged_register(const int* rowptr, int nrows, const int* tile_row, int ntiles, int cap_nnz, int max_rows);
+void sfem_staged_unregister(const int* rowptr);
+/* matrices with fewer tiles than min_tiles use the vector engine (<= 0: default = SM count); returns the old value */
+int sfem_staged_set_min_tiles(int min_tiles);
+int sfem_spmv_csr_f64_staged(int nrows, int ncols, int nnz, const int* rowptr, const int* cols, const double* vals,
+                             const double* x, const double* b, double* y, int mode, int nb, void* stream);
 
 /* ------------------------------------------------------------------ assembly ---------------- */
 /* Element matrices of  D grad(c).grad(phi) + (u.grad c) phi  on P2 triangles.

@@ -23,6 +23,15 @@ def small():
     return mesh, mk, om
 
 
+@pytest.fixture(params=['vector', 'staged'])
+def engine(request, ctx):
+    """Run a test once with the vector SpMV engine only and once with the TMA-staged engine forced on
+    every matrix that has a tile plan (by default only large matrices use it)."""
+    old = ctx.lib.sfem_staged_set_min_tiles(1 if request.param == 'staged' else 1 << 30)
+    yield request.param
+    ctx.lib.sfem_staged_set_min_tiles(old)
+
+
 def _rel(a, b):
     return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
 
@@ -42,14 +51,25 @@ def test_spmv_variants(ctx):
         x = rng.random(n); b = rng.random(n)
         dx = torch.from_numpy(x).cuda(); db = torch.from_numpy(b).cuda()
         ref = A @ x
-        for staged in (False, True):
+        for min_tiles, staged in ((1 << 30, False), (1, True)):
+            ctx.lib.sfem_staged_set_min_tiles(min_tiles)
             y = dA.spmv(dx, staged=staged)
             assert _rel(y.cpu().numpy(), ref) < 1e-14, (n, staged)
             r = dA.spmv(dx, b=db, mode=1, staged=staged)
             assert _rel(r.cpu().numpy(), b - ref) < 1e-13, (n, staged)
-        y2 = torch.from_numpy(b.copy()).cuda()
-        dA.spmv(dx, y=y2, mode=2)
-        assert _rel(y2.cpu().numpy(), b + ref) < 1e-14
+            y2 = torch.from_numpy(b.copy()).cuda()
+            dA.spmv(dx, y=y2, mode=2, staged=staged)
+            assert _rel(y2.cpu().numpy(), b + ref) < 1e-14
+        ctx.lib.sfem_staged_set_min_tiles(0)
+    # a row longer than one tile: no plan -> the vector engine serves the matrix
+    n = 5000
+    A = sp.random(n, n, 0.001, random_state=2, format='lil')
+    A[11, :3000] = 0.25
+    A = A.tocsr(); A.sort_indices()
+    dA = DeviceCsr(ctx, n, n, A.indptr, A.indices, A.data)
+    assert dA.tile_row is None
+    x = rng.random(n)
+    assert _rel(dA.spmv(torch.from_numpy(x).cuda()).cpu().numpy(), A @ x) < 1e-14
 
 
 def test_spmv_two_rhs_and_rectangular(ctx):
@@ -67,20 +87,24 @@ def test_spmv_two_rhs_and_rectangular(ctx):
         X = rng.random((n, 2)); B = rng.random((m, 2))
         dX = torch.from_numpy(X.ravel().copy()).cuda(); dB = torch.from_numpy(B.ravel().copy()).cuda()
         ref = A @ X
-        y = dA.spmv(dX, nb=2).cpu().numpy().reshape(m, 2)
-        assert _rel(y, ref) < 1e-14 or np.linalg.norm(ref) == 0
-        r = dA.spmv(dX, b=dB, mode=1, nb=2).cpu().numpy().reshape(m, 2)
-        assert _rel(r, B - ref) < 1e-13
-        y2 = dB.clone()
-        dA.spmv(dX, y=y2, mode=2, nb=2)
-        assert _rel(y2.cpu().numpy().reshape(m, 2), B + ref) < 1e-14
+        for min_tiles, staged in ((1 << 30, False), (1, True)):
+            ctx.lib.sfem_staged_set_min_tiles(min_tiles)
+            y = dA.spmv(dX, nb=2, staged=staged).cpu().numpy().reshape(m, 2)
+            assert _rel(y, ref) < 1e-14 or np.linalg.norm(ref) == 0
+            r = dA.spmv(dX, b=dB, mode=1, nb=2, staged=staged).cpu().numpy().reshape(m, 2)
+            assert _rel(r, B - ref) < 1e-13
+            y2 = dB.clone()
+            dA.spmv(dX, y=y2, mode=2, nb=2, staged=staged)
+            assert _rel(y2.cpu().numpy().reshape(m, 2), B + ref) < 1e-14
+        ctx.lib.sfem_staged_set_min_tiles(0)
         if m != n:
             y1 = dA.spmv(torch.from_numpy(X[:, 0].copy()).cuda(), nb=1).cpu().numpy()
             assert _rel(y1, ref[:, 0]) < 1e-14 or np.linalg.norm(ref) == 0
 
 
-def test_vcycle_two_rhs_equals_two_cycles(ctx, small):
-    """One nb = 2 V-cycle is bit-identical to two scalar V-cycles."""
+def test_vcycle_two_rhs_equals_two_cycles(ctx, small, engine):
+    """One nb = 2 V-cycle = two scalar V-cycles (up to the summation order of rows reduced by a
+    different number of lanes)."""
     import torch
     from sulcusfem.device import ScalarProblem
     mesh, mk, om = small
@@ -94,7 +118,7 @@ def test_vcycle_two_rhs_equals_two_cycles(ctx, small):
     za = p1.mg.vcycle(r[:, 0].contiguous()).cpu().numpy()
     zb = p1.mg.vcycle(r[:, 1].contiguous()).cpu().numpy()
     z2 = p2.mg.vcycle(r.reshape(-1).contiguous()).cpu().numpy().reshape(-1, 2)
-    assert np.array_equal(z2[:, 0], za) and np.array_equal(z2[:, 1], zb)
+    assert _rel(z2[:, 0], za) < 1e-13 and _rel(z2[:, 1], zb) < 1e-13
 
 
 def test_p2_assembly_matches_oracle(ctx, small):
@@ -170,7 +194,7 @@ def test_dense_inverse(ctx):
     assert np.abs(inv @ A.toarray() - np.eye(n)).max() < 1e-11
 
 
-def test_diffusion_solve_matches_lu(ctx, small):
+def test_diffusion_solve_matches_lu(ctx, small, engine):
     from oracle import cpu_oracle as co
     from sulcusfem.device import ScalarProblem
     mesh, mk, om = small
@@ -186,7 +210,7 @@ def test_diffusion_solve_matches_lu(ctx, small):
         assert _rel(c, ref) < 1e-10      # north_star: fields within 1e-10 relative L2
 
 
-def test_advdiff_solve_matches_lu(ctx, small):
+def test_advdiff_solve_matches_lu(ctx, small, engine):
     import torch
     from oracle import cpu_oracle as co
     from sulcusfem.device import ScalarProblem
@@ -206,7 +230,7 @@ def test_advdiff_solve_matches_lu(ctx, small):
         assert _rel(c, ref) < 1e-10
 
 
-def test_stokes_solve_matches_lu(ctx, small):
+def test_stokes_solve_matches_lu(ctx, small, engine):
     from oracle import cpu_oracle as co
     from sulcusfem.device import StokesProblem
     from sulcusfem import dofmap as dm

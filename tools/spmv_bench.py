@@ -36,9 +36,11 @@ def main():
     ap.add_argument('--nx', type=int, default=2000)
     ap.add_argument('--ny', type=int, default=200)
     ap.add_argument('--space', default='p2')
-    ap.add_argument('--variants', default='vector,staged:64:3,staged:128:3,staged:128:4,staged:256:3,staged:256:4')
+    ap.add_argument('--variants', default='vector,staged:1536,staged:1024,staged:2048')
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--nb', type=int, default=1)
     ap.add_argument('--no-flush', action='store_true')
+    ap.add_argument('--flush', default='write', help='write: 512 MiB memset (leaves dirty lines); read: memset then read another 512 MiB buffer (clean L2)')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'spmv_bench.json'))
     args = ap.parse_args()
     import torch
@@ -52,7 +54,8 @@ def main():
     x = torch.rand(n, dtype=torch.float64, device=ctx.device)
     y = torch.empty(n, dtype=torch.float64, device=ctx.device)
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
-    bytes_alg = 12.0 * nnz + 20.0 * n
+    flush2 = torch.ones(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
+    bytes_alg = 12.0 * nnz + 4.0 * n + 16.0 * n * args.nb
     peak = 6449.4
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -64,36 +67,41 @@ def main():
     for v in args.variants.split(','):
         parts = v.split(':')
         staged = parts[0] == 'staged'
-        tile_rows = int(parts[1]) if len(parts) > 1 else 128
-        stages = int(parts[2]) if len(parts) > 2 else 3
-        if len(parts) > 3:
-            os.environ['SFEM_STAGED_CTAS_PER_SM'] = parts[3]
-        else:
-            os.environ.pop('SFEM_STAGED_CTAS_PER_SM', None)
-        A = DeviceCsr(ctx, n, n, rowptr, cols, vals, tile_rows=tile_rows)
+        if len(parts) > 1:
+            DeviceCsr.STAGED_CAP = int(parts[1])
+        if len(parts) > 2:
+            DeviceCsr.STAGED_ROWS = int(parts[2])
+        ctx.lib.sfem_staged_set_min_tiles(1 if staged else 1 << 30)
+        A = DeviceCsr(ctx, n, n, rowptr, cols, vals)
+        nbv = args.nb
+        if nbv == 2 and x.numel() == n:
+            x = torch.rand(2 * n, dtype=torch.float64, device=ctx.device)
+            y = torch.empty(2 * n, dtype=torch.float64, device=ctx.device)
         for _ in range(3):
-            A.spmv(x, y, staged=staged, stages=stages)
+            A.spmv(x, y, staged=staged, nb=nbv)
         torch.cuda.synchronize()
         got = y.clone()
         if ref is None:
             import scipy.sparse as sp
             M = sp.csr_matrix((vals, cols, rowptr), shape=(n, n))
-            ref = torch.from_numpy(M @ x.cpu().numpy()).to(ctx.device)
+            ref = torch.from_numpy(np.ascontiguousarray(M @ x.cpu().numpy().reshape(n, nbv)).ravel()).to(ctx.device)
         err = float((got - ref).norm() / ref.norm())
         ms = []
         for _ in range(args.iters):
             if not args.no_flush:
                 flush.zero_()
+                if args.flush == 'read':
+                    flush2.sum()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            A.spmv(x, y, staged=staged, stages=stages)
+            A.spmv(x, y, staged=staged, nb=nbv)
             e1.record()
             torch.cuda.synchronize()
             ms.append(e0.elapsed_time(e1))
         ms = np.array(ms)
-        r = {"variant": v, "space": args.space, "n": n, "nnz": nnz, "ms_med": float(np.median(ms)), "ms_min": float(ms.min()),
+        r = {"variant": v, "nb": nbv, "ntiles": A.ntiles, "space": args.space, "n": n, "nnz": nnz, "ms_med": float(np.median(ms)), "ms_min": float(ms.min()),
              "gbs_med": bytes_alg / 1e9 / (float(np.median(ms)) / 1e3), "gbs_best": bytes_alg / 1e9 / (float(ms.min()) / 1e3),
-             "rel_err": err, "flush": not args.no_flush}
+             "rel_err": err, "flush": ("none" if args.no_flush else args.flush)}
         r["frac_of_measured_peak"] = r["gbs_med"] / peak
         results.append(r)
         print(json.dumps(r), flush=True)
