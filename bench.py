@@ -6,10 +6,11 @@
 One *step* = one full advection-diffusion sulcus run (BASELINE.json configs[1]): Taylor-Hood Stokes
 assembly + MINRES solve, P2 advection-diffusion assembly (Pe = 40, Robin mu = 1) + FGMRES solve, and
 all flux / mass functionals, on a synthetic sulcus mesh (w = 0.5, d = 1.0, h = 0.02, R uniform
-refinements).  Metric: DOFs/s = (Taylor-Hood dofs + P2 dofs) solved per second, whole job.
+refinements; default R = 2 -> 6.1 M DOFs per case, matrices larger than L2).  Metric: DOFs/s = (Taylor-Hood dofs + P2 dofs) solved per second, whole job.
 N > 1: every rank solves its own independent sweep case (no data-path collective) -> weak scaling.
 
-`value`    device-resident inputs, CUDA-event timed per step, L2 flushed between steps.
+`value`    device-resident inputs, CUDA-event timed per step, L2 flushed between steps (512 MiB written, then
+           512 MiB of another buffer read, so the cache holds clean unrelated lines).
 `e2e`      the same run through the reference-facing API (sulcusfem.solvers / analysis) with host
            inputs and host results, wall clock around each call (H2D / D2H inside).
 `roofline` dominant kernel family, from a per-launch CUDA-event profile of one extra step.
@@ -95,7 +96,7 @@ def workload_config(args):
     return {"workload": f"adv-diff sulcus (BASELINE configs[1]): Stokes TH + adv-diff P2 + functionals, "
                         f"w={W_SULCUS} d={D_SULCUS} Pe={PE:g} mu={MU:g}, synthetic Delaunay mesh h={args.h} "
                         f"+ {args.refine} uniform refinements",
-            "h": args.h, "refine": args.refine, "l2": "flushed between steps (512 MiB memset)",
+            "h": args.h, "refine": args.refine, "l2": "flushed between steps (512 MiB memset + 512 MiB read of a second buffer)",
             "krylov_rtol": 1e-13, "parallelism": f"case-sharded x{args.gpus} (no collectives)"}
 
 
@@ -180,6 +181,11 @@ def run_gpu(args, rank, world):
         return F, M
 
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
+    flush2 = torch.ones(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
+
+    def flush_l2():
+        flush.zero_()          # evicts everything ...
+        flush2.sum()           # ... and replaces the dirty lines of the memset by clean ones
 
     def barrier():
         if dist is not None:
@@ -193,7 +199,7 @@ def run_gpu(args, rank, world):
     lib.sfem_launch_count_reset()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for e0, e1 in ev:
-        flush.zero_()
+        flush_l2()
         e0.record()
         F, M = step()
         e1.record()
@@ -231,7 +237,7 @@ def run_gpu(args, rank, world):
     t0 = time.perf_counter()
     n_e2e = max(1, min(args.steps, 3))
     for _ in range(n_e2e):
-        flush.zero_()
+        flush_l2()
         fm, mm = api_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / n_e2e
@@ -257,9 +263,17 @@ def run_gpu(args, rank, world):
         sel = cats == k
         if sel.any():
             per_cat[name] = {"launches": int(sel.sum()), "ms": float(mss[sel].sum()), "gbytes": float(byts[sel].sum() / 1e9)}
+    # dominant kernel family: SpMV-type launches (plain / +dot / Chebyshev step / residual) on the system-level
+    # matrices, i.e. every launch whose algorithmic bytes are >= half of the largest such launch
     spmv_family = np.isin(cats, [0, 1, 2, 3, 8])
     big = spmv_family & (byts >= 0.5 * byts[spmv_family].max())
     ach = float(byts[big].sum() / 1e9 / (mss[big].sum() / 1e3))
+    fine_lvl = {}
+    for k, name in enumerate(CAT_NAMES):
+        sel = big & (cats == k)
+        if sel.any():
+            fine_lvl[name] = {"launches": int(sel.sum()), "avg_ms": float(mss[sel].mean()),
+                              "gbs": float(byts[sel].sum() / 1e9 / (mss[sel].sum() / 1e3))}
     peaks = {}
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -268,12 +282,14 @@ def run_gpu(args, rank, world):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": "FP64 CSR SpMV family on the system-level matrices (k_spmv / k_spmv_dot / k_cheb_step / k_resid_d0)",
+                "kernel": "FP64 CSR SpMV family on the system-level matrices (k_spmv / k_spmv_dot / k_cheb_step / k_resid_d0 / k_staged)",
                 "launches": int(big.sum()), "avg_launch_ms": float(mss[big].mean()),
                 "algorithmic_bytes_per_launch": float(byts[big].mean()),
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if 'hbm_gbs' in peaks else "fallback 6650 GB/s",
                 "share_of_profiled_step": float(mss[big].sum() / mss.sum()),
-                "by_category": per_cat, "profiled_step_kernel_ms": float(mss.sum())}
+                "system_level_by_kernel": fine_lvl,
+                "by_category": per_cat, "profiled_step_kernel_ms": float(mss.sum()),
+                "note": "profiled step runs un-graphed with a CUDA event pair around every launch; traffic: see profiles/"}
 
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 only
     cpu = None
@@ -308,7 +324,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--h', type=float, default=0.02)
-    ap.add_argument('--refine', type=int, default=int(os.environ.get('SFEM_BENCH_REFINE', 1)))
+    ap.add_argument('--refine', type=int, default=int(os.environ.get('SFEM_BENCH_REFINE', 2)))
     ap.add_argument('--cpu-h', type=float, default=0.04)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

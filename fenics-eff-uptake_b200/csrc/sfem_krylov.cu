@@ -6,6 +6,7 @@
 // decide when to stop.  Summation order is fixed -> results are bit-reproducible run to run.
 #include "sfem_mg.h"
 #include "sfem_graph.h"
+#include "sfem_dist.h"
 
 #include <cmath>
 #include <cstring>
@@ -43,10 +44,14 @@ int precond_apply(sfem_mg* mg, const double* dinv, int n, const double* r, doubl
 
 // ================================================================== CG
 // S: [0]=rz [1]=pq [2]=alpha [3]=beta [4]=rr [5]=bb
-__global__ void k_cg_alpha(const double* __restrict__ partial, int np, double* __restrict__ S) {
+// (with a communicator the partial sums are all-reduced over the ranks inside these one-block kernels)
+__global__ void k_cg_alpha(const double* __restrict__ partial, int np, double* __restrict__ S, DistDev D) {
   __shared__ double sh[33];
-  const double pq = block_sum_array(partial, np, sh);
-  if (threadIdx.x == 0) { S[1] = pq; S[2] = S[0] / pq; }
+  double pq = block_sum_array(partial, np, sh);
+  if (threadIdx.x == 0) {
+    dist_allreduce_scalars(D, &pq, 1);
+    S[1] = pq; S[2] = S[0] / pq;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) k_cg_update(int n, const double* __restrict__ S, const double* __restrict__ p,
@@ -66,11 +71,14 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int n, const double* __r
 }
 
 __global__ void k_cg_beta(const double* __restrict__ p_rz, int n_rz, const double* __restrict__ p_rr, int n_rr,
-                          double* __restrict__ S, int first) {
+                          double* __restrict__ S, int first, DistDev D) {
   __shared__ double sh[33];
-  const double rz = block_sum_array(p_rz, n_rz, sh);
-  const double rr = (n_rr > 0) ? block_sum_array(p_rr, n_rr, sh) : 0.0;
+  double rz = block_sum_array(p_rz, n_rz, sh);
+  double rr = (n_rr > 0) ? block_sum_array(p_rr, n_rr, sh) : 0.0;
   if (threadIdx.x == 0) {
+    double v[2] = {rz, rr};
+    dist_allreduce_scalars(D, v, 2);
+    rz = v[0]; rr = v[1];
     S[3] = first ? 0.0 : rz / S[0];
     S[0] = rz;
     if (n_rr > 0) S[4] = rr;
@@ -262,7 +270,11 @@ int sfem_krylov_cg(int n, int nnz, const int* rowptr, const int* cols, const dou
   if (n <= 0) { set_error("cg: empty system"); return SFEM_ERR_ARG; }
   if (mg && (!mg->ready || mg->nb != 1)) { set_error("cg: multigrid not set up (or nb != 1)"); return SFEM_ERR_ARG; }
   Csr A; A.nrows = A.ncols = n; A.nnz = nnz; A.rowptr = rowptr; A.cols = cols; A.vals = vals;
-  const size_t nn = (size_t)n;
+  // row-partitioned operator (multi-GPU): n = owned rows; vectors read by an SpMV carry the ghosts behind them
+  const Halo* halo = find_halo(rowptr);
+  if (halo) A.ncols = halo->dev.n_loc;
+  const DistDev D = dist_dev();
+  const size_t nn = (size_t)(halo ? halo->dev.n_loc : n);
   SFEM_TRY(t_ws.ensure(5 * nn + 3 * kMaxPartials + 64));
   SFEM_TRY(t_poll.init());
   bool forked = false;
@@ -284,7 +296,7 @@ int sfem_krylov_cg(int n, int nnz, const int* rowptr, const int* cols, const dou
   auto iteration = [&]() -> int {
     int npq = 0, nrz = 0;
     SFEM_TRY(spmv_dot(A, p, q, part0, &npq, st));
-    k_cg_alpha<<<1, kThreads, 0, st>>>(part0, npq, S);
+    k_cg_alpha<<<1, kThreads, 0, st>>>(part0, npq, S, D);
     SFEM_LAUNCH_CHECK();
     const int nrr = grid_for(n, kThreads * 4, 4);
     { Prof prof(PC_VEC, 48.0 * n, st);
@@ -292,7 +304,7 @@ int sfem_krylov_cg(int n, int nnz, const int* rowptr, const int* cols, const dou
     SFEM_LAUNCH_CHECK();
     SFEM_TRY(precond_apply(mg, dinv, n, r, z, st));
     SFEM_TRY(vec_dot_partial(n, r, z, part0, &nrz, st));
-    k_cg_beta<<<1, kThreads, 0, st>>>(part0, nrz, part1, nrr, S, 0);
+    k_cg_beta<<<1, kThreads, 0, st>>>(part0, nrz, part1, nrr, S, 0, D);
     SFEM_LAUNCH_CHECK();
     { Prof prof(PC_VEC, 24.0 * n, st);
     k_cg_p<<<grid_for(n, kThreads * 4), kThreads, 0, st>>>(n, S, z, p); }
@@ -303,7 +315,7 @@ int sfem_krylov_cg(int n, int nnz, const int* rowptr, const int* cols, const dou
     int np = 0;
     SFEM_TRY(precond_apply(mg, dinv, n, r, z, st));
     SFEM_TRY(vec_dot_partial(n, r, z, part0, &np, st));
-    k_cg_beta<<<1, kThreads, 0, st>>>(part0, np, nullptr, 0, S, 1);
+    k_cg_beta<<<1, kThreads, 0, st>>>(part0, np, nullptr, 0, S, 1, D);
     SFEM_LAUNCH_CHECK();
     SFEM_TRY(vec_copy(n, z, p, st));
     const bool use_graph = graphs_enabled();
@@ -345,6 +357,7 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
   cudaStream_t user = (cudaStream_t)stream;
   if (n <= 0 || restart < 1) { set_error("fgmres: bad arguments"); return SFEM_ERR_ARG; }
   if (mg && (!mg->ready || mg->nb != 1)) { set_error("fgmres: multigrid not set up (or nb != 1)"); return SFEM_ERR_ARG; }
+  if (dist_dev().nranks > 1) { set_error("fgmres: the row-partitioned (multi-GPU) path serves CG only in this version"); return SFEM_ERR_ARG; }
   Csr A; A.nrows = A.ncols = n; A.nnz = nnz; A.rowptr = rowptr; A.cols = cols; A.vals = vals;
   const int m = restart;
   const size_t nn = (size_t)n;

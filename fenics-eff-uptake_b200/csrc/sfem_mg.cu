@@ -13,6 +13,7 @@
 // CUDA graphs of a cycle stay valid when the operator is re-assembled.
 // With nb = 2 a cycle carries two interleaved right-hand sides (see sfem_spmv.cu).
 #include "sfem_mg.h"
+#include "sfem_dist.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -57,12 +58,20 @@ __global__ void __launch_bounds__(kThreads) k_gershgorin(int n, const int* __res
 }
 
 __global__ void k_cheb_coef(const double* __restrict__ partial, int np, double fixed_lmax, double ratio, int degree,
-                            double* __restrict__ coef) {
+                            double* __restrict__ coef, DistDev D) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   double lmax = fixed_lmax;
   if (np > 0) {
     lmax = 0.0;
     for (int i = 0; i < np; ++i) lmax = fmax(lmax, partial[i]);
+    if (D.nranks > 1) {
+      // row-partitioned operator: the bound must be the same on every rank (a rank-dependent polynomial
+      // would not be a symmetric preconditioner).  All-gather through the scalar all-reduce, then max.
+      double v[kAllreduceMaxK];
+      for (int q = 0; q < kAllreduceMaxK; ++q) v[q] = (q == D.rank) ? lmax : 0.0;
+      dist_allreduce_scalars(D, v, D.nranks < kAllreduceMaxK ? D.nranks : kAllreduceMaxK);
+      for (int q = 0; q < D.nranks && q < kAllreduceMaxK; ++q) lmax = fmax(lmax, v[q]);
+    }
     if (!(lmax > 0.0)) lmax = 2.0;
   }
   const double lmin = lmax / ratio;
@@ -83,7 +92,7 @@ constexpr int kCoarseFallbackDegree = 12;
 }  // namespace
 
 int cheb_setup(const Csr* A, const double* dinv, double fixed_lmax, double ratio, int degree, double* scratch,
-               double* coef, cudaStream_t st) {
+               double* coef, cudaStream_t st, bool distributed) {
   if (degree < 1 || degree > kMaxChebDegree) { set_error("chebyshev degree out of range"); return SFEM_ERR_ARG; }
   int np = 0;
   if (A != nullptr) {
@@ -91,7 +100,7 @@ int cheb_setup(const Csr* A, const double* dinv, double fixed_lmax, double ratio
     k_gershgorin<<<np, kThreads, 0, st>>>(A->nrows, A->rowptr, A->vals, dinv, scratch);
     SFEM_LAUNCH_CHECK();
   }
-  k_cheb_coef<<<1, 32, 0, st>>>(scratch, np, fixed_lmax, ratio, degree, coef);
+  k_cheb_coef<<<1, 32, 0, st>>>(scratch, np, fixed_lmax, ratio, degree, coef, distributed ? dist_dev() : DistDev());
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -120,17 +129,26 @@ int mg_vcycle_level(sfem_mg* mg, int l, const double* b, double* x, cudaStream_t
   MgLevel& L = mg->levels[l];
   const int last = (int)mg->levels.size() - 1;
   const int nb = mg->nb;
-  if (l == last) {
+  if (l == last && mg->tail == nullptr) {
     if (mg->coarse_inv != nullptr) return dense_gemv(L.A.nrows, mg->coarse_inv, b, x, st, nb);
     // no dense inverse given: a long smoothing sweep stands in for the coarse solve
     return smooth(L.A, L.dinv, L.coef, kCoarseFallbackDegree, b, x, L.r, L.d0, L.d1, true, st, nb);
   }
   SFEM_TRY(smooth(L.A, L.dinv, L.coef, mg->degree, b, x, L.r, L.d0, L.d1, true, st, nb));
   SFEM_TRY(spmv(L.A, x, b, L.r, 1, st, nb));
-  MgLevel& C = mg->levels[l + 1];
-  SFEM_TRY(spmv(L.R, L.r, nullptr, C.b, 0, st, nb));
-  SFEM_TRY(mg_vcycle_level(mg, l + 1, C.b, C.x, st));
-  SFEM_TRY(spmv(L.P, C.x, nullptr, x, 2, st, nb));
+  if (l == last) {
+    // last row-partitioned level: restrict the owned part, sum over ranks, solve the replicated
+    // hierarchy redundantly (identical on every rank), prolong to the owned rows
+    SFEM_TRY(spmv(L.R, L.r, nullptr, mg->tail_b, 0, st, nb));
+    SFEM_TRY(dist_allreduce_vec(active_dist(), mg->tail_b, mg->n_tail * nb, st));
+    SFEM_TRY(mg_vcycle_level(mg->tail, 0, mg->tail_b, mg->tail_x, st));
+    SFEM_TRY(spmv(L.P, mg->tail_x, nullptr, x, 2, st, nb));
+  } else {
+    MgLevel& C = mg->levels[l + 1];
+    SFEM_TRY(spmv(L.R, L.r, nullptr, C.b, 0, st, nb));
+    SFEM_TRY(mg_vcycle_level(mg, l + 1, C.b, C.x, st));
+    SFEM_TRY(spmv(L.P, C.x, nullptr, x, 2, st, nb));
+  }
   SFEM_TRY(smooth(L.A, L.dinv, L.coef, mg->degree, b, x, L.r, L.d0, L.d1, false, st, nb));
   return SFEM_OK;
 }
@@ -170,7 +188,10 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
       L.R.nrows = nc; L.R.ncols = n; L.R.nnz = h_P_nnz[l];
       L.R.rowptr = h_R_rowptr[l]; L.R.cols = h_R_cols[l]; L.R.vals = h_R_vals[l];
     }
-    const size_t bytes = (size_t)n * nb * sizeof(double);
+    // a row-partitioned level keeps ghost entries behind the owned ones in every vector an SpMV reads
+    const Halo* halo = find_halo(L.A.rowptr);
+    const int n_alloc = (halo && halo->dev.n_loc > n) ? halo->dev.n_loc : n;
+    const size_t bytes = (size_t)n_alloc * nb * sizeof(double);
     bool ok = cudaMalloc(&L.dinv, (size_t)n * sizeof(double)) == cudaSuccess && cudaMalloc(&L.r, bytes) == cudaSuccess &&
               cudaMalloc(&L.d0, bytes) == cudaSuccess && cudaMalloc(&L.d1, bytes) == cudaSuccess &&
               cudaMalloc(&L.coef, kChebCoefLen * sizeof(double)) == cudaSuccess;
@@ -196,14 +217,33 @@ int sfem_mg_setup(sfem_mg_t mg, void* stream) {
   for (size_t l = 0; l < nl; ++l) {
     MgLevel& L = mg->levels[l];
     SFEM_TRY(extract_diag_inv(L.A, L.dinv, st));
-    if (l + 1 == nl) {
+    const bool dist = find_halo(L.A.rowptr) != nullptr || mg->tail != nullptr;
+    if (l + 1 == nl && mg->tail == nullptr) {
       if (mg->coarse_inv == nullptr)
-        SFEM_TRY(cheb_setup(&L.A, L.dinv, 0.0, 30.0, kCoarseFallbackDegree, mg->scratch, L.coef, st));
+        SFEM_TRY(cheb_setup(&L.A, L.dinv, 0.0, 30.0, kCoarseFallbackDegree, mg->scratch, L.coef, st, dist));
       continue;
     }
-    SFEM_TRY(cheb_setup(&L.A, L.dinv, 0.0, mg->ratio, mg->degree, mg->scratch, L.coef, st));
+    SFEM_TRY(cheb_setup(&L.A, L.dinv, 0.0, mg->ratio, mg->degree, mg->scratch, L.coef, st, dist));
   }
   mg->ready = true;
+  return SFEM_OK;
+}
+
+/* Multi-GPU: `mg` holds the row-partitioned levels; below its last level the replicated hierarchy `tail`
+ * (n_tail dofs on its finest level) is solved redundantly.  P_last: n_own(last) x n_tail, R_last: n_tail x
+ * n_own(last) restricted to the owned columns (the partial results are summed over the ranks). */
+int sfem_mg_set_tail(sfem_mg_t mg, sfem_mg_t tail, int n_tail, int P_nnz, const int* P_rowptr, const int* P_cols,
+                     const double* P_vals, int R_nnz, const int* R_rowptr, const int* R_cols, const double* R_vals) {
+  if (!mg || !tail || n_tail <= 0 || tail->nb != mg->nb) { set_error("sfem_mg_set_tail: bad arguments"); return SFEM_ERR_ARG; }
+  MgLevel& L = mg->levels.back();
+  L.P.nrows = L.A.nrows; L.P.ncols = n_tail; L.P.nnz = P_nnz; L.P.rowptr = P_rowptr; L.P.cols = P_cols; L.P.vals = P_vals;
+  L.R.nrows = n_tail; L.R.ncols = L.A.nrows; L.R.nnz = R_nnz; L.R.rowptr = R_rowptr; L.R.cols = R_cols; L.R.vals = R_vals;
+  mg->tail = tail;
+  mg->n_tail = n_tail;
+  cudaFree(mg->tail_b); cudaFree(mg->tail_x);
+  const size_t bytes = (size_t)n_tail * mg->nb * sizeof(double);
+  SFEM_CUDA(cudaMalloc(&mg->tail_b, bytes));
+  SFEM_CUDA(cudaMalloc(&mg->tail_x, bytes));
   return SFEM_OK;
 }
 
@@ -230,6 +270,8 @@ void sfem_mg_destroy(sfem_mg_t mg) {
     cudaFree(L.dinv); cudaFree(L.r); cudaFree(L.d0); cudaFree(L.d1); cudaFree(L.x); cudaFree(L.b); cudaFree(L.coef);
   }
   cudaFree(mg->scratch);
+  cudaFree(mg->tail_b);
+  cudaFree(mg->tail_x);
   delete mg;
 }
 

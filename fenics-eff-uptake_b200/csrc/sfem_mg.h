@@ -31,6 +31,12 @@ struct sfem_mg {
   double ratio = 8.0;
   double* scratch = nullptr;
   bool ready = false;
+  // multi-GPU: levels above are row-partitioned; below them a replicated hierarchy (`tail`) is solved
+  // redundantly by every rank after an all-reduce of the restricted residual
+  sfem_mg* tail = nullptr;
+  int n_tail = 0;
+  double* tail_b = nullptr;
+  double* tail_x = nullptr;
 };
 
 namespace sfem {
@@ -41,6 +47,6 @@ int smooth(const Csr& A, const double* dinv, const double* coef, int degree, con
 // coef <- coefficients for the window [lmax/ratio, lmax]; lmax = Gershgorin bound of D^-1 A when A is
 // given (scratch: kMaxPartials doubles), else fixed_lmax.  No host synchronisation.
 int cheb_setup(const Csr* A, const double* dinv, double fixed_lmax, double ratio, int degree, double* scratch,
-               double* coef, cudaStream_t st);
+               double* coef, cudaStream_t st, bool distributed = false);
 int mg_vcycle_level(sfem_mg* mg, int l, const double* b, double* x, cudaStream_t st);
 }  // namespace sfem

@@ -17,6 +17,7 @@
 #include "sfem_common.cuh"
 #include "sfem_internal.h"
 #include "sfem_spmv_epi.cuh"
+#include "sfem_dist.h"
 
 #include <cstdlib>
 
@@ -224,6 +225,7 @@ int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cu
   if (mode == 1 && b == nullptr) { set_error("spmv mode 1 needs b"); return SFEM_ERR_ARG; }
   if (nb != 1 && nb != 2) { set_error("spmv: nb must be 1 or 2"); return SFEM_ERR_ARG; }
   if (nb == 2 && (reinterpret_cast<uintptr_t>(x) & 15u)) { set_error("spmv: nb = 2 needs a 16-byte aligned x"); return SFEM_ERR_ARG; }
+  SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));   // distributed matrix: fill the ghosts of x
   { const int took = staged_spmv(A, x, b, y, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   if (nb == 1) {
@@ -238,6 +240,7 @@ int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* npa
              const double* dotx, int mode) {
   if (dotx == nullptr) dotx = x;
   if (mode != 0 && mode != 2) { set_error("spmv_dot: mode must be 0 or 2"); return SFEM_ERR_ARG; }
+  SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));
   { const int took = staged_spmv_dot(A, x, dotx, y, partial, nparts, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   int grid = 1;
@@ -263,6 +266,7 @@ int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* npa
 
 int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
               const double* c12, int last, cudaStream_t st, int nb) {
+  SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(d_old), nb, st));
   { const int took = staged_cheb_step(A, dinv, d_old, d_new, r, x, c12, last, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   Prof prof(PC_CHEB, 12.0 * A.nnz + 12.0 * A.nrows + 48.0 * nb * A.nrows, st);
@@ -284,6 +288,7 @@ int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_n
 
 int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
              const double* c0, cudaStream_t st, int nb) {
+  SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));
   { const int took = staged_resid_d0(A, dinv, b, x, r, d, c0, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   Prof prof(PC_RESID_D0, 12.0 * A.nnz + 12.0 * A.nrows + 32.0 * nb * A.nrows, st);

@@ -21,6 +21,7 @@
 // residual estimate one iteration late, so the device never waits for the host.
 #include "sfem_mg.h"
 #include "sfem_graph.h"
+#include "sfem_dist.h"
 
 #include <cmath>
 #include <vector>
@@ -291,6 +292,7 @@ void sfem_stokes_destroy(sfem_stokes_t h) {
 
 int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, int maxit, double* h_info, void* stream) {
   if (!h || !h->mg->ready) { set_error("stokes solve: handle / multigrid not set up"); return SFEM_ERR_ARG; }
+  if (dist_dev().nranks > 1) { set_error("stokes solve: the row-partitioned (multi-GPU) path serves CG only in this version"); return SFEM_ERR_ARG; }
   if ((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15u) {
     set_error("stokes solve: b and x must be 16-byte aligned (interleaved velocity is read as double2)");
     return SFEM_ERR_ARG;

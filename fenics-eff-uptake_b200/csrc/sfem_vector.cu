@@ -3,6 +3,7 @@
 #include "sfem_common.cuh"
 #include "sfem_internal.h"
 #include "sfem_graph.h"
+#include "sfem_dist.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -85,11 +86,15 @@ __global__ void __launch_bounds__(kThreads) k_dot_partial(int n, const double* _
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
+// out[0] = sum of the partials, summed over all ranks when a communicator is active
 __global__ void __launch_bounds__(kThreads) k_sum_partials(const double* __restrict__ partial, int n,
-                                                           double* __restrict__ out) {
+                                                           double* __restrict__ out, DistDev D) {
   __shared__ double sh[33];
-  const double t = block_sum_array(partial, n, sh);
-  if (threadIdx.x == 0) out[0] = t;
+  double t = block_sum_array(partial, n, sh);
+  if (threadIdx.x == 0) {
+    dist_allreduce_scalars(D, &t, 1);
+    out[0] = t;
+  }
 }
 
 __global__ void k_diag_inv(int n, const int* __restrict__ rowptr, const int* __restrict__ cols,
@@ -205,8 +210,13 @@ int vec_dot_partial(int n, const double* x, const double* y, double* partial, in
   return SFEM_OK;
 }
 
+DistDev dist_dev() {
+  Dist* d = active_dist();
+  return d ? d->dev : DistDev();
+}
+
 int vec_sum_partials(const double* partial, int n, double* out, cudaStream_t st) {
-  k_sum_partials<<<1, kThreads, 0, st>>>(partial, n, out);
+  k_sum_partials<<<1, kThreads, 0, st>>>(partial, n, out, dist_dev());
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -215,7 +225,7 @@ int vec_sum_partials(const double* partial, int n, double* out, cudaStream_t st)
 int vec_dot_host(int n, const double* x, const double* y, double* scratch, double* h_out, cudaStream_t st) {
   int np = 0;
   SFEM_TRY(vec_dot_partial(n, x, y, scratch, &np, st));
-  k_sum_partials<<<1, kThreads, 0, st>>>(scratch, np, scratch + kMaxPartials);
+  k_sum_partials<<<1, kThreads, 0, st>>>(scratch, np, scratch + kMaxPartials, dist_dev());
   SFEM_LAUNCH_CHECK();
   SFEM_CUDA(cudaMemcpyAsync(h_out, scratch + kMaxPartials, sizeof(double), cudaMemcpyDeviceToHost, st));
   SFEM_CUDA(cudaStreamSynchronize(st));

@@ -62,6 +62,7 @@ SIGNATURES = {
                             C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), _p, _i, _d, _i]),
     'sfem_mg_setup': (_i, [_p, _p]),
     'sfem_mg_vcycle': (_i, [_p, _p, _p, _p]),
+    'sfem_mg_set_tail': (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
     'sfem_mg_lambda_max': (_i, [_p, C.POINTER(_d)]),
     'sfem_mg_destroy': (None, [_p]),
     'sfem_krylov_cg': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _d, _i, C.POINTER(_d), _p]),
@@ -70,6 +71,21 @@ SIGNATURES = {
                                 _i, _p, _p, _p, _p, _p, _p]),
     'sfem_stokes_solve': (_i, [_p, _p, _p, _d, _i, C.POINTER(_d), _p]),
     'sfem_stokes_destroy': (None, [_p]),
+    'sfem_dist_header_words': (C.c_longlong, [_i, C.c_longlong]),
+    'sfem_dist_create': (_p, [_i, _i, C.c_longlong, C.c_longlong]),
+    'sfem_dist_ipc_handle': (_i, [_p, _p]),
+    'sfem_dist_open_peers': (_i, [_p, _p]),
+    'sfem_dist_set_peer_pointer': (_i, [_p, _i, _p]),
+    'sfem_dist_mailbox': (_p, [_p]),
+    'sfem_dist_activate': (_i, [_p]),
+    'sfem_dist_error': (_i, [_p]),
+    'sfem_dist_destroy': (None, [_p]),
+    'sfem_halo_create': (_p, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'sfem_halo_destroy': (None, [_p]),
+    'sfem_halo_attach': (_i, [_p, _p]),
+    'sfem_halo_exchange': (_i, [_p, _p, _i, _i, _p]),
+    'sfem_dist_allreduce_vec': (_i, [_p, _p, _i, _i, _p]),
+    'sfem_dist_allreduce_scalars': (_i, [_p, _p, _i, _p]),
     'sfem_facet_functionals': (_i, [_i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _d, _d, _p, _p, _p]),
     'sfem_cell_functionals': (_i, [_i, _p, _p, _p, _i, _p, _p, _p]),
 }

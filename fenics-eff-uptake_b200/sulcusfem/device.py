@@ -246,7 +246,7 @@ class Multigrid:
         self.ctx, self.levels, self.transfers = ctx, levels, transfers
         self.nb = int(nb)
         nl = len(levels)
-        self.coarse_inv = ctx.zeros(levels[-1].n ** 2) if nl > 1 else None
+        self.coarse_inv = ctx.zeros(levels[-1].n ** 2) if (nl > 1 or levels[-1].n <= 2048) else None
         IntArr, PtrArr = C.c_int * nl, C.c_void_p * nl
 
         def parr(ts):
@@ -309,6 +309,7 @@ class ScalarProblem:
             self.levels.append(ScalarLevel(self.ctx, m, mk, 1, dirichlet_ids, robin_id))
         self.transfers = [DeviceTransfer(self.ctx, T, self.levels[l].bc_flag_host, self.levels[l + 1].bc_flag_host)
                           for l, T in enumerate(H.transfers)]
+        self.mg_cheb_degree, self.mg_eig_ratio = cheb_degree, eig_ratio
         self.mg = Multigrid(self.ctx, self.levels, self.transfers, cheb_degree, eig_ratio, nb)
         self.n = self.fine.n
         self.x = self.ctx.zeros(self.n)

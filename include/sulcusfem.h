@@ -147,6 +147,12 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
  * every level from the current operator values -- all on the device, no host synchronisation */
 int sfem_mg_setup(sfem_mg_t mg, void* stream);
 int sfem_mg_vcycle(sfem_mg_t mg, const double* b, double* x, void* stream);   /* x = M^-1 b */
+/* Multi-GPU: `mg` holds the row-partitioned levels (halo patterns attached to their matrices with
+ * sfem_halo_attach BEFORE sfem_mg_create); below its last level the replicated hierarchy `tail` (n_tail
+ * dofs on its finest level) is solved redundantly on every rank after a vector all-reduce.
+ * P_last: n_own(last) x n_tail; R_last: n_tail x n_own(last), owned columns only. */
+int sfem_mg_set_tail(sfem_mg_t mg, sfem_mg_t tail, int n_tail, int P_nnz, const int* P_rowptr, const int* P_cols,
+                     const double* P_vals, int R_nnz, const int* R_rowptr, const int* R_cols, const double* R_vals);
 int sfem_mg_lambda_max(sfem_mg_t mg, double* h_out);                            /* per level, host */
 void sfem_mg_destroy(sfem_mg_t mg);
 
@@ -183,6 +189,41 @@ sfem_stokes_t sfem_stokes_create(int n2, int nv,
                                  const int* zidx, const double* zw, const double* Cc);
 int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, int maxit, double* h_info, void* stream);
 void sfem_stokes_destroy(sfem_stokes_t h);
+
+/* ------------------------------------------------------------------ multi-GPU (one process per GPU) ---
+ * Peer-memory mailboxes over NVLink: every rank allocates one device mailbox, exports it with CUDA IPC
+ * (the 64-byte handles are all-gathered by the host, e.g. with torch.distributed) and maps its peers'.
+ * Halo exchange and the Krylov all-reduces then run as kernels that store straight into peer memory
+ * and synchronise through sequence flags -- no library collective on the data path.
+ * replaces: nothing (the reference is serial); SURVEY 8(e): domain-decomposed refined meshes.
+ *   mailbox_words   size of the mailbox in 8-byte words: sfem_dist_header_words(nranks, vec_cap) +
+ *                   the halo channels laid out by the host (sulcusfem/partition.py)
+ *   vec_cap         largest vector all-reduce (restriction onto the replicated coarse hierarchy) */
+typedef struct sfem_dist* sfem_dist_t;
+typedef struct sfem_halo* sfem_halo_t;
+long long sfem_dist_header_words(int nranks, long long vec_cap);
+sfem_dist_t sfem_dist_create(int rank, int nranks, long long mailbox_words, long long vec_cap);
+int sfem_dist_ipc_handle(sfem_dist_t h, void* out64);
+int sfem_dist_open_peers(sfem_dist_t h, const void* handles);
+int sfem_dist_set_peer_pointer(sfem_dist_t h, int q, void* mailbox);   /* single-process emulation (tests) */
+void* sfem_dist_mailbox(sfem_dist_t h);
+int sfem_dist_activate(sfem_dist_t h);
+int sfem_dist_error(sfem_dist_t h);
+void sfem_dist_destroy(sfem_dist_t h);
+/* Halo pattern of one level: HOST arrays of length nneigh (send_idx: send_ptr[nneigh] local owned
+ * indices in the order of the receiver's ghost list); offsets in 8-byte words into the peer's / own
+ * mailbox; cap = words per parity slot (>= 2 * count). */
+sfem_halo_t sfem_halo_create(int nneigh, int n_own, int n_loc, const int* peer, const int* send_ptr, const int* send_idx,
+                             const int* recv_cnt, const int* recv_off, const long long* peer_data_off,
+                             const long long* peer_flag_off, const long long* my_data_off, const long long* my_flag_off,
+                             const long long* cap);
+void sfem_halo_destroy(sfem_halo_t h);
+/* attach to the matrix whose rowptr lives at this device address: every SpMV-family launch on it first
+ * fills the ghost entries of its input vector (vectors hold n_loc entries per right-hand side) */
+int sfem_halo_attach(const int* rowptr, sfem_halo_t h);
+int sfem_halo_exchange(sfem_halo_t h, double* x, int nb, int phase, void* stream);
+int sfem_dist_allreduce_vec(sfem_dist_t h, double* x, int n, int phase, void* stream);
+int sfem_dist_allreduce_scalars(sfem_dist_t h, double* vals, int K, void* stream);
 
 /* ------------------------------------------------------------------ functionals -------------- */
 /* Facet functionals of analysis.py, all groups in one launch.

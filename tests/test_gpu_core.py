@@ -314,3 +314,65 @@ def test_functionals_match_oracle(ctx, small):
     close(F[7, 3], ref['_conc']['C_y0_ext']); close(F[8, 3], ref['_conc']['C_mouth'])
     close(Cc[1, 0], refm['sulcus_mass']); close(Cc[2, 0], refm['rectangle_mass'])
     close(Cc[1, 1], refm['sulcus_area']); close(Cc[2, 1], refm['rectangle_area'])
+
+
+def test_mailbox_halo_exchange_and_vector_allreduce_emulated(ctx):
+    """Two 'ranks' inside one process on one GPU: the send halves of all ranks run first, then the
+    wait + unpack halves (the production kernels do both in one launch, one rank per GPU)."""
+    import torch
+    import ctypes as C
+    from sulcusfem import hostmesh as hm, dofmap as dm, partition as pt, capi
+    from sulcusfem.device import P
+    from sulcusfem.dist import DistContext, DeviceHalo
+    lib = ctx.lib
+    mesh = hm.rectangle_mesh(10.0, 1.0, 30, 6)
+    cd = dm.p2_cell_dofs(mesh); n = dm.p2_num_dofs(mesh)
+    pat = dm.build_pattern(n, n, [(cd, cd)])
+    X = dm.p2_dof_coordinates(mesh)
+    R = 3
+    owner = pt.slab_owner(X[:, 0], R, X[:, 1])
+    gh = pt.ghost_sets(owner, R, [(pat.rowptr, pat.cols, owner)])
+    vec_cap = 500
+    header = int(lib.sfem_dist_header_words(R, vec_cap))
+    parts = [pt.partition_level(owner, R, r, gh, [header] * R, nb_max=2) for r in range(R)]
+    words = max(p.mailbox_end for p in parts) + 8
+    dists = [DistContext(ctx, r, R, words, vec_cap, emulate=True) for r in range(R)]
+    try:
+        for r in range(R):
+            for q in range(R):
+                if q != r:
+                    capi.check(lib.sfem_dist_set_peer_pointer(dists[r].handle, q, lib.sfem_dist_mailbox(dists[q].handle)))
+        halos = [DeviceHalo(ctx, p) for p in parts]
+        rng = np.random.default_rng(0)
+        for nb in (1, 2):
+            for trial in range(3):                       # several rounds: both slot parities get reused
+                xg = rng.random((n, nb))
+                xs = []
+                for p in parts:
+                    x = torch.zeros(p.n_loc * nb, dtype=torch.float64, device=ctx.device)
+                    x[:p.n_own * nb] = torch.from_numpy(xg[p.owned].ravel()).to(ctx.device)
+                    xs.append(x)
+                for phase in (1, 2):
+                    for r in range(R):
+                        dists[r].activate()
+                        halos[r].exchange(xs[r], nb=nb, phase=phase)
+                torch.cuda.synchronize()
+                for p, x in zip(parts, xs):
+                    assert np.array_equal(x.cpu().numpy().reshape(-1, nb)[p.n_own:], xg[p.ghost]), (nb, trial, p.rank)
+        # vector all-reduce
+        for trial in range(3):
+            vs = [torch.from_numpy(rng.random(vec_cap - 7)).to(ctx.device) for _ in range(R)]
+            want = sum(v.cpu().numpy() for v in vs)
+            for phase in (1, 2):
+                for r in range(R):
+                    capi.check(lib.sfem_dist_allreduce_vec(dists[r].handle, P(vs[r]), vec_cap - 7, phase, ctx.stream))
+            torch.cuda.synchronize()
+            for v in vs:
+                assert np.allclose(v.cpu().numpy(), want, rtol=1e-15)
+                assert np.array_equal(v.cpu().numpy(), vs[0].cpu().numpy())       # bit-identical on every rank
+        assert not any(d.error() for d in dists)
+        for h in halos:
+            lib.sfem_halo_destroy(h.handle)
+    finally:
+        for d in dists:
+            d.close()

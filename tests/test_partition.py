@@ -1,0 +1,150 @@
+"""Host-side domain decomposition: partition plans, local operators, and a world_size-2 gloo
+run that moves the halos with torch.distributed exactly as the device mailbox plan prescribes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _problem(nx=40, ny=8):
+    import scipy.sparse as sp
+    from sulcusfem import hostmesh as hm, dofmap as dm
+    mesh = hm.rectangle_mesh(10.0, 1.0, nx, ny)
+    cd = dm.p2_cell_dofs(mesh)
+    n = dm.p2_num_dofs(mesh)
+    pat = dm.build_pattern(n, n, [(cd, cd)])
+    X = dm.p2_dof_coordinates(mesh)
+    rng = np.random.default_rng(0)
+    vals = rng.random(pat.nnz)
+    A = sp.csr_matrix((vals, pat.cols, pat.rowptr), shape=(n, n))
+    return mesh, pat, X, vals, A
+
+
+@pytest.mark.parametrize('nranks', [2, 3, 4, 8])
+def test_partition_plan_and_local_spmv(nranks):
+    import scipy.sparse as sp
+    from sulcusfem import partition as pt
+    mesh, pat, X, vals, A = _problem()
+    n = A.shape[0]
+    owner = pt.slab_owner(X[:, 0], nranks, X[:, 1])
+    counts = np.bincount(owner, minlength=nranks)
+    assert counts.max() - counts.min() <= 1                     # balanced
+    gh = pt.ghost_sets(owner, nranks, [(pat.rowptr, pat.cols, owner)])
+    parts = [pt.partition_level(owner, nranks, r, gh, [17] * nranks, nb_max=2) for r in range(nranks)]
+    rng = np.random.default_rng(1)
+    xg = rng.random((n, 2))
+    yg = A @ xg
+    xs = []
+    for lp in parts:
+        assert np.array_equal(np.sort(np.concatenate([lp.owned, lp.ghost])), np.flatnonzero(lp.g2l >= 0))
+        x = np.zeros((lp.n_loc, 2))
+        x[:lp.n_own] = xg[lp.owned]
+        xs.append(x.reshape(-1))
+    pt.emulate_exchange(parts, xs, nb=2)
+    for lp, x in zip(parts, xs):
+        x = x.reshape(-1, 2)
+        assert np.array_equal(x[lp.n_own:], xg[lp.ghost])
+        rp, c, slot = pt.localize_csr(pat.rowptr, pat.cols, lp.owned, lp.g2l)
+        Al = sp.csr_matrix((vals[slot], c, rp), shape=(lp.n_own, lp.n_loc))
+        assert np.allclose(Al @ x, yg[lp.owned], rtol=1e-13, atol=0)
+        # x-slabs: at most two neighbours, symmetric relation, channels do not overlap
+        assert len(lp.neighbors) <= 2
+        for k, q in enumerate(lp.neighbors):
+            assert lp.rank in parts[q].neighbors
+            kk = parts[q].neighbors.index(lp.rank)
+            assert lp.peer_data_off[k] == parts[q].my_data_off[kk] and lp.peer_flag_off[k] == parts[q].my_flag_off[kk]
+            assert lp.cap[k] == parts[q].cap[kk] and lp.cap[k] % 2 == 0 and lp.my_data_off[k] % 2 == 0
+            assert len(lp.send_idx[k]) == parts[q].recv_cnt[kk] and 2 * lp.recv_cnt[k] <= lp.cap[k]
+        spans = sorted((lp.my_data_off[k], lp.my_flag_off[k] + 2) for k in range(len(lp.neighbors)))
+        assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+        assert spans[0][0] >= 17 and spans[-1][1] <= lp.mailbox_end
+
+
+def test_restriction_onto_replicated_level_sums_to_global():
+    """R restricted to owned columns: the partial products of all ranks add up to the global product."""
+    import scipy.sparse as sp
+    from sulcusfem import hostmesh as hm, partition as pt
+    from sulcusfem.hierarchy import midpoint_transfer
+    mesh = hm.rectangle_mesh(10.0, 1.0, 20, 4)
+    T = midpoint_transfer(mesh)                                  # P1(mesh) -> P2(mesh)
+    R = sp.csr_matrix((T.t_vals, T.t_cols, T.t_rowptr), shape=(T.n_coarse, T.n_fine))
+    from sulcusfem import dofmap as dm
+    X = dm.p2_dof_coordinates(mesh)
+    nranks = 3
+    owner = pt.slab_owner(X[:, 0], nranks, X[:, 1])
+    gh = pt.ghost_sets(owner, nranks, [])
+    rng = np.random.default_rng(3)
+    r = rng.random(T.n_fine)
+    total = np.zeros(T.n_coarse)
+    for q in range(nranks):
+        lp = pt.partition_level(owner, nranks, q, gh, [0] * nranks)
+        own_only = np.where(lp.g2l < lp.n_own, lp.g2l, -1)
+        rp, c, slot = pt.localize_csr(T.t_rowptr, T.t_cols, np.arange(T.n_coarse), own_only, drop_missing=True)
+        Rl = sp.csr_matrix((T.t_vals[slot], c, rp), shape=(T.n_coarse, lp.n_own))
+        total += Rl @ r[lp.owned]
+    assert np.allclose(total, R @ r, rtol=1e-13)
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(ROOT, 'fenics-eff-uptake_b200'))
+    import torch
+    import torch.distributed as dist
+    import scipy.sparse as sp
+    from sulcusfem import partition as pt
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    mesh, pat, X, vals, A = _problem(24, 6)
+    n = A.shape[0]
+    owner = pt.slab_owner(X[:, 0], world, X[:, 1])
+    gh = pt.ghost_sets(owner, world, [(pat.rowptr, pat.cols, owner)])
+    lp = pt.partition_level(owner, world, rank, gh, [0] * world)
+    xg = np.random.default_rng(5).random(n)
+    x = np.zeros(lp.n_loc)
+    x[:lp.n_own] = xg[lp.owned]
+    # halo exchange over gloo following the plan (the device path stores into peer mailboxes instead)
+    reqs, bufs = [], []
+    for k, q in enumerate(lp.neighbors):
+        reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(x[lp.send_idx[k]])), q))
+        b = torch.empty(lp.recv_cnt[k], dtype=torch.float64)
+        bufs.append(b)
+        reqs.append(dist.irecv(b, q))
+    for r in reqs:
+        r.wait()
+    for k, b in enumerate(bufs):
+        x[lp.recv_off[k]:lp.recv_off[k] + lp.recv_cnt[k]] = b.numpy()
+    rp, c, slot = pt.localize_csr(pat.rowptr, pat.cols, lp.owned, lp.g2l)
+    y = sp.csr_matrix((vals[slot], c, rp), shape=(lp.n_own, lp.n_loc)) @ x
+    # Krylov-style global dot through an all-reduce
+    d = torch.tensor([float(y @ y)], dtype=torch.float64)
+    dist.all_reduce(d)
+    yg = A @ xg
+    ok = np.allclose(y, yg[lp.owned], rtol=1e-13) and abs(d.item() - yg @ yg) <= 1e-12 * (yg @ yg)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_halo_and_allreduce():
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context('spawn')
+    mgr = ctxm.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctxm.Process(target=_gloo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(0) is True and out.get(1) is True
+
+
+def test_case_sharding_round_robin():
+    """Sweep cases (independent (geometry, mu) solves) are dealt to ranks without communication."""
+    from sulcusfem.sweep import shard_cases
+    cases = list(range(23 * 3))
+    got = [shard_cases(cases, r, 8) for r in range(8)]
+    assert sorted(sum(got, [])) == cases
+    assert max(map(len, got)) - min(map(len, got)) <= 1
