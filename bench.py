@@ -223,14 +223,22 @@ def run_gpu(args, rank, world):
     import contextlib
     import io
 
+    api_ms = {}
+
     def api_step():
+        t = [time.perf_counter()]
         with contextlib.redirect_stdout(io.StringIO()):
             u, p = solvers.stokes_solver(mr, Wsp, L_CH, H_CH, 'sulcus')
+            t.append(time.perf_counter())
             u._dev = None                                  # velocity re-enters from its host array (H2D)
             c = solvers.advdiff_solver(mr, u, Csp, Constant(D), Constant(mu), 'sulcus')
+            t.append(time.perf_counter())
             c._dev = None
             fm = analysis.compute_flux_metrics(c, u, mr, 'sulcus', {}, D, mu)
             mm = analysis.compute_mass_metrics(c, {}, 'sulcus')
+            t.append(time.perf_counter())
+        for name, a, b in (('stokes_solver', 0, 1), ('advdiff_solver', 1, 2), ('functionals', 2, 3)):
+            api_ms[name] = 1e3 * (t[b] - t[a])
         return fm, mm
     api_step()
     barrier()
@@ -309,7 +317,8 @@ def run_gpu(args, rank, world):
         "iterations": {"stokes_minres": info['stokes']['iterations'], "advdiff_fgmres": info['advdiff']['iterations'],
                        "stokes_relres": info['stokes']['relres'], "advdiff_relres": info['advdiff']['relres']},
         "e2e": {"value": world * ndof / e2e_s, "unit": "DOFs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s, "api": "sulcusfem.solvers.stokes_solver + advdiff_solver + analysis.compute_*_metrics"},
+                "ms_per_step": 1e3 * e2e_s, "last_step_breakdown_ms": api_ms,
+                "api": "sulcusfem.solvers.stokes_solver + advdiff_solver + analysis.compute_*_metrics"},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "setup_s": t_setup,
         "functionals": {"uptake_flux": fm['uptake_flux'], "total_mass": mm['total_mass']},

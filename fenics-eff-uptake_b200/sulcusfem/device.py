@@ -188,6 +188,10 @@ class ScalarLevel:
 
     def set_bc_values(self, values: Dict[int, object]):
         """values[id] = scalar or array over the dofs of that id; applied in dict order."""
+        key = tuple((i, float(v)) for i, v in values.items()) if all(np.isscalar(v) for v in values.values()) else None
+        if key is not None and getattr(self, '_bc_key', None) == key:
+            return None                                   # same constants as last time: already on the device
+        self._bc_key = key
         g = np.zeros(self.n)
         for i, v in values.items():
             g[self.bc_dofs[i]] = v

@@ -55,7 +55,13 @@ def th_cell_dofs(mesh: HostMesh) -> np.ndarray:
 
 
 def p2_dof_coordinates(mesh: HostMesh) -> np.ndarray:
-    return np.concatenate([mesh.coords, mesh.edge_midpoints()], axis=0)
+    """Coordinates of the P2 dofs (vertices, then edge midpoints); cached on the mesh (read-only)."""
+    X = getattr(mesh, '_p2_dof_coords', None)
+    if X is None:
+        X = np.concatenate([mesh.coords, mesh.edge_midpoints()], axis=0)
+        X.setflags(write=False)
+        mesh._p2_dof_coords = X
+    return X
 
 
 def p2_facet_dofs(mesh: HostMesh, facets: np.ndarray) -> np.ndarray:

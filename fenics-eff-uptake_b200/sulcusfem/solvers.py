@@ -203,16 +203,25 @@ def stokes_solver(mesh_results, W, L_domain, H, mesh_type="sulcus"):
     on id 2.  The reference's "pointwise" pressure pin matches no dof, so the
     pressure level is fixed by the outflow condition alone -- same here.
     """
-    unique_vals = np.unique(_markers_array(mesh_results['bc_markers']))
+    bm_obj = mesh_results['bc_markers']
+    unique_vals = getattr(bm_obj, '_unique_ids', None)
+    if unique_vals is None:
+        unique_vals = np.unique(_markers_array(bm_obj))
+        try:
+            bm_obj._unique_ids = unique_vals
+        except AttributeError:
+            pass
     print(f"Boundary markers present: {unique_vals}")
     try:
         mesh = _check_space(W, 'TH')
         bm = _markers_array(mesh_results['bc_markers'])
         prob = stokes_problem(mesh, bm)
-        X = dm.p2_dof_coordinates(mesh)
-        d1 = dm.dirichlet_dofs_p2(mesh, bm, 1)
         print(f"Trying pressure constraint at outlet center: ({L_domain}, {H/2})")
-        prob.set_bcs({1: (4.0 * X[d1, 1] * (H - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+        if getattr(prob, '_inflow_H', None) != float(H):    # Dirichlet data depend on the mesh and H only
+            X = dm.p2_dof_coordinates(mesh)
+            d1 = dm.dirichlet_dofs_p2(mesh, bm, 1)
+            prob.set_bcs({1: (4.0 * X[d1, 1] * (H - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+            prob._inflow_H = float(H)
         prob.assemble(bc_mode=1)
         ux, uy, p = prob.solve(rtol=STOKES_RTOL)
         if not np.isfinite(prob.last_info['relres']) or prob.last_info['relres'] > 1e-9:
