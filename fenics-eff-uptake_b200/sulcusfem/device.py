@@ -301,7 +301,10 @@ class ScalarProblem:
 
     def __init__(self, mesh: HostMesh, bc_markers: np.ndarray, dirichlet_ids=(1, 2), robin_id: Optional[int] = 4,
                  hierarchy: Optional[hy.Hierarchy] = None, ctx: Optional[Context] = None,
-                 cheb_degree=2, eig_ratio=8.0, nb=1):
+                 cheb_degree=None, eig_ratio=None, nb=1):
+        import os
+        cheb_degree = int(os.environ.get('SFEM_CHEB_DEGREE', 2)) if cheb_degree is None else cheb_degree
+        eig_ratio = float(os.environ.get('SFEM_EIG_RATIO', 8.0)) if eig_ratio is None else eig_ratio
         self.ctx = ctx or Context.get()
         self.mesh = mesh
         self.hierarchy = hierarchy or hy.build_hierarchy(mesh)
