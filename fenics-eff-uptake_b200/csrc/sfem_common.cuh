@@ -111,6 +111,15 @@ __device__ __forceinline__ double csr_row_dot(const int* __restrict__ rowptr, co
   return acc;
 }
 
+// 16-byte alignment of every pointer in the list (vectorised double2 streaming paths)
+template <class... P>
+inline bool aligned16(P... ptrs) {
+  uintptr_t acc = 0;
+  const uintptr_t v[] = {reinterpret_cast<uintptr_t>(ptrs)...};
+  for (uintptr_t a : v) acc |= a;
+  return (acc & 15u) == 0;
+}
+
 // lanes per row from the average row length
 inline int pick_lanes(long long nnz, int nrows) {
   double avg = nrows > 0 ? (double)nnz / nrows : 1.0;

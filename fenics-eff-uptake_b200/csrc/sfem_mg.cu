@@ -25,15 +25,26 @@ namespace sfem {
 namespace {
 
 // n = rows * nb entries; dinv is per row
-__global__ void k_cheb_init0(int n, int nb, const double* __restrict__ dinv, const double* __restrict__ b,
-                             double* __restrict__ r, double* __restrict__ d, double* __restrict__ x,
-                             const double* __restrict__ coef) {
+// NB == 2: one thread per dof streams the interleaved pair as double2 (b, r, d, x are 16-byte aligned)
+template <int NB>
+__global__ void __launch_bounds__(kThreads) k_cheb_init0(int nrows, const double* __restrict__ dinv,
+                                                         const double* __restrict__ b, double* __restrict__ r,
+                                                         double* __restrict__ d, double* __restrict__ x,
+                                                         const double* __restrict__ coef) {
   const double c0 = coef[1];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double bi = b[i];
-    r[i] = bi;
-    d[i] = c0 * dinv[nb == 2 ? (i >> 1) : i] * bi;
-    x[i] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
+    const double s = c0 * dinv[i];
+    if (NB == 2) {
+      const double2 bi = reinterpret_cast<const double2*>(b)[i];
+      reinterpret_cast<double2*>(r)[i] = bi;
+      reinterpret_cast<double2*>(d)[i] = make_double2(s * bi.x, s * bi.y);
+      reinterpret_cast<double2*>(x)[i] = make_double2(0.0, 0.0);
+    } else {
+      const double bi = b[i];
+      r[i] = bi;
+      d[i] = s * bi;
+      x[i] = 0.0;
+    }
   }
 }
 
@@ -110,7 +121,8 @@ int smooth(const Csr& A, const double* dinv, const double* coef, int degree, con
   const int n = A.nrows * nb;
   if (zero_init) {
     { Prof prof(PC_VEC, 32.0 * n + 8.0 * A.nrows, st);
-    k_cheb_init0<<<grid_for(n, kThreads * 2), kThreads, 0, st>>>(n, nb, dinv, b, r, d0, x, coef); }
+    if (nb == 2) k_cheb_init0<2><<<grid_for(A.nrows, kThreads * 2), kThreads, 0, st>>>(A.nrows, dinv, b, r, d0, x, coef);
+    else k_cheb_init0<1><<<grid_for(A.nrows, kThreads * 2), kThreads, 0, st>>>(A.nrows, dinv, b, r, d0, x, coef); }
     SFEM_LAUNCH_CHECK();
   } else {
     SFEM_TRY(resid_d0(A, dinv, b, x, r, d0, coef + 1, st, nb));

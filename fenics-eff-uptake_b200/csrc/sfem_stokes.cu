@@ -60,11 +60,30 @@ __global__ void k_sm_delta(const double* __restrict__ pu, int npu, const double*
 }
 
 // v_prev <- Az/gamma - (delta/gamma) v - (gamma/gamma_prev) v_prev     (then v_prev is the new v)
-__global__ void k_sm_vnext(int n, const double* __restrict__ S, const double* __restrict__ Az,
-                           const double* __restrict__ v, double* __restrict__ v_prev) {
+// (VEC: 16-byte aligned arrays are streamed as double2 pairs, two pairs in flight per thread)
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) k_sm_vnext(int n, const double* __restrict__ S, const double* __restrict__ Az,
+                                                       const double* __restrict__ v, double* __restrict__ v_prev) {
   const double invg = S[16], a = S[14], b = S[15];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    v_prev[i] = Az[i] * invg - a * v[i] - b * v_prev[i];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (VEC) {
+    const int n2 = n >> 1;
+    const double2* A2 = reinterpret_cast<const double2*>(Az);
+    const double2* V2 = reinterpret_cast<const double2*>(v);
+    double2* P2 = reinterpret_cast<double2*>(v_prev);
+    for (int i = tid; i < n2; i += 2 * nt) {
+      const int j = i + nt;
+      const bool two = j < n2;
+      const double2 a0 = A2[i], v0 = V2[i], p0 = P2[i];
+      double2 a1 = a0, v1 = v0, p1 = p0;
+      if (two) { a1 = A2[j]; v1 = V2[j]; p1 = P2[j]; }
+      P2[i] = make_double2(a0.x * invg - a * v0.x - b * p0.x, a0.y * invg - a * v0.y - b * p0.y);
+      if (two) P2[j] = make_double2(a1.x * invg - a * v1.x - b * p1.x, a1.y * invg - a * v1.y - b * p1.y);
+    }
+    if ((n & 1) && tid == 0) v_prev[n - 1] = Az[n - 1] * invg - a * v[n - 1] - b * v_prev[n - 1];
+  } else {
+    for (int i = tid; i < n; i += nt) v_prev[i] = Az[i] * invg - a * v[i] - b * v_prev[i];
+  }
 }
 
 __global__ void k_sm_rot(const double* __restrict__ partial, int np, double* __restrict__ S) {
@@ -88,13 +107,45 @@ __global__ void k_sm_rot(const double* __restrict__ partial, int np, double* __r
 }
 
 // w_prev <- (z/gamma - a3 w_prev - a2 w)/a1 ; x += xcoef w_prev        (then w_prev is the new w)
-__global__ void k_sm_wx(int n, const double* __restrict__ S, const double* __restrict__ z,
-                        const double* __restrict__ w, double* __restrict__ w_prev, double* __restrict__ x) {
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) k_sm_wx(int n, const double* __restrict__ S, const double* __restrict__ z,
+                                                    const double* __restrict__ w, double* __restrict__ w_prev,
+                                                    double* __restrict__ x) {
   const double invg = S[16], inv = 1.0 / S[9], a2 = S[10], a3 = S[11], xc = S[12];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double wn = (z[i] * invg - a3 * w_prev[i] - a2 * w[i]) * inv;
-    w_prev[i] = wn;
-    x[i] = fma(xc, wn, x[i]);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (VEC) {
+    const int n2 = n >> 1;
+    const double2* Z2 = reinterpret_cast<const double2*>(z);
+    const double2* W2 = reinterpret_cast<const double2*>(w);
+    double2* P2 = reinterpret_cast<double2*>(w_prev);
+    double2* X2 = reinterpret_cast<double2*>(x);
+    for (int i = tid; i < n2; i += 2 * nt) {
+      const int j = i + nt;
+      const bool two = j < n2;
+      const double2 z0 = Z2[i], w0 = W2[i], p0 = P2[i], x0 = X2[i];
+      double2 z1 = z0, w1 = w0, p1 = p0, x1 = x0;
+      if (two) { z1 = Z2[j]; w1 = W2[j]; p1 = P2[j]; x1 = X2[j]; }
+      const double2 n0 = make_double2((z0.x * invg - a3 * p0.x - a2 * w0.x) * inv, (z0.y * invg - a3 * p0.y - a2 * w0.y) * inv);
+      P2[i] = n0;
+      X2[i] = make_double2(fma(xc, n0.x, x0.x), fma(xc, n0.y, x0.y));
+      if (two) {
+        const double2 n1 = make_double2((z1.x * invg - a3 * p1.x - a2 * w1.x) * inv, (z1.y * invg - a3 * p1.y - a2 * w1.y) * inv);
+        P2[j] = n1;
+        X2[j] = make_double2(fma(xc, n1.x, x1.x), fma(xc, n1.y, x1.y));
+      }
+    }
+    if ((n & 1) && tid == 0) {
+      const int i = n - 1;
+      const double wn = (z[i] * invg - a3 * w_prev[i] - a2 * w[i]) * inv;
+      w_prev[i] = wn;
+      x[i] = fma(xc, wn, x[i]);
+    }
+  } else {
+    for (int i = tid; i < n; i += nt) {
+      const double wn = (z[i] * invg - a3 * w_prev[i] - a2 * w[i]) * inv;
+      w_prev[i] = wn;
+      x[i] = fma(xc, wn, x[i]);
+    }
   }
 }
 
@@ -216,7 +267,7 @@ int st_precond(sfem_stokes* h, const double* r, double* out, cudaStream_t st) {
 // one MINRES iteration with buffer parity q (z[q] holds the current unscaled z, v[q] the current v)
 int st_iteration(sfem_stokes* h, int q, double* x, cudaStream_t st) {
   const int n = h->n;
-  const int gv = grid_for(n, kThreads * 4);
+  const int gv = grid_for(n, kThreads * 4, 4);
   double* zc = h->z[q];     double* zn = h->z[q ^ 1];
   double* vc = h->v[q];     double* vp = h->v[q ^ 1];
   double* wc = h->w[q];     double* wp = h->w[q ^ 1];
@@ -224,7 +275,8 @@ int st_iteration(sfem_stokes* h, int q, double* x, cudaStream_t st) {
   k_sm_delta<<<1, kThreads, 0, st>>>(h->part_u, h->npu, h->part_p, h->npp, h->S);
   SFEM_LAUNCH_CHECK();
   { Prof prof(PC_VEC, 32.0 * n, st);
-  k_sm_vnext<<<gv, kThreads, 0, st>>>(n, h->S, h->Az, vc, vp); }
+  if (aligned16(h->Az, vc, vp)) k_sm_vnext<true><<<gv, kThreads, 0, st>>>(n, h->S, h->Az, vc, vp);
+  else k_sm_vnext<false><<<gv, kThreads, 0, st>>>(n, h->S, h->Az, vc, vp); }
   SFEM_LAUNCH_CHECK();
   SFEM_TRY(st_precond(h, vp, zn, st));                       // vp now holds v_{j+1}
   int np = 0;
@@ -232,7 +284,8 @@ int st_iteration(sfem_stokes* h, int q, double* x, cudaStream_t st) {
   k_sm_rot<<<1, kThreads, 0, st>>>(h->part, np, h->S);
   SFEM_LAUNCH_CHECK();
   { Prof prof(PC_VEC, 48.0 * n, st);
-  k_sm_wx<<<gv, kThreads, 0, st>>>(n, h->S, zc, wc, wp, x); }
+  if (aligned16(zc, wc, wp, x)) k_sm_wx<true><<<gv, kThreads, 0, st>>>(n, h->S, zc, wc, wp, x);
+  else k_sm_wx<false><<<gv, kThreads, 0, st>>>(n, h->S, zc, wc, wp, x); }
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

@@ -77,11 +77,32 @@ __global__ void k_mul_scale(int n, double a, const double* __restrict__ d, const
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a * d[i] * x[i];
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(kThreads) k_dot_partial(int n, const double* __restrict__ x,
                                                           const double* __restrict__ y, double* __restrict__ partial) {
   __shared__ double sh[33];
-  double acc = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc = fma(x[i], y[i], acc);
+  double acc = 0.0, acc1 = 0.0;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (VEC) {
+    const int n2 = n >> 1;
+    const double2* X2 = reinterpret_cast<const double2*>(x);
+    const double2* Y2 = reinterpret_cast<const double2*>(y);
+    for (int i = tid; i < n2; i += 2 * nt) {
+      const int j = i + nt;
+      const double2 x0 = X2[i], y0 = Y2[i];
+      acc = fma(x0.x, y0.x, acc);
+      acc = fma(x0.y, y0.y, acc);
+      if (j < n2) {
+        const double2 x1 = X2[j], y1 = Y2[j];
+        acc1 = fma(x1.x, y1.x, acc1);
+        acc1 = fma(x1.y, y1.y, acc1);
+      }
+    }
+    if ((n & 1) && tid == 0) acc = fma(x[n - 1], y[n - 1], acc);
+    acc += acc1;
+  } else {
+    for (int i = tid; i < n; i += nt) acc = fma(x[i], y[i], acc);
+  }
   const double t = block_sum(acc, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
@@ -204,7 +225,8 @@ int vec_mul_scale(int n, double a, const double* d, const double* x, double* y, 
 int vec_dot_partial(int n, const double* x, const double* y, double* partial, int* nparts, cudaStream_t st) {
   const int grid = grid_for(n, kThreads * 4, 4);
   Prof prof(PC_VEC, 16.0 * n, st);
-  k_dot_partial<<<grid, kThreads, 0, st>>>(n, x, y, partial);
+  if (aligned16(x, y)) k_dot_partial<true><<<grid, kThreads, 0, st>>>(n, x, y, partial);
+  else k_dot_partial<false><<<grid, kThreads, 0, st>>>(n, x, y, partial);
   SFEM_LAUNCH_CHECK();
   *nparts = grid;
   return SFEM_OK;
