@@ -16,128 +16,13 @@
 // mbarrier, multi-buffered, then reduced from shared memory.  See sfem_spmv_staged.cu.
 #include "sfem_common.cuh"
 #include "sfem_internal.h"
+#include "sfem_row_engine.cuh"
 #include "sfem_spmv_epi.cuh"
 #include "sfem_dist.h"
 
 #include <cstdlib>
 
 namespace sfem {
-
-// ------------------------------------------------------------------ pipelined row engine
-// A warp owns kThreads/LANES... rows per pass: LANES lanes per row, UNROLL entries per lane and pass.
-// Per row the dependent chain is  rowptr -> (cols, vals) -> gather x -> reduce -> epilogue loads;
-// executed naively that is three exposed memory latencies per row group and the kernel is
-// latency-bound (measured 3.6 TB/s on B200).  The engine software-pipelines it: while the gathers
-// of row group i are in flight it already holds the (cols, vals) of group i+1 in registers and has
-// the rowptr entries of group i+2 and the epilogue operands of group i+1 requested.
-template <int NB>
-struct Acc {
-  double v[NB];
-};
-
-constexpr int kUnroll = 4;
-constexpr int kSpmvBlocksPerSm = 4;   // matches __launch_bounds__(kThreads, 4): one resident wave, persistent grid-stride
-
-template <int NB>
-struct XVal;
-template <>
-struct XVal<1> {
-  double a;
-  __device__ __forceinline__ void load(const double* __restrict__ x, int col, bool ok) { a = ok ? __ldg(x + col) : 0.0; }
-  __device__ __forceinline__ void fma_into(double v, Acc<1>& acc) const { acc.v[0] = fma(v, a, acc.v[0]); }
-};
-template <>
-struct XVal<2> {
-  double2 a;
-  __device__ __forceinline__ void load(const double* __restrict__ x, int col, bool ok) {
-    a = ok ? __ldg(reinterpret_cast<const double2*>(x) + col) : make_double2(0.0, 0.0);
-  }
-  __device__ __forceinline__ void fma_into(double v, Acc<2>& acc) const {
-    acc.v[0] = fma(v, a.x, acc.v[0]);
-    acc.v[1] = fma(v, a.y, acc.v[1]);
-  }
-};
-
-template <int LANES>
-__device__ __forceinline__ void load_pass(const int* __restrict__ cols, const double* __restrict__ vals, int k, int e,
-                                          int (&cc)[kUnroll], double (&vv)[kUnroll]) {
-#pragma unroll
-  for (int j = 0; j < kUnroll; ++j) {
-    const int kk = k + j * LANES;
-    const bool ok = kk < e;
-    cc[j] = ok ? __ldcs(cols + kk) : -1;
-    vv[j] = ok ? __ldcs(vals + kk) : 0.0;
-  }
-}
-
-// Epi: struct with   Pre pre(int row, int lane, bool active)   (loads issued early)
-//                    void fin(int row, int lane, double value, const Pre&)   (called for lane < NB of valid rows)
-template <int LANES, int NB, class Epi>
-__device__ __forceinline__ void row_engine(int nrows, const int* __restrict__ rowptr, const int* __restrict__ cols,
-                                           const double* __restrict__ vals, const double* __restrict__ x, Epi& epi) {
-  constexpr int ROWS = kThreads / LANES;
-  const int lane = threadIdx.x % LANES;
-  const int sub = threadIdx.x / LANES;
-  const long long stride = (long long)gridDim.x * ROWS;
-  long long base = (long long)blockIdx.x * ROWS;
-  if (base >= nrows) return;
-  // prologue: row group 0 fully fetched, rowptr of group 1 requested
-  long long row = base + sub;
-  bool valid = row < nrows;
-  int s = 0, e = 0;
-  if (valid) { s = rowptr[row]; e = rowptr[row + 1]; }
-  int cc[kUnroll];
-  double vv[kUnroll];
-  load_pass<LANES>(cols, vals, s + lane, e, cc, vv);
-  typename Epi::Pre pre = epi.pre((int)row, lane, valid && lane < NB);
-  long long nrow = row + stride;
-  bool nvalid = nrow < nrows;
-  int ns = 0, ne = 0;
-  if (nvalid) { ns = rowptr[nrow]; ne = rowptr[nrow + 1]; }
-  for (; base < nrows; base += stride) {
-    // rowptr of the group after next
-    const long long nnrow = nrow + stride;
-    const bool nnvalid = nnrow < nrows;
-    int nns = 0, nne = 0;
-    if (nnvalid) { nns = rowptr[nnrow]; nne = rowptr[nnrow + 1]; }
-    // gathers of the current group (first pass)
-    XVal<NB> xv[kUnroll];
-#pragma unroll
-    for (int j = 0; j < kUnroll; ++j) xv[j].load(x, cc[j], cc[j] >= 0);
-    // (cols, vals) and epilogue operands of the next group
-    int ncc[kUnroll];
-    double nvv[kUnroll];
-    load_pass<LANES>(cols, vals, ns + lane, ne, ncc, nvv);
-    typename Epi::Pre npre = epi.pre((int)nrow, lane, nvalid && lane < NB);
-    Acc<NB> a0, a1;
-#pragma unroll
-    for (int c = 0; c < NB; ++c) { a0.v[c] = 0.0; a1.v[c] = 0.0; }
-#pragma unroll
-    for (int j = 0; j < kUnroll; ++j) xv[j].fma_into(vv[j], (j & 1) ? a1 : a0);
-    // rows longer than one pass (rare for FEM patterns)
-    for (int k = s + lane + kUnroll * LANES; k < e; k += kUnroll * LANES) {
-      load_pass<LANES>(cols, vals, k, e, cc, vv);
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j) xv[j].load(x, cc[j], cc[j] >= 0);
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j) xv[j].fma_into(vv[j], (j & 1) ? a1 : a0);
-    }
-#pragma unroll
-    for (int c = 0; c < NB; ++c) {
-      double t = a0.v[c] + a1.v[c];
-#pragma unroll
-      for (int o = LANES >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      a0.v[c] = t;
-    }
-    if (valid && lane < NB) epi.fin((int)row, lane, (NB == 2 && lane == 1) ? a0.v[NB - 1] : a0.v[0], pre);
-    // rotate the pipeline
-    row = nrow; valid = nvalid; s = ns; e = ne;
-    nrow = nnrow; nvalid = nnvalid; ns = nns; ne = nne;
-    pre = npre;
-#pragma unroll
-    for (int j = 0; j < kUnroll; ++j) { cc[j] = ncc[j]; vv[j] = nvv[j]; }
-  }
-}
 
 // ------------------------------------------------------------------ kernels
 template <int LANES, int NB, int MODE>
@@ -182,28 +67,17 @@ __global__ void __launch_bounds__(kThreads, 4) k_resid_d0(int nrows, const int* 
   row_engine<LANES, NB>(nrows, rowptr, cols, vals, x, epi);
 }
 
-#define SFEM_DISPATCH_LANES(L, ...)       \
-  switch (L) {                            \
-    case 1: { constexpr int LN = 1; __VA_ARGS__; } break;   \
-    case 2: { constexpr int LN = 2; __VA_ARGS__; } break;   \
-    case 4: { constexpr int LN = 4; __VA_ARGS__; } break;   \
-    case 8: { constexpr int LN = 8; __VA_ARGS__; } break;   \
-    case 16: { constexpr int LN = 16; __VA_ARGS__; } break; \
-    default: { constexpr int LN = 32; __VA_ARGS__; } break; \
-  }
-
-// with NB = 2 the two result lanes need LANES >= 2
-static inline int lanes_for(const Csr& A, int nb) {
-  // 4 entries per lane and pass: the smallest lane group that covers an average row in one pass
+int engine_lanes(long long nnz, int nrows, int nb) {
   static int forced = -1;
   if (forced < 0) { const char* e = std::getenv("SFEM_LANES"); forced = e ? std::atoi(e) : 0; }
-  const double avg = A.nrows > 0 ? (double)A.nnz / A.nrows : 1.0;
+  const double avg = nrows > 0 ? (double)nnz / nrows : 1.0;
   int l = 1;
   while (l < 32 && 4.0 * l < avg) l <<= 1;
   if (forced > 0) l = forced;
   if (l < nb) l = nb;
   return l;
 }
+static inline int lanes_for(const Csr& A, int nb) { return engine_lanes(A.nnz, A.nrows, nb); }
 
 static inline double spmv_bytes(const Csr& A, int nb, int vec_passes) {
   return 12.0 * A.nnz + 4.0 * A.nrows + 8.0 * nb * ((double)A.ncols + (double)A.nrows * vec_passes);

@@ -9,10 +9,11 @@ namespace sfem {
 
 // ---- epilogues
 // MODE 0: y = s;  1: y = b - s;  2: y += s
-template <int NB, int MODE>
+// (TX = storage type of the vectors: double, or float in the FP32-storage preconditioner; values are FP64)
+template <int NB, int MODE, class TX = double>
 struct EpiStore {
-  const double* __restrict__ b;
-  double* __restrict__ y;
+  const TX* __restrict__ b;
+  TX* __restrict__ y;
   struct Pre { double a; };
   __device__ __forceinline__ Pre pre(int row, int lane, bool active) const {
     Pre p; p.a = 0.0;
@@ -25,7 +26,7 @@ struct EpiStore {
   }
   __device__ __forceinline__ void fin(int row, int lane, double sv, const Pre& p) const {
     const size_t i = (size_t)row * NB + lane;
-    y[i] = (MODE == 0) ? sv : (MODE == 1 ? p.a - sv : p.a + sv);
+    y[i] = (TX)((MODE == 0) ? sv : (MODE == 1 ? p.a - sv : p.a + sv));
   }
 };
 
@@ -55,13 +56,13 @@ struct EpiDot {
 
 // One fused Chebyshev-Jacobi step (see sfem_mg.cu), x of the engine = d_old:
 //   t = (A d_old)_i;  r_i -= t;  x_i += d_old_i (+ d_new_i when LAST);  d_new_i = c1 d_old_i + c2 dinv_i r_i
-template <int NB>
+template <int NB, class TX = double>
 struct EpiCheb {
-  const double* __restrict__ dinv;
-  const double* __restrict__ d_old;
-  double* __restrict__ d_new;
-  double* __restrict__ r;
-  double* __restrict__ xx;
+  const TX* __restrict__ dinv;
+  const TX* __restrict__ d_old;
+  TX* __restrict__ d_new;
+  TX* __restrict__ r;
+  TX* __restrict__ xx;
   double c1, c2;
   int last;
   struct Pre { double r, d, di, x; };
@@ -77,19 +78,19 @@ struct EpiCheb {
     const size_t i = (size_t)row * NB + lane;
     const double rn = p.r - t;
     const double dn = c1 * p.d + c2 * p.di * rn;
-    r[i] = rn;
-    d_new[i] = dn;
-    xx[i] = p.x + (last ? (p.d + dn) : p.d);
+    r[i] = (TX)rn;
+    d_new[i] = (TX)dn;
+    xx[i] = (TX)(p.x + (last ? (p.d + dn) : p.d));
   }
 };
 
 // r = b - A x ; d = c0 * dinv * r      (start of a smoothing sweep with a non-zero iterate)
-template <int NB>
+template <int NB, class TX = double>
 struct EpiResidD0 {
-  const double* __restrict__ dinv;
-  const double* __restrict__ b;
-  double* __restrict__ r;
-  double* __restrict__ d;
+  const TX* __restrict__ dinv;
+  const TX* __restrict__ b;
+  TX* __restrict__ r;
+  TX* __restrict__ d;
   double c0;
   struct Pre { double b, di; };
   __device__ __forceinline__ Pre pre(int row, int lane, bool active) const {
@@ -100,8 +101,8 @@ struct EpiResidD0 {
   __device__ __forceinline__ void fin(int row, int lane, double sv, const Pre& p) const {
     const size_t i = (size_t)row * NB + lane;
     const double rr = p.b - sv;
-    r[i] = rr;
-    d[i] = c0 * p.di * rr;
+    r[i] = (TX)rr;
+    d[i] = (TX)(c0 * p.di * rr);
   }
 };
 
