@@ -386,6 +386,7 @@ int sfem_facet_p1_robin(int nf, const double* fgeo, const int* fdofs, double mu_
 int sfem_gather_csr(int nnz, const int* contrib_ptr, const int* contrib_code, const double* E, double* vals,
                     void* stream) {
   if (nnz <= 0) return SFEM_OK;
+  sell_mark_dirty(vals);
   Prof prof(PC_GATHER, (double)nnz * 12.0, (cudaStream_t)stream);   // + 12 B per contribution, unknown here
   k_gather<<<grid_for(nnz, kThreads, 16), kThreads, 0, (cudaStream_t)stream>>>(nnz, contrib_ptr, contrib_code, E, vals);
   SFEM_LAUNCH_CHECK();
@@ -394,6 +395,7 @@ int sfem_gather_csr(int nnz, const int* contrib_ptr, const int* contrib_code, co
 
 int sfem_csr_extract(int n, const int* slot, const double* src_vals, double* dst_vals, void* stream) {
   if (n <= 0) return SFEM_OK;
+  sell_mark_dirty(dst_vals);
   Prof prof(PC_GATHER, (double)n * 20.0, (cudaStream_t)stream);
   k_extract<<<grid_for(n, kThreads * 2, 16), kThreads, 0, (cudaStream_t)stream>>>(n, slot, src_vals, dst_vals);
   SFEM_LAUNCH_CHECK();
@@ -419,6 +421,7 @@ int sfem_apply_dirichlet(int n, int nnz, const int* rowptr, const int* cols, dou
   if (n <= 0) return SFEM_OK;
   if (mode != 0 && mode != 1) { set_error("dirichlet mode must be 0 or 1"); return SFEM_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
+  sell_mark_dirty(vals);
   const int lanes = pick_lanes(nnz, n);
   switch (lanes) {
     case 1: case 2:

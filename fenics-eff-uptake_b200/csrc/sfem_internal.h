@@ -35,6 +35,17 @@ int staged_cheb_step(const Csr& A, const double* dinv, const double* d_old, doub
 int staged_resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
                     const double* c0, int nb, cudaStream_t st);
 
+// sfem_spmv_sell.cu: sliced-ELL mirror engine; same return convention as the staged engine
+int sell_spmv(const Csr& A, const double* x, const double* b, double* y, int mode, int nb, cudaStream_t st);
+int sell_spmv_dot(const Csr& A, const double* x, const double* dx, double* y, double* partial, int* nparts, int mode,
+                  int nb, cudaStream_t st);
+int sell_cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
+                   const double* c12, int last, int nb, cudaStream_t st);
+int sell_resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
+                  const double* c0, int nb, cudaStream_t st);
+void sell_mark_dirty(const double* csr_vals);     // called by every entry that writes CSR values
+int sell_ensure_all(cudaStream_t st);             // re-pack every dirty mirror (solver entries, before graph replays)
+
 // sfem_vector.cu
 int vec_set(int n, double a, double* x, cudaStream_t st);
 int vec_copy(int n, const double* x, double* y, cudaStream_t st);

@@ -267,6 +267,7 @@ extern "C" {
 int sfem_krylov_cg(int n, int nnz, const int* rowptr, const int* cols, const double* vals, sfem_mg_t mg,
                    const double* b, double* x, double rtol, int maxit, double* h_info, void* stream) {
   cudaStream_t user = (cudaStream_t)stream;
+  SFEM_TRY(sell_ensure_all(user));          // dirty sliced-ELL mirrors are re-packed before any graph replay
   if (n <= 0) { set_error("cg: empty system"); return SFEM_ERR_ARG; }
   if (mg && (!mg->ready || mg->nb != 1)) { set_error("cg: multigrid not set up (or nb != 1)"); return SFEM_ERR_ARG; }
   Csr A; A.nrows = A.ncols = n; A.nnz = nnz; A.rowptr = rowptr; A.cols = cols; A.vals = vals;
@@ -355,6 +356,7 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
                        const double* b, double* x, double rtol, int restart, int maxit, double* h_info,
                        void* stream) {
   cudaStream_t user = (cudaStream_t)stream;
+  SFEM_TRY(sell_ensure_all(user));          // dirty sliced-ELL mirrors are re-packed before any graph replay
   if (n <= 0 || restart < 1) { set_error("fgmres: bad arguments"); return SFEM_ERR_ARG; }
   if (mg && (!mg->ready || mg->nb != 1)) { set_error("fgmres: multigrid not set up (or nb != 1)"); return SFEM_ERR_ARG; }
   if (dist_dev().nranks > 1) { set_error("fgmres: the row-partitioned (multi-GPU) path serves CG only in this version"); return SFEM_ERR_ARG; }

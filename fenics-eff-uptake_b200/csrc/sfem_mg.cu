@@ -225,6 +225,7 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
 int sfem_mg_setup(sfem_mg_t mg, void* stream) {
   if (!mg) { set_error("null mg handle"); return SFEM_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
+  SFEM_TRY(sell_ensure_all(st));            // operator values were just re-assembled: refresh the sliced-ELL mirrors
   const size_t nl = mg->levels.size();
   for (size_t l = 0; l < nl; ++l) {
     MgLevel& L = mg->levels[l];
@@ -261,6 +262,7 @@ int sfem_mg_set_tail(sfem_mg_t mg, sfem_mg_t tail, int n_tail, int P_nnz, const 
 
 int sfem_mg_vcycle(sfem_mg_t mg, const double* b, double* x, void* stream) {
   if (!mg || !mg->ready) { set_error("mg handle not set up"); return SFEM_ERR_ARG; }
+  SFEM_TRY(sell_ensure_all((cudaStream_t)stream));
   return mg_vcycle_level(mg, 0, b, x, (cudaStream_t)stream);
 }
 

@@ -11,6 +11,9 @@
 // is the same scalar stiffness matrix for u_x and u_y, so the Stokes solver runs everything that
 // touches it (operator, smoother, transfers) with NB = 2.
 //
+// Variant 3 ("sliced ELL", sfem_spmv_sell.cu): matrices with a registered SELL-32 mirror are served by a
+// one-lane-per-row kernel with perfectly coalesced matrix loads; it is tried first.
+//
 // Variant 2 ("staged"): a CTA owns a block of consecutive rows; its contiguous span of vals/cols is
 // streamed HBM -> shared memory with 1-D bulk async copies (TMA, cp.async.bulk) completing on an
 // mbarrier, multi-buffered, then reduced from shared memory.  See sfem_spmv_staged.cu.
@@ -100,6 +103,7 @@ int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cu
   if (nb != 1 && nb != 2) { set_error("spmv: nb must be 1 or 2"); return SFEM_ERR_ARG; }
   if (nb == 2 && (reinterpret_cast<uintptr_t>(x) & 15u)) { set_error("spmv: nb = 2 needs a 16-byte aligned x"); return SFEM_ERR_ARG; }
   SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));   // distributed matrix: fill the ghosts of x
+  { const int took = sell_spmv(A, x, b, y, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   { const int took = staged_spmv(A, x, b, y, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   if (nb == 1) {
@@ -115,6 +119,7 @@ int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* npa
   if (dotx == nullptr) dotx = x;
   if (mode != 0 && mode != 2) { set_error("spmv_dot: mode must be 0 or 2"); return SFEM_ERR_ARG; }
   SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));
+  { const int took = sell_spmv_dot(A, x, dotx, y, partial, nparts, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   { const int took = staged_spmv_dot(A, x, dotx, y, partial, nparts, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   int grid = 1;
@@ -141,6 +146,7 @@ int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* npa
 int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
               const double* c12, int last, cudaStream_t st, int nb) {
   SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(d_old), nb, st));
+  { const int took = sell_cheb_step(A, dinv, d_old, d_new, r, x, c12, last, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   { const int took = staged_cheb_step(A, dinv, d_old, d_new, r, x, c12, last, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   Prof prof(PC_CHEB, 12.0 * A.nnz + 12.0 * A.nrows + 48.0 * nb * A.nrows, st);
@@ -163,6 +169,7 @@ int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_n
 int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
              const double* c0, cudaStream_t st, int nb) {
   SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));
+  { const int took = sell_resid_d0(A, dinv, b, x, r, d, c0, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   { const int took = staged_resid_d0(A, dinv, b, x, r, d, c0, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
   Prof prof(PC_RESID_D0, 12.0 * A.nnz + 12.0 * A.nrows + 32.0 * nb * A.nrows, st);

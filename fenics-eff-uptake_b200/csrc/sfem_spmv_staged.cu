@@ -22,6 +22,7 @@
 #include "sfem_common.cuh"
 #include "sfem_internal.h"
 #include "sfem_spmv_epi.cuh"
+#include "sfem_tma.cuh"
 
 #include <cstdlib>
 #include <mutex>
@@ -37,46 +38,9 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxTileRows = 128;         // rows per tile = consumer lane pairs = CT / 2 (CT = 128 or 256)
 constexpr int kPhase1Unroll = 6;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 // barrier among the consumer warps only (the producer warp never joins)
 template <int CT>
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
-
-template <int NB, int MODE>
-__device__ __forceinline__ double epi_acc(const EpiDot<NB, MODE>& e) { return e.acc; }
-template <class E>
-__device__ __forceinline__ double epi_acc(const E&) { return 0.0; }
 
 template <int NB>
 __host__ __device__ constexpr size_t stage_bytes(int cap, int rp_cap) {
@@ -208,7 +172,7 @@ __global__ void __launch_bounds__(CT + kProducerThreads)
     }
     if (REDUCE) {
       // deterministic sum of the consumers' dot contributions (fixed order)
-      double a = warp_sum(epi_acc(epi));
+      double a = warp_sum(epi_acc_of(epi));
       if (lane32 == 0) red[warp - 1] = a;
       consumer_sync<CT>();
       if (ct == 0) {
@@ -340,59 +304,6 @@ int staged_spmv_dot(const Csr& A, const double* x, const double* dx, double* y, 
   }
   return rc == SFEM_OK ? 1 : rc;
 }
-
-// Chebyshev coefficients are read on the device by a tiny prologue in the epilogue constructor path:
-// the staged engine takes them by value, so they are fetched through these device pointers in pre().
-template <int NB>
-struct EpiChebPtr {
-  const double* __restrict__ dinv;
-  const double* __restrict__ d_old;
-  double* __restrict__ d_new;
-  double* __restrict__ r;
-  double* __restrict__ xx;
-  const double* __restrict__ c12;
-  int last;
-  struct Pre { double r, d, di, x, c1, c2; };
-  __device__ __forceinline__ Pre pre(int row, int lane, bool active) const {
-    Pre p; p.r = p.d = p.di = p.x = 0.0;
-    p.c1 = c12[0]; p.c2 = c12[1];
-    if (active) {
-      const size_t i = (size_t)row * NB + lane;
-      p.r = r[i]; p.d = d_old[i]; p.di = dinv[row]; p.x = xx[i];
-    }
-    return p;
-  }
-  __device__ __forceinline__ void fin(int row, int lane, double t, const Pre& p) const {
-    const size_t i = (size_t)row * NB + lane;
-    const double rn = p.r - t;
-    const double dn = p.c1 * p.d + p.c2 * p.di * rn;
-    r[i] = rn;
-    d_new[i] = dn;
-    xx[i] = p.x + (last ? (p.d + dn) : p.d);
-  }
-};
-
-template <int NB>
-struct EpiResidD0Ptr {
-  const double* __restrict__ dinv;
-  const double* __restrict__ b;
-  double* __restrict__ r;
-  double* __restrict__ d;
-  const double* __restrict__ c0p;
-  struct Pre { double b, di, c0; };
-  __device__ __forceinline__ Pre pre(int row, int lane, bool active) const {
-    Pre p; p.b = p.di = 0.0;
-    p.c0 = c0p[0];
-    if (active) { p.b = b[(size_t)row * NB + lane]; p.di = dinv[row]; }
-    return p;
-  }
-  __device__ __forceinline__ void fin(int row, int lane, double sv, const Pre& p) const {
-    const size_t i = (size_t)row * NB + lane;
-    const double rr = p.b - sv;
-    r[i] = rr;
-    d[i] = p.c0 * p.di * rr;
-  }
-};
 
 int staged_cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
                      const double* c12, int last, int nb, cudaStream_t st) {

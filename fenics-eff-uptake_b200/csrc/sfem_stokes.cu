@@ -351,6 +351,7 @@ int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, 
     return SFEM_ERR_ARG;
   }
   cudaStream_t user = (cudaStream_t)stream;
+  SFEM_TRY(sell_ensure_all(user));          // dirty sliced-ELL mirrors are re-packed before any graph replay
   SFEM_TRY(h->ws.fork(user));
   cudaStream_t st = h->ws.s;
   const int n = h->n;

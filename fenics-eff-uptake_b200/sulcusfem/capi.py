@@ -39,6 +39,13 @@ SIGNATURES = {
     'sfem_staged_unregister': (None, [_p]),
     'sfem_staged_set_min_tiles': (_i, [_i]),
     'sfem_spmv_csr_f64_staged': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    'sfem_sell_parts': (_i, []),
+    'sfem_sell_register': (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, C.c_longlong, _p, _i]),
+    'sfem_sell_unregister': (None, [_p]),
+    'sfem_sell_mark_dirty': (_i, [_p]),
+    'sfem_sell_sync': (_i, [_p]),
+    'sfem_sell_set_min_rows': (_i, [_i]),
+    'sfem_spmv_csr_f64_sell': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     'sfem_elem_p2_advdiff': (_i, [_i, _p, _p, _d, _p, _p, _p, _p]),
     'sfem_elem_p1_advdiff': (_i, [_i, _p, _p, _d, _p, _p, _i, _p, _p]),
     'sfem_elem_th_stokes': (_i, [_i, _p, _p, _p]),

@@ -75,8 +75,11 @@ class DeviceCsr:
     PAD = 16
     STAGED_CAP = 768             # entries per tile (one shared-memory stage)
     STAGED_ROWS = 64             # rows per tile (64: 128 consumer threads per CTA, 128: 256)
+    SELL_SIGMA = 256             # sorting window of the sliced-ELL mirror (rows)
+    SELL_MIN_ROWS = 2048         # smaller matrices never get a mirror (launch-latency bound anyway)
+    SELL_MAX_FILL = 1.5          # mirrors that would store > 1.5x the non-zeros are not built (irregular rows)
 
-    def __init__(self, ctx: Context, nrows, ncols, rowptr, cols, vals=None, staged=True):
+    def __init__(self, ctx: Context, nrows, ncols, rowptr, cols, vals=None, staged=True, sell=True):
         torch = _torch()
         self.ctx = ctx
         self.nrows, self.ncols = int(nrows), int(ncols)
@@ -103,22 +106,47 @@ class DeviceCsr:
                 self.tile_row = ctx.up(tr[:nt + 1], np.int32)
                 capi.check(ctx.lib.sfem_staged_register(P(self.rowptr), self.nrows, P(self.tile_row), self.ntiles,
                                                         self.STAGED_CAP, self.STAGED_ROWS), 'sfem_staged_register')
+        self.sell = None
+        if sell and self.nrows >= self.SELL_MIN_ROWS and self.nnz > 0:
+            from . import sell as sl
+            plan = sl.build_plan(rp[:self.nrows + 1], cc[:self.nnz], self.SELL_SIGMA)
+            nparts = int(ctx.lib.sfem_sell_parts())
+            if plan.padded <= self.SELL_MAX_FILL * self.nnz:
+                self.sell = dict(
+                    fill=plan.padded / self.nnz, nslices=plan.nslices, padded=plan.padded,
+                    slice_ptr=ctx.up(plan.slice_ptr, np.int32), perm=ctx.up(plan.perm, np.int32),
+                    scols=ctx.up(plan.scols, np.int32), src=ctx.up(plan.src, np.int32),
+                    parts=ctx.up(sl.partition(plan, nparts), np.int32), nparts=nparts,
+                    svals=torch.zeros(max(plan.padded, 1), dtype=torch.float64, device=ctx.device))
+                k = self.sell
+                capi.check(ctx.lib.sfem_sell_register(P(self.rowptr), P(self.vals_buf), self.nrows, plan.nslices,
+                                                      P(k['slice_ptr']), P(k['perm']), P(k['scols']), P(k['src']),
+                                                      P(k['svals']), plan.padded, P(k['parts']), nparts), 'sfem_sell_register')
+
+    def mark_dirty(self):
+        """Tell the library that the CSR values were written outside of it (torch ops on ``vals``)."""
+        if self.sell is not None:
+            self.ctx.lib.sfem_sell_mark_dirty(P(self.rowptr))
 
     def __del__(self):
         try:
             if getattr(self, 'tile_row', None) is not None:
                 self.ctx.lib.sfem_staged_unregister(P(self.rowptr))
                 self.tile_row = None
+            if getattr(self, 'sell', None) is not None:
+                self.ctx.lib.sfem_sell_unregister(P(self.rowptr))
+                self.sell = None
         except Exception:
             pass
 
-    def spmv(self, x, y=None, b=None, mode=0, staged=False, nb=1):
-        """y = A x (0), b - A x (1), y += A x (2).  ``staged=True`` insists on the TMA-staged engine (error
-        if the matrix is too small / has no plan); otherwise the library picks the engine."""
+    def spmv(self, x, y=None, b=None, mode=0, staged=False, nb=1, sell=False):
+        """y = A x (0), b - A x (1), y += A x (2).  ``staged=True`` / ``sell=True`` insist on the TMA-staged /
+        sliced-ELL engine (error if the matrix is too small / has no plan); otherwise the library picks."""
         ctx = self.ctx
         if y is None:
             y = ctx.empty(self.nrows * nb)
-        fn = ctx.lib.sfem_spmv_csr_f64_staged if staged else ctx.lib.sfem_spmv_csr_f64_nb
+        fn = ctx.lib.sfem_spmv_csr_f64_sell if sell else (
+            ctx.lib.sfem_spmv_csr_f64_staged if staged else ctx.lib.sfem_spmv_csr_f64_nb)
         capi.check(fn(self.nrows, self.ncols, self.nnz, P(self.rowptr), P(self.cols), P(self.vals_buf),
                       P(x), P(b), P(y), mode, nb, ctx.stream), 'sfem_spmv_csr_f64')
         return y
@@ -402,7 +430,7 @@ class StokesProblem:
         cd = dm.th_cell_dofs(mesh)
         self.pattern = dm.build_pattern(self.n, self.n, [(cd, cd)])
         pat = self.pattern
-        self.A = DeviceCsr(ctx, self.n, self.n, pat.rowptr, pat.cols)
+        self.A = DeviceCsr(ctx, self.n, self.n, pat.rowptr, pat.cols, sell=False)   # parity / export only: the solver iterates on the block views
         self.contrib_ptr = ctx.up(pat.contrib_ptr, np.int32)
         self.contrib_code = ctx.up(pat.contrib_code, np.int32)
         self.E = ctx.zeros(pat.buffer_len)

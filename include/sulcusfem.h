@@ -71,6 +71,39 @@ int sfem_staged_set_min_tiles(int min_tiles);
 int sfem_spmv_csr_f64_staged(int nrows, int ncols, int nnz, const int* rowptr, const int* cols, const double* vals,
                              const double* x, const double* b, double* y, int mode, int nb, void* stream);
 
+/* Sliced-ELL (SELL-32-sigma) mirror.  Finite-element rows are short and nearly uniform, so the solver keeps a
+ * second copy of every operator it iterates on in a sliced ELLPACK layout: rows sorted by length inside windows
+ * of sigma rows, slices of 32 rows stored column-major and padded to their longest row --
+ *     entry j of the row held by lane l of slice s  lives at  slice_ptr[s] + 32*j + l.
+ * One lane owns one row, so the matrix stream is read in contiguous 256-byte (values) / 128-byte (indices)
+ * spans.  The mirror is attached to the CSR by the DEVICE address of its rowptr; it follows the CSR value array
+ * `csr_vals`: every entry of this library that writes CSR values marks the mirror dirty, and a dirty mirror is
+ * re-packed (svals[i] = csr_vals[src[i]]) at the next solver entry / SpMV -- it is never read stale.
+ *   slice_ptr [nslices+1]  start of every slice in entries (multiples of 32)
+ *   perm      [nslices*32] CSR row of every lane (-1: no row)
+ *   scols, src [padded]    column index / CSR slot of every position (-1 on padding)
+ *   svals     [padded]     mirror values (written by the library)
+ *   parts     [nparts+1]   first slice of each of nparts = sfem_sell_parts() contiguous parts holding equal numbers
+ *                          of entries; a warp of the SpMV kernel walks a run of consecutive parts, i.e. one
+ *                          contiguous span of the mirror, in fixed-size chunks that ignore slice boundaries
+ * All arrays are DEVICE arrays owned by the caller and kept alive until unregister (sulcusfem/device.py builds
+ * them once per pattern on the host).
+ *   sfem_sell_mark_dirty   for callers that write the CSR values themselves
+ *   sfem_sell_sync         re-pack all dirty mirrors now
+ *   sfem_sell_set_min_rows matrices with fewer rows keep the lane-group engine (<= 0: default); returns old value
+ *   sfem_spmv_csr_f64_sell like sfem_spmv_csr_f64_nb but fails if the matrix has no usable mirror
+ * replaces: PETSc MatMult (as above); the layout is new -- nothing like it exists in the reference. */
+int sfem_sell_parts(void);
+int sfem_sell_register(const int* rowptr, const double* csr_vals, int nrows, int nslices, const int* slice_ptr,
+                       const int* perm, const int* scols, const int* src, double* svals, long long padded,
+                       const int* parts, int nparts);
+void sfem_sell_unregister(const int* rowptr);
+int sfem_sell_mark_dirty(const int* rowptr);
+int sfem_sell_sync(void* stream);
+int sfem_sell_set_min_rows(int min_rows);
+int sfem_spmv_csr_f64_sell(int nrows, int ncols, int nnz, const int* rowptr, const int* cols, const double* vals,
+                           const double* x, const double* b, double* y, int mode, int nb, void* stream);
+
 /* ------------------------------------------------------------------ assembly ---------------- */
 /* Element matrices of  D grad(c).grad(phi) + (u.grad c) phi  on P2 triangles.
  *   geo      [6][nc] SoA vertex coordinates x0,y0,x1,y1,x2,y2 of every cell

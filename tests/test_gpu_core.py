@@ -23,13 +23,16 @@ def small():
     return mesh, mk, om
 
 
-@pytest.fixture(params=['vector', 'staged'])
+@pytest.fixture(params=['vector', 'staged', 'sell'])
 def engine(request, ctx):
-    """Run a test once with the vector SpMV engine only and once with the TMA-staged engine forced on
-    every matrix that has a tile plan (by default only large matrices use it)."""
+    """Run a test once with the vector SpMV engine only, once with the TMA-staged engine forced on every matrix
+    that has a tile plan and once with the sliced-ELL engine forced on every matrix that has a mirror (by
+    default only large matrices use the latter two)."""
     old = ctx.lib.sfem_staged_set_min_tiles(1 if request.param == 'staged' else 1 << 30)
+    old_sell = ctx.lib.sfem_sell_set_min_rows(1 if request.param == 'sell' else 1 << 30)
     yield request.param
     ctx.lib.sfem_staged_set_min_tiles(old)
+    ctx.lib.sfem_sell_set_min_rows(old_sell)
 
 
 def _rel(a, b):
@@ -41,6 +44,7 @@ def test_spmv_variants(ctx):
     import scipy.sparse as sp
     from sulcusfem.device import DeviceCsr
     rng = np.random.default_rng(0)
+    ctx.lib.sfem_sell_set_min_rows(1 << 30)          # this test: lane-group and staged engines only
     for n, dens in ((1, 1.0), (37, 0.3), (1000, 0.02), (20011, 0.0006)):
         A = sp.random(n, n, dens, random_state=1, format='csr') + sp.eye(n, format='csr')
         A.sort_indices()
@@ -70,6 +74,71 @@ def test_spmv_variants(ctx):
     assert dA.tile_row is None
     x = rng.random(n)
     assert _rel(dA.spmv(torch.from_numpy(x).cuda()).cpu().numpy(), A @ x) < 1e-14
+    ctx.lib.sfem_sell_set_min_rows(0)
+
+
+def test_spmv_sell(ctx):
+    """Sliced-ELL mirror: all modes, 1 and 2 right-hand sides, ragged / empty / long rows, rectangular operators,
+    every sorting window; and the mirror follows the CSR values (dirty -> re-packed, never stale)."""
+    import torch
+    import scipy.sparse as sp
+    from sulcusfem.device import DeviceCsr
+    rng = np.random.default_rng(7)
+    old = ctx.lib.sfem_sell_set_min_rows(1)
+    sig0, min0, fill0 = DeviceCsr.SELL_SIGMA, DeviceCsr.SELL_MIN_ROWS, DeviceCsr.SELL_MAX_FILL
+    try:
+        DeviceCsr.SELL_MIN_ROWS = 1
+        DeviceCsr.SELL_MAX_FILL = 64.0          # tiny random matrices pad a lot
+        for (m, n, dens, sigma) in ((1, 1, 1.0, 256), (37, 37, 0.3, 32), (53, 31, 0.2, 64), (1000, 1000, 0.02, 256),
+                                    (3000, 4100, 0.004, 128), (20011, 20011, 0.0006, 1024)):
+            DeviceCsr.SELL_SIGMA = sigma
+            A = sp.random(m, n, dens, random_state=3, format='csr')
+            if m == n:
+                A = A + sp.eye(n, format='csr')
+            if m > 100:
+                A = A.tolil(); A[5, :] = 0; A[7, :25] = 1.5; A = A.tocsr(); A.eliminate_zeros()
+            A.sort_indices()
+            dA = DeviceCsr(ctx, m, n, A.indptr, A.indices, A.data)
+            assert dA.sell is not None, (m, n)
+            for nb in (1, 2):
+                X = rng.random((n, nb)); B = rng.random((m, nb))
+                dX = torch.from_numpy(X.ravel().copy()).cuda(); dB = torch.from_numpy(B.ravel().copy()).cuda()
+                ref = A @ X
+                y = dA.spmv(dX, nb=nb, sell=True).cpu().numpy().reshape(m, nb)
+                assert _rel(y, ref) < 1e-14, (m, n, nb)
+                r = dA.spmv(dX, b=dB, mode=1, nb=nb, sell=True).cpu().numpy().reshape(m, nb)
+                assert _rel(r, B - ref) < 1e-13, (m, n, nb)
+                y2 = dB.clone()
+                dA.spmv(dX, y=y2, mode=2, nb=nb, sell=True)
+                assert _rel(y2.cpu().numpy().reshape(m, nb), B + ref) < 1e-14
+                # the default entry point picks the same engine and gives the same bits
+                y3 = dA.spmv(dX, nb=nb).cpu().numpy().reshape(m, nb)
+                assert np.array_equal(y3, y)
+            # values rewritten behind the library's back: mark_dirty -> the next product uses the new values
+            dA.vals.mul_(2.0)
+            dA.mark_dirty()
+            x = rng.random(n)
+            assert _rel(dA.spmv(torch.from_numpy(x).cuda(), sell=True).cpu().numpy(), 2.0 * (A @ x)) < 1e-14
+            # values rewritten by a library entry (sfem_csr_extract): the mirror is refreshed without being told
+            new = torch.from_numpy(rng.random(A.nnz)).cuda()
+            slot = torch.arange(A.nnz, dtype=torch.int32, device='cuda')
+            from sulcusfem import capi
+            capi.check(ctx.lib.sfem_csr_extract(A.nnz, capi.ptr(slot), capi.ptr(new), capi.ptr(dA.vals), ctx.stream))
+            A2 = sp.csr_matrix((new.cpu().numpy(), A.indices, A.indptr), shape=A.shape)
+            assert _rel(dA.spmv(torch.from_numpy(x).cuda()).cpu().numpy(), A2 @ x) < 1e-14
+        # a matrix with wildly irregular rows gets no mirror (padding would exceed SELL_MAX_FILL)
+        DeviceCsr.SELL_SIGMA = 32
+        DeviceCsr.SELL_MAX_FILL = fill0
+        A = sp.random(5000, 5000, 0.001, random_state=2, format='lil')
+        A[11, :3000] = 0.25
+        A = A.tocsr(); A.sort_indices()
+        dA = DeviceCsr(ctx, 5000, 5000, A.indptr, A.indices, A.data)
+        assert dA.sell is None
+        x = rng.random(5000)
+        assert _rel(dA.spmv(torch.from_numpy(x).cuda()).cpu().numpy(), A @ x) < 1e-14
+    finally:
+        DeviceCsr.SELL_SIGMA, DeviceCsr.SELL_MIN_ROWS, DeviceCsr.SELL_MAX_FILL = sig0, min0, fill0
+        ctx.lib.sfem_sell_set_min_rows(old)
 
 
 def test_spmv_two_rhs_and_rectangular(ctx):

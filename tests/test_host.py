@@ -186,3 +186,62 @@ def test_mesh_generator_interface(tmp_path):
     assert np.array_equal(back.cells, res['mesh'].cells) and np.array_equal(back.coords, res['mesh'].coords)
     res3 = MeshGenerator(10.0, 1.0, 1.0, 0.5, 0.2, 1, 'sulcus', mesh_file=path).generate_mesh()
     assert np.array_equal(res3['bc_markers'].array(), res['bc_markers'].array())
+
+
+@pytest.mark.parametrize('sigma', [32, 64, 256, 4096])
+def test_sell_plan_layout(sigma):
+    """Sliced-ELL plan (sulcusfem/sell.py): every CSR entry is stored exactly once at slice_ptr[s] + 32 j + lane,
+    entries of a row keep their column order, slices are padded to their longest row, empty / ragged rows and
+    row counts that are not multiples of 32 are handled, and a P2 pattern pads by a few per cent at most."""
+    import scipy.sparse as sp
+    from sulcusfem import sell as sl
+    rng = np.random.default_rng(11)
+    cases = [sp.csr_matrix((0, 0)), sp.csr_matrix((5, 7)), sp.eye(1, format='csr')]
+    for (m, n, dens) in ((33, 40, 0.2), (257, 257, 0.05), (1000, 900, 0.01)):
+        A = sp.random(m, n, dens, random_state=4, format='lil')
+        A[m // 2, :] = 0
+        A[m // 3, : min(n, 30)] = 2.0
+        A = A.tocsr(); A.sort_indices()
+        cases.append(A)
+    for A in cases:
+        m, n = A.shape
+        p = sl.build_plan(A.indptr, A.indices, sigma)
+        assert p.nslices == (m + 31) // 32 and len(p.perm) == p.nslices * 32
+        assert p.padded == int(p.slice_ptr[-1]) and np.all(np.diff(p.slice_ptr) % 32 == 0)
+        rows = p.perm[p.perm >= 0]
+        assert np.array_equal(np.sort(rows), np.arange(m))               # a permutation of the rows
+        assert np.array_equal(np.sort(p.src[p.src >= 0]), np.arange(A.nnz))   # every CSR slot exactly once
+        assert np.array_equal(p.scols >= 0, p.src >= 0)
+        lens = np.diff(A.indptr)
+        for s in range(p.nslices):
+            base, width = int(p.slice_ptr[s]), (int(p.slice_ptr[s + 1]) - int(p.slice_ptr[s])) // 32
+            lane_rows = p.perm[s * 32:(s + 1) * 32]
+            ll = np.where(lane_rows >= 0, lens[np.maximum(lane_rows, 0)], 0) if m else np.zeros(32, int)
+            assert width == ll.max()
+            blk = p.src[base:base + width * 32].reshape(width, 32)
+            for l in range(32):
+                r = lane_rows[l]
+                want = np.arange(A.indptr[r], A.indptr[r + 1]) if r >= 0 else np.zeros(0, int)
+                assert np.array_equal(blk[:len(want), l], want) and np.all(blk[len(want):, l] == -1)
+        for nparts in (1, 7, 96, 14208):                                   # contiguous parts balanced by column-steps
+            parts = sl.partition(p, nparts)
+            assert len(parts) == nparts + 1 and parts[0] == 0 and parts[-1] == p.nslices
+            assert np.all(np.diff(parts) >= 0)
+            steps = p.slice_ptr.astype(np.int64)[parts] // 32
+            widest = int(np.diff(p.slice_ptr).max() // 32) if p.nslices else 0
+            assert np.all(np.abs(np.diff(steps) - p.padded / 32 / nparts) <= widest + 1)
+        if sigma > 32:                                                     # sorted by decreasing length inside windows
+            sig = ((sigma + 31) // 32) * 32
+            ordl = np.where(p.perm >= 0, lens[np.maximum(p.perm, 0)], 0) if m else np.zeros(0, int)
+            for w0 in range(0, len(ordl), sig):
+                assert np.all(np.diff(ordl[w0:w0 + sig]) <= 0)
+    from sulcusfem import dofmap as dm, hostmesh as hm
+    mesh = hm.rectangle_mesh(10.0, 1.0, 200, 20)
+    cd = dm.p2_cell_dofs(mesh)
+    pat = dm.build_pattern(dm.p2_num_dofs(mesh), dm.p2_num_dofs(mesh), [(cd, cd)])
+    p = sl.build_plan(pat.rowptr, pat.cols, sigma)
+    assert p.fill < (1.10 if sigma < 256 else 1.03), p.fill
+    r, c, v = sl.to_dense_rows(p, np.arange(pat.nnz, dtype=float))
+    B = sp.coo_matrix((v, (r, c)), shape=(pat.nrows, pat.ncols) if hasattr(pat, 'nrows') else None).tocsr()
+    A = sp.csr_matrix((np.arange(pat.nnz, dtype=float), pat.cols, pat.rowptr))
+    assert abs(A - B).max() == 0

@@ -33,7 +33,18 @@ def launches(src, dst):
     iu = hdr.index('Metric Unit')
     agg = defaultdict(lambda: [0, 0.0])
     tot = 0.0
-    for r in rows[1:]:
+    body = rows[1:]
+    # bench.py brackets its timed region with two erfinv marker kernels: keep what lies between them, and only
+    # this library's kernels (the L2 flush between steps is torch)
+    marks = [i for i, r in enumerate(body) if 'erfinv' in r[ik]]
+    note = ''
+    if len(marks) >= 2:
+        body = [r for r in body[marks[0] + 1:marks[1]] if 'sfem' in r[ik]]
+        note = ' (timed region between the two marker kernels, libsulcusfem kernels only)'
+    elif len(marks) == 1:
+        body = [r for r in body[marks[0] + 1:] if 'sfem' in r[ik]]
+        note = ' (timed region from the first marker kernel to the end of the capture -- capture cut short, libsulcusfem kernels only)'
+    for r in body:
         try:
             v = float(r[iv].replace(',', ''))
         except ValueError:
@@ -47,7 +58,7 @@ def launches(src, dst):
         agg[k][1] += v
         tot += v
     with open(dst, 'w') as f:
-        f.write(f"# ncu launch list summary ({src}): {sum(a[0] for a in agg.values())} launches, {tot / 1e3:.2f} ms kernel time\n\n")
+        f.write(f"# ncu launch list summary ({src}){note}: {sum(a[0] for a in agg.values())} launches, {tot / 1e3:.2f} ms kernel time\n\n")
         f.write("ncu times are cold-cache and serialised (one kernel at a time): compare SHARES, not absolutes.\n\n")
         f.write("| kernel | launches | total us | share | avg us |\n|---|---:|---:|---:|---:|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
