@@ -140,15 +140,172 @@ def compute_mass_metrics(c, measures, domain_type):
     return {'total_mass': tm, 'total_area': ta, 'average_concentration': ta and tm / ta or 0.0}
 
 
-def compute_velocity_metrics(u, mesh_results, params):
-    """Line / sample statistics of |u| (reference analysis.py:721-830).  The reference's sampling is
-    unseeded random point evaluation for plots (out of scope); the no-advection branch
-    returns {} exactly like the reference (:733-734)."""
-    if u is None or not np.any(u.values):
+# ====================================================================== line profiles (device point evaluation)
+def _line_points(mesh, fixed, axis, rng, n_points):
+    k = 1 if axis == 'v' else 0
+    if rng is None:
+        X = mesh.coordinates()
+        lo, hi = X[:, k].min(), X[:, k].max()
+    else:
+        lo, hi = rng
+    s = np.linspace(lo, hi, n_points)
+    f = np.full(n_points, float(fixed))
+    return s, (np.stack([f, s], axis=1) if axis == 'v' else np.stack([s, f], axis=1))
+
+
+def _eval_lines(f, mesh, lines, n_points):
+    """All sample points of all lines in ONE device launch.  lines: [(fixed, axis, range)] ->
+    [(coords_inside, values_inside)] (values [k] or [k, 2])."""
+    S, P = zip(*[_line_points(mesh, fx, ax, rg, n_points) for fx, ax, rg in lines]) if lines else ((), ())
+    if not lines:
+        return []
+    vals, ok = f.eval_points(np.concatenate(P, axis=0))
+    out = []
+    for i, s in enumerate(S):
+        sl = slice(i * n_points, (i + 1) * n_points)
+        out.append((s[ok[sl]], vals[sl][ok[sl]]))
+    return out
+
+
+def extract_concentration_vertical_line_profile(c, mesh, x_location, y_range=None, n_points=100):
+    """Reference analysis.py:341-378 (same keys); the per-point collision test + c(Point) loop is one launch."""
+    (y, v), = _eval_lines(c, mesh, [(x_location, 'v', y_range)], n_points)
+    return {'y_coords': y, 'c': v}
+
+
+def extract_concentration_horizontal_line_profile(c, mesh, y_location, x_range=None, n_points=100):
+    """Reference analysis.py:380-419."""
+    (x, v), = _eval_lines(c, mesh, [(y_location, 'h', x_range)], n_points)
+    return {'x_coords': x, 'c': v}
+
+
+def extract_velocity_vertical_line_profile(u, mesh, x_location, y_range=None, n_points=100):
+    """Reference analysis.py:544-586."""
+    (y, v), = _eval_lines(u, mesh, [(x_location, 'v', y_range)], n_points)
+    return {'y_coords': y, 'u_x': v[:, 0], 'u_y': v[:, 1], 'u_mag': np.sqrt(v[:, 0] ** 2 + v[:, 1] ** 2)}
+
+
+def extract_velocity_horizontal_line_profile(u, mesh, y_location, x_range=None, n_points=100):
+    """Reference analysis.py:588-632."""
+    (x, v), = _eval_lines(u, mesh, [(y_location, 'h', x_range)], n_points)
+    return {'x_coords': x, 'u_x': v[:, 0], 'u_y': v[:, 1], 'u_mag': np.sqrt(v[:, 0] ** 2 + v[:, 1] ** 2)}
+
+
+def compute_conc_profiles(results, *, n_points=400):
+    """Horizontal and vertical concentration line profiles, statistics and full samples
+    (reference analysis.py:421-542: same lines, same result keys under results['mass_metrics']).  All eight lines
+    are located and evaluated in one launch."""
+    c = results.get('c')
+    mesh = (results.get('mesh_results') or {}).get('mesh')
+    params = results.get('params', None)
+    if c is None or mesh is None or params is None:
+        return results
+    L = float(getattr(params, 'L_dim', getattr(params, 'L', 1.0)))
+    H = float(getattr(params, 'H_dim', getattr(params, 'H', 1.0)))
+    domain_type = results.get('domain_type', None)
+    if domain_type is None:
+        h_dim = getattr(params, 'sulci_h_dim', 0.0)
+        domain_type = 'sulcus' if (h_dim and h_dim > 0) else 'rectangular'
+        results['domain_type'] = domain_type
+    mass_metrics = results.setdefault('mass_metrics', {})
+
+    def _stats(vals):
+        vals = np.asarray(vals)
+        if vals.size == 0:
+            return {'min_c': None, 'max_c': None, 'avg_c': None, 'n_samples': 0}
+        return {'min_c': float(np.min(vals)), 'max_c': float(np.max(vals)), 'avg_c': float(np.mean(vals)),
+                'n_samples': int(vals.size)}
+    vert_lines = [(0.25 * L, "x_quarter"), (0.50 * L, "x_mid"), (0.75 * L, "x_three_quarters")]
+    horiz_lines = [(1e-6 * H, "mouth_level"), (0.25 * H, "lower_channel"), (0.50 * H, "mid_channel"),
+                   (0.75 * H, "upper_channel")]
+    if domain_type == 'rectangular':
+        x_range, y_range = (0.0, float(L)), (0.0, float(H))
+    else:
+        coords = mesh.coordinates()
+        y_min = float(coords[:, 1].min())
+        horiz_lines = [(0.5 * (y_min + 0.0), "sulcus_mid")] + horiz_lines
+        x_range, y_range = (float(coords[:, 0].min()), float(coords[:, 0].max())), None
+    try:
+        c.set_allow_extrapolation(True)
+    except Exception:
+        pass
+    lines = [(float(y), 'h', x_range) for y, _ in horiz_lines] + [(float(x), 'v', y_range) for x, _ in vert_lines]
+    profs = _eval_lines(c, mesh, lines, n_points)
+    profiles_stats = {'horizontal': {}, 'vertical': {}}
+    profiles_full = {'horizontal': {}, 'vertical': {}}
+    for (y_loc, name), (xs, cs) in zip(horiz_lines, profs[:len(horiz_lines)]):
+        s = _stats(cs)
+        if s['n_samples'] > 0:
+            profiles_stats['horizontal'][name] = {'y': float(y_loc), **s}
+            profiles_full['horizontal'][name] = {'y': float(y_loc), 'x': np.asarray(xs).tolist(), 'c': np.asarray(cs).tolist()}
+    for (x_loc, name), (ys, cs) in zip(vert_lines, profs[len(horiz_lines):]):
+        s = _stats(cs)
+        if s['n_samples'] > 0:
+            profiles_stats['vertical'][name] = {'x': float(x_loc), **s}
+            profiles_full['vertical'][name] = {'x': float(x_loc), 'y': np.asarray(ys).tolist(), 'c': np.asarray(cs).tolist()}
+    mass_metrics['profiles'] = profiles_stats
+    mass_metrics['profiles_full'] = profiles_full
+    mass_metrics['profiles_meta'] = {
+        'n_points': int(n_points), 'domain_type': domain_type,
+        'x_range': tuple(map(float, x_range)) if x_range is not None else None,
+        'y_range': tuple(map(float, y_range)) if y_range is not None else None}
+    return results
+
+
+def compute_velocity_metrics(u, mesh_results, params, rng=None):
+    """Key velocity metrics (reference analysis.py:721-830, same keys): statistics of 4 horizontal and 3 vertical
+    line profiles (100 samples each) and of u at <= 1000 randomly chosen mesh vertices.  All 700 line samples go
+    through one device launch; the vertex sample needs no location (vertex dofs are nodal values).  Like the
+    reference the vertex sample is unseeded unless ``rng`` (a numpy Generator) is given; modes without flow
+    return {} (:733-734)."""
+    if u is None:
         return {}
-    n2 = len(u.values) // 2
-    speed = np.hypot(u.values[:n2], u.values[n2:])
-    return {'max_velocity_global': float(speed.max()), 'avg_velocity_global': float(speed.mean())}
+    mesh = mesh_results['mesh']
+    mode = getattr(params, 'mode', 'unknown')
+    if mode not in ['adv-diff', 'no-uptake']:
+        return {}
+    try:
+        L, H, sulcus_w = params.L, params.H, params.sulci_w
+        xc = L / 2
+        horizontal_lines = [(1e-6 * H, "mouth_level"), (0.25 * H, "lower_channel"), (0.50 * H, "mid_channel"),
+                            (0.75 * H, "upper_channel")]
+        vertical_lines = [(xc - sulcus_w / 2, "sulcus_leading"), (xc, "sulcus_center"), (xc + sulcus_w / 2, "sulcus_trailing")]
+        hl = [(y, n) for y, n in horizontal_lines if 0 <= y <= H]
+        vl = [(x, n) for x, n in vertical_lines if 0 <= x <= L]
+        profs = _eval_lines(u, mesh, [(float(y), 'h', (0, L)) for y, _ in hl] + [(float(x), 'v', (0, H)) for x, _ in vl], 100)
+        vm = {}
+        for (_, name), (_, v) in zip(hl, profs[:len(hl)]):
+            ok = len(v) > 0
+            mag = np.sqrt(v[:, 0] ** 2 + v[:, 1] ** 2) if ok else None
+            vm[f'max_ux_{name}'] = np.max(np.abs(v[:, 0])) if ok else 0
+            vm[f'max_umag_{name}'] = np.max(mag) if ok else 0
+            vm[f'avg_ux_{name}'] = np.mean(np.abs(v[:, 0])) if ok else 0
+            vm[f'avg_umag_{name}'] = np.mean(mag) if ok else 0
+        for (_, name), (_, v) in zip(vl, profs[len(hl):]):
+            ok = len(v) > 0
+            mag = np.sqrt(v[:, 0] ** 2 + v[:, 1] ** 2) if ok else None
+            vm[f'max_umag_{name}'] = np.max(mag) if ok else 0
+            vm[f'max_uy_{name}'] = np.max(np.abs(v[:, 1])) if ok else 0
+            vm[f'avg_umag_{name}'] = np.mean(mag) if ok else 0
+            vm[f'avg_uy_{name}'] = np.mean(np.abs(v[:, 1])) if ok else 0
+        coords = mesh.coordinates()
+        n_sample = min(1000, len(coords))
+        idx = (rng.choice(len(coords), n_sample, replace=False) if rng is not None
+               else np.random.choice(len(coords), n_sample, replace=False))
+        n2 = len(u.values) // 2
+        gx, gy = u.values[idx], u.values[n2 + idx]             # P2 vertex dofs = values at the vertices
+        gm = np.sqrt(gx ** 2 + gy ** 2)
+        if len(gm):
+            vm.update({'global_max_umag': np.max(gm), 'global_avg_umag': np.mean(gm),
+                       'global_max_ux': np.max(np.abs(gx)), 'global_avg_ux': np.mean(np.abs(gx)),
+                       'global_max_uy': np.max(np.abs(gy)), 'global_avg_uy': np.mean(np.abs(gy))})
+        else:
+            vm.update({k: 0 for k in ('global_max_umag', 'global_avg_umag', 'global_max_ux', 'global_avg_ux',
+                                      'global_max_uy', 'global_avg_uy')})
+        return vm
+    except Exception as e:
+        print(f"⚠️ Warning: Could not extract velocity metrics: {e}")
+        return {}
 
 
 # ====================================================================== mu_eff

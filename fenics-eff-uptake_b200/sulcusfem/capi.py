@@ -95,6 +95,7 @@ SIGNATURES = {
     'sfem_dist_allreduce_scalars': (_i, [_p, _p, _i, _p]),
     'sfem_facet_functionals': (_i, [_i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _d, _d, _p, _p, _p]),
     'sfem_cell_functionals': (_i, [_i, _p, _p, _p, _i, _p, _p, _p]),
+    'sfem_eval_points': (_i, [_i, _i, _p, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i, _p, _i, C.POINTER(_p), _d, _p, _p, _p]),
 }
 
 _lib = None

@@ -274,7 +274,24 @@ class Function:
                 self._dev = (ctx.up(self.values, np.float64),)
         return self._dev
 
-    # ------------------------------------------------------------------ point evaluation (host)
+    # ------------------------------------------------------------------ point evaluation (device, batched)
+    def eval_points(self, pts, tol=None):
+        """Values at many points in one launch of ``sfem_eval_points`` (uniform-grid locator, sulcusfem/locator.py).
+
+        Returns ``(values, inside)``: values ``[npts]`` (scalar spaces) or ``[npts, 2]`` (P2 vector), ``inside``
+        the mask of points that lie in some cell -- what the reference tests with
+        ``mesh.bounding_box_tree().compute_first_entity_collision(Point)`` before calling ``f(Point)``
+        (``analysis.py:367-372``).  Points outside get value 0."""
+        from .locator import locator_for, TOL
+        kind = self._V.kind
+        if kind == 'TH':
+            raise ValueError("point evaluation of a mixed function is not supported")
+        loc = locator_for(self._V.mesh())
+        vals, cell = loc.eval(pts, self.device_components(), degree=1 if kind == 'P1' else 2,
+                              tol=TOL if tol is None else tol)
+        return (vals[0] if kind != 'P2v' else vals.T.copy()), cell >= 0
+
+    # ------------------------------------------------------------------ point evaluation (host, one point)
     def __call__(self, *x):
         from .hierarchy import locate_points
         p = x[0] if len(x) == 1 else x

@@ -276,6 +276,19 @@ int sfem_facet_functionals(int ngroups, const int* grp_ptr, const int* ent_cell,
 int sfem_cell_functionals(int nc, const double* geo, const int* celldofs, const int* cell_marker,
                           int nmarkers, const double* c, double* out, void* stream);
 
+/* ------------------------------------------------------------------ point evaluation -------- */
+/* Locate npts points and evaluate up to 4 nodal P1 (degree 1) or P2 (degree 2) fields there, one launch.
+ *   pts [npts][2];  bin grid: nbx x nby bins of size hx x hy from (x0, y0); bin_ptr [nbx*nby+1], bin_cells =
+ *   ascending cells whose bounding box overlaps the bin (sulcusfem/locator.py builds it once per mesh)
+ *   geo [6][nc], celldofs [ndof][nc] SoA as in the assembly kernels; h_fields: HOST array of nfields device pointers
+ *   tol: a point is inside a cell when min(barycentric) >= -tol; the lowest-numbered such candidate wins
+ *   out [nfields][npts] (0 where outside), cell_out [npts] (-1 = in no cell)
+ * replaces: mesh.bounding_box_tree().compute_first_entity_collision(Point) + c(Point) / u(Point) per sample,
+ *           analysis.py:367-372, 405-410, 574-583, 616-625, 805-810 */
+int sfem_eval_points(int degree, int npts, const double* pts, int nbx, int nby, double x0, double y0, double hx, double hy,
+                     const int* bin_ptr, const int* bin_cells, const double* geo, int nc, const int* celldofs,
+                     int nfields, const double* const* h_fields, double tol, double* out, int* cell_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

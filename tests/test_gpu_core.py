@@ -445,3 +445,67 @@ def test_mailbox_halo_exchange_and_vector_allreduce_emulated(ctx):
     finally:
         for d in dists:
             d.close()
+
+
+def test_point_evaluation_and_line_profiles_match_oracle(ctx, small):
+    """sfem_eval_points (uniform-grid locator + P1/P2 evaluation, one launch) against the oracle's brute-force
+    location: same inside/outside decisions, values to 1e-13; then the reference-shaped profile extractors,
+    compute_conc_profiles and compute_velocity_metrics (analysis.py:341-632, 721-830) against the oracle."""
+    from oracle import cpu_oracle as co
+    from sulcusfem import analysis, fem
+    from sulcusfem.parameters import Parameters
+    mesh, mk, om = small
+    X = om.p2_dof_coords()
+    rng = np.random.default_rng(3)
+    c_vals = np.sin(0.7 * X[:, 0]) * np.cos(1.3 * X[:, 1]) + 0.1 * X[:, 0]
+    ux_vals = 4 * X[:, 1] * (1 - X[:, 1]) + 0.05 * np.sin(X[:, 0])
+    uy_vals = 0.02 * np.cos(2 * X[:, 0]) * X[:, 1]
+    c = fem.Function(fem.FunctionSpace(mesh, 'CG', 2), c_vals)
+    u = fem.Function(fem.VectorFunctionSpace(mesh, 'CG', 2), np.concatenate([ux_vals, uy_vals]))
+    p1 = fem.Function(fem.FunctionSpace(mesh, 'CG', 1), c_vals[:mesh.num_vertices])
+    pts = np.concatenate([
+        np.stack([rng.uniform(-0.2, 10.2, 3000), rng.uniform(-1.1, 1.1, 3000)], axis=1),
+        mesh.coords[rng.integers(0, mesh.num_vertices, 200)],
+        mesh.edge_midpoints()[rng.integers(0, mesh.num_edges, 200)],
+        np.array([[0.0, 0.0], [10.0, 1.0], [0.0, 1.0], [10.0, 0.0], [5.0, -1.0], [4.75, 0.0], [5.25, 0.0]]),
+        np.zeros((0, 2))])
+    ref_c, ok = co.eval_points(om, c_vals, pts)
+    got_c, inside = c.eval_points(pts)
+    assert np.array_equal(inside, ok)
+    assert np.abs(got_c - ref_c).max() < 1e-13
+    got_u, inside_u = u.eval_points(pts)
+    assert np.array_equal(inside_u, ok)
+    assert np.abs(got_u[:, 0] - co.eval_points(om, ux_vals, pts)[0]).max() < 1e-13
+    assert np.abs(got_u[:, 1] - co.eval_points(om, uy_vals, pts)[0]).max() < 1e-13
+    got_p1, _ = p1.eval_points(pts)
+    assert np.abs(got_p1 - co.eval_points(om, c_vals[:mesh.num_vertices], pts, degree=1)[0]).max() < 1e-13
+    e, ins = c.eval_points(np.zeros((0, 2)))
+    assert e.shape == (0,) and ins.shape == (0,)
+    # reference-shaped extractors
+    prof = analysis.extract_concentration_vertical_line_profile(c, mesh, 5.0, n_points=101)
+    s, v = co.line_profile(om, c_vals, 5.0, 'v', None, 101)
+    assert np.array_equal(prof['y_coords'], s) and np.abs(prof['c'] - v).max() < 1e-13
+    prof = analysis.extract_velocity_horizontal_line_profile(u, mesh, 0.25, x_range=(0, 10.0), n_points=100)
+    s, a = co.line_profile(om, ux_vals, 0.25, 'h', (0, 10.0), 100)
+    assert np.array_equal(prof['x_coords'], s) and np.abs(prof['u_x'] - a).max() < 1e-13
+    params = Parameters(mode='adv-diff', mesh_size_dim=0.08, sulci_w_dim=0.5, sulci_h_dim=1.0)
+    params.validate(); params.nondim()
+    res = analysis.compute_conc_profiles({'c': c, 'mesh_results': {'mesh': mesh}, 'params': params}, n_points=400)
+    want = co.conc_profiles(om, c_vals, float(params.L_dim), float(params.H_dim), 'sulcus', 400)
+    got = res['mass_metrics']['profiles']
+    assert set(got['horizontal']) == set(want['horizontal']) and set(got['vertical']) == set(want['vertical'])
+    for grp in ('horizontal', 'vertical'):
+        for name, w in want[grp].items():
+            g = got[grp][name]
+            assert g['n_samples'] == w['n_samples']
+            for k in ('min_c', 'max_c', 'avg_c'):
+                assert abs(g[k] - w[k]) < 1e-12, (grp, name, k)
+    assert len(res['mass_metrics']['profiles_full']['vertical']['x_mid']['c']) == got['vertical']['x_mid']['n_samples']
+    vm = analysis.compute_velocity_metrics(u, {'mesh': mesh}, params, rng=np.random.default_rng(1))
+    wantv = co.velocity_line_metrics(om, ux_vals, uy_vals, params.L, params.H, params.sulci_w, 100)
+    for k, w in wantv.items():
+        assert abs(vm[k] - w) < 1e-12, k
+    idx = np.random.default_rng(1).choice(mesh.num_vertices, min(1000, mesh.num_vertices), replace=False)
+    assert abs(vm['global_max_umag'] - np.sqrt(ux_vals[idx] ** 2 + uy_vals[idx] ** 2).max()) < 1e-14
+    params.mode = 'no-adv'
+    assert analysis.compute_velocity_metrics(u, {'mesh': mesh}, params) == {}

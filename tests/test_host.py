@@ -245,3 +245,55 @@ def test_sell_plan_layout(sigma):
     B = sp.coo_matrix((v, (r, c)), shape=(pat.nrows, pat.ncols) if hasattr(pat, 'nrows') else None).tocsr()
     A = sp.csr_matrix((np.arange(pat.nnz, dtype=float), pat.cols, pat.rowptr))
     assert abs(A - B).max() == 0
+
+
+def test_locator_bins_contain_the_cell_of_every_point():
+    """Uniform-grid locator plan (sulcusfem/locator.py): the bin of a point lists, in ascending order, every cell
+    that contains it (checked against the oracle's brute-force location), including points on edges, vertices,
+    the domain boundary and the corners of the bin grid."""
+    from sulcusfem import locator as lc
+    mesh = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.1, 'sulcus')
+    om = co.Mesh(mesh.coords, mesh.cells)
+    g = lc.build_bins(mesh)
+    assert g.bin_ptr[0] == 0 and g.bin_ptr[-1] == len(g.bin_cells) and len(g.bin_ptr) == g.nbx * g.nby + 1
+    for b in range(g.nbx * g.nby):
+        seg = g.bin_cells[g.bin_ptr[b]:g.bin_ptr[b + 1]]
+        assert np.all(np.diff(seg) > 0)
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([
+        np.stack([rng.uniform(0, 10, 400), rng.uniform(-1, 1, 400)], axis=1),
+        mesh.coords[rng.integers(0, mesh.num_vertices, 100)],                  # vertices
+        mesh.edge_midpoints()[rng.integers(0, mesh.num_edges, 100)],           # edge midpoints
+        np.array([[0.0, 0.0], [10.0, 1.0], [0.0, 1.0], [10.0, 0.0], [5.0, -1.0]])])
+    cell, _ = co.locate_brute(om, pts)
+    bx = np.clip(np.floor((pts[:, 0] - g.x0) / g.hx).astype(int), 0, g.nbx - 1)
+    by = np.clip(np.floor((pts[:, 1] - g.y0) / g.hy).astype(int), 0, g.nby - 1)
+    b = by * g.nbx + bx
+    inside = cell >= 0
+    assert inside.sum() > 300 and (~inside).sum() > 50
+    for i in np.flatnonzero(inside):
+        seg = g.bin_cells[g.bin_ptr[b[i]]:g.bin_ptr[b[i] + 1]]
+        assert cell[i] in seg, (i, pts[i])
+    # a handful of candidates per bin, not the whole mesh
+    assert np.diff(g.bin_ptr).mean() < 16
+
+
+def test_oracle_point_evaluation_known_answers():
+    """P2 interpolation reproduces quadratics exactly; points outside the mesh are flagged invalid
+    (reference analysis.py:367-372 semantics)."""
+    mesh = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.1, 'sulcus')
+    om = co.Mesh(mesh.coords, mesh.cells)
+    X = om.p2_dof_coords()
+    f = lambda x, y: 1 + 2 * x - 3 * y + 0.5 * x * x - x * y + 0.25 * y * y   # noqa: E731
+    vals = f(X[:, 0], X[:, 1])
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.uniform(-0.5, 10.5, 600), rng.uniform(-1.2, 1.2, 600)], axis=1)
+    v, ok = co.eval_points(om, vals, pts)
+    in_channel = (pts[:, 0] > 0) & (pts[:, 0] < 10) & (pts[:, 1] > 0) & (pts[:, 1] < 1)
+    assert np.all(ok[in_channel]) and not np.any(ok[(pts[:, 0] < 0) | (pts[:, 0] > 10) | (pts[:, 1] > 1)])
+    assert np.abs(v[ok] - f(pts[ok, 0], pts[ok, 1])).max() < 1e-12
+    s, vv = co.line_profile(om, vals, 5.0, 'v', None, 101)
+    assert s.min() < -0.9 and s.max() == 1.0 and np.abs(vv - f(5.0, s)).max() < 1e-12
+    # the mouth-level line of compute_velocity_metrics stays inside the channel on its whole length
+    s, _ = co.line_profile(om, vals, 1e-6, 'h', (0, 10.0), 100)
+    assert len(s) == 100
