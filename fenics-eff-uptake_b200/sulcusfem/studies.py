@@ -1,0 +1,360 @@
+"""Data paths of the reference's study drivers -- the loops over independent cases, the row extraction and the CSV
+files with the reference's exact column names -- without the plotting / menu layers.
+
+    reference driver                                         here
+    no_advection_analysis_B.py:86-200  run_no_adv_mu_sweep   run_no_adv_mu_sweep      no_adv_mu_sweep_results.csv
+    adv_diff_analysis.py:177-300       run_advdiff_step_...  run_advdiff_step_validation  advdiff_validation_step_pe_x_mu.csv
+    no_advection_analysis_A.py:1257-1347  run_mu_sweep       run_mu_sweep             mu_parameter_sweep_results.csv
+    no_advection_analysis_A.py:1349-1452  run_aspect_ratio_analysis  run_aspect_ratio_analysis  aspect_ratio_analysis_results.csv
+
+The reference runs every case serially; the cases are independent, so each driver deals them round-robin to the
+ranks (one process per GPU, ``sweep.run_sharded``) and gathers only the small row dictionaries -- no data-path
+collective (BASELINE config 4).  On one GPU a driver reuses the device problems of a geometry across its mu / Pe
+values through the per-mesh caches of ``simulation`` / ``solvers``.
+
+Every driver takes ``mesh_size_dim`` (default: the reference's 0.02) so tests and smoke runs can use coarse meshes,
+and ``rank`` / ``world`` (default: read from ``torch.distributed`` when initialised).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import time
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from .parameters import Parameters, StepUptakeOpen, create_geometry_variations
+from .simulation import run_simulation
+from .sweep import run_sharded
+
+
+def _world(rank, world):
+    if rank is not None and world is not None:
+        return int(rank), int(world)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def _run(quiet, **kw):
+    if not quiet:
+        return run_simulation(**kw)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return run_simulation(**kw)
+
+
+def _frame(rows: List[dict], sort: Optional[Sequence[str]] = None):
+    import pandas as pd
+    df = pd.DataFrame(rows)
+    if sort and len(df):
+        df = df.sort_values(list(sort)).reset_index(drop=True)
+    return df
+
+
+def _save(df, directory, name, meta=None, rank=0):
+    if directory is None or rank != 0:
+        return None
+    os.makedirs(directory, exist_ok=True)
+    path = os.path.join(directory, name)
+    df.to_csv(path, index=False)
+    if meta is not None:
+        with open(os.path.join(directory, "study_metadata.json"), 'w') as f:
+            json.dump(meta, f, indent=4)
+    return path
+
+
+# ====================================================================== Phase B: no advection, mu x geometry
+MU_FACTORS_PHASE_B = [0.1, 0.5, 1.0]                       # no_advection_analysis_B.py:34
+
+
+def _params_no_adv(mu_factor, w_dim, h_dim, mesh_size_dim):
+    p = Parameters(mode='no-adv', mesh_size_dim=mesh_size_dim)
+    p.mu_dim = float(getattr(Parameters, 'MU_DIM_NO_ADV', p.mu_dim)) * float(mu_factor)   # :48-50
+    p.sulci_w_dim, p.sulci_h_dim = w_dim, h_dim
+    p.validate()
+    p.nondim()
+    return p
+
+
+def _flux_of(results, domain_type):                       # no_advection_analysis_B.py:55-66
+    fm = results.get('flux_metrics') or {}
+    if domain_type == 'sulcus':
+        pf = (fm.get('sulcus_specific') or {}).get('physical_flux') or {}
+        for key in ('y0_flux', 'y0_combined'):
+            if key in pf and isinstance(pf[key], dict):
+                return pf[key].get('total', np.nan)
+        return np.nan
+    return ((fm.get('physical_flux') or {}).get('bottom', {}) or {}).get('total', np.nan)
+
+
+def _avg_conc_of(results, domain_type):                   # no_advection_analysis_B.py:68-78
+    avg = (results.get('mass_metrics') or {}).get('average_concentration', None)
+    if domain_type == 'sulcus':
+        return avg.get('total', None) if isinstance(avg, dict) else None
+    return avg if isinstance(avg, (int, float)) else None
+
+
+def phase_b_case(case, mesh_size_dim=0.02, quiet=True):
+    """One (mu, geometry) pair: sulcus run + rectangle run -> CSV row (no_advection_analysis_B.py:112-172)."""
+    mu, gkey, gcfg = case
+    name = f"{gkey}_mu{str(mu).replace('.', 'p')}"
+    sulc = _run(quiet, mode='no-adv', study_type="mu Sweep", config_name=f"Sulcus_{name}", domain_type='sulcus',
+                params=_params_no_adv(mu, gcfg['sulci_w_dim'], gcfg['sulci_h_dim'], mesh_size_dim))
+    rect = _run(quiet, mode='no-adv', study_type="mu Sweep", config_name=f"Rect_{name}", domain_type='rectangular',
+                params=_params_no_adv(mu, gcfg['sulci_w_dim'], gcfg['sulci_h_dim'], mesh_size_dim))
+    conc_s, conc_r = _avg_conc_of(sulc, 'sulcus'), _avg_conc_of(rect, 'rectangular')
+    flux_s, flux_r = _flux_of(sulc, 'sulcus'), _flux_of(rect, 'rectangular')
+    CR = (conc_s / conc_r) if (conc_s is not None and conc_r not in (None, 0)) else np.nan
+    if flux_s is None or not np.isfinite(flux_s) or np.isclose(flux_s, 0.0):
+        flux_ratio = flux_err = np.nan
+    else:
+        flux_ratio = flux_r / flux_s
+        denom = abs(flux_s) if not np.isclose(abs(flux_s), 0.0) else 1.0
+        flux_err = 100.0 * (flux_r - flux_s) / denom
+    return {'geometry': gkey, 'width_mm': gcfg['sulci_w_dim'], 'depth_mm': gcfg['sulci_h_dim'],
+            'aspect_ratio': gcfg.get('aspect_ratio'), 'mu_factor': mu, 'avg_conc_sulc': conc_s, 'avg_conc_rect': conc_r,
+            'flux_sulc_y0': flux_s, 'flux_rect_bottom': flux_r, 'CR': CR, 'flux_ratio': flux_ratio,
+            'flux_error_pct': flux_err}
+
+
+def run_no_adv_mu_sweep(output_dir=None, mu_factors: Iterable[float] = None, geometries: Optional[Dict] = None,
+                        mesh_size_dim=0.02, rank=None, world=None, quiet=True):
+    """Reference ``run_no_adv_mu_sweep`` (23 geometries x 3 mu x {sulcus, rectangle} = 138 solves by default).
+    Returns the DataFrame with the reference's columns; rank 0 writes ``no_adv_mu_sweep_results.csv``."""
+    rank, world = _world(rank, world)
+    mu_factors = list(MU_FACTORS_PHASE_B if mu_factors is None else mu_factors)
+    configs = geometries if geometries is not None else create_geometry_variations(Parameters(mode='no-adv'), max_width=1.0)
+    cases = [(mu, g, cfg) for mu in mu_factors for g, cfg in configs.items()]
+    t0 = time.time()
+    done = run_sharded(cases, lambda c: phase_b_case(c, mesh_size_dim, quiet), rank, world)
+    df = _frame([row for _, row in done], ['mu_factor', 'geometry'])
+    p0 = Parameters(mode='no-adv')
+    p0.validate()
+    p0.nondim()
+    meta = {'study_type': 'No Advection — mu Sweep', 'timestamp': time.strftime("%Y-%m-%dT%H:%M:%S"),
+            'mu_factors': mu_factors, 'n_gpus': world, 'wall_s': time.time() - t0,
+            'baselines': {'MU_DIM_NO_ADV': getattr(Parameters, 'MU_DIM_NO_ADV', None), 'D_dim': p0.D_dim,
+                          'H_dim': p0.H_dim, 'L_dim': p0.L_dim}}
+    _save(df, output_dir, "no_adv_mu_sweep_results.csv", meta, rank)
+    return df
+
+
+# ====================================================================== adv-diff validation: Pe x mu, step surrogate
+PE_VALUES = [0.1, 1.0, 10]                                 # adv_diff_analysis.py:49-50
+MU_FACTORS_ADV = [0.1, 1.0, 10]
+REFERENCE_GEOMETRY = {'L_dim': 10.0, 'H_dim': 1.0, 'sulci_w_dim': 0.5, 'sulci_h_dim': 1.0, 'mesh_size_dim': 0.02,
+                      'refinement_factor': 1}              # :52-59
+D_DIM = 0.0003                                             # :61
+MU_DIM_BASE = 0.0003                                       # :62
+STEP_PARAMS = {'L_c': None, 'Gamma': 5.0, 'degree': 2}     # :64-68
+
+
+def create_base_parameters(Pe_target, mu_factor, mesh_size_dim=None):
+    """adv_diff_analysis.py:75-87."""
+    geo = dict(REFERENCE_GEOMETRY)
+    if mesh_size_dim is not None:
+        geo['mesh_size_dim'] = mesh_size_dim
+    params = Parameters(mode='adv-diff', U_ref_dim=Pe_target * D_DIM / geo['H_dim'], D_dim=D_DIM, **geo)
+    params.mu_dim = MU_DIM_BASE * float(mu_factor)
+    return params
+
+
+def extract_flux_data(results, domain_type):
+    """adv_diff_analysis.py:89-109."""
+    fm = results.get('flux_metrics', {}) or {}
+    if domain_type == 'sulcus':
+        src = ((fm.get('sulcus_specific') or {}).get('physical_flux') or {}).get('y0_flux', {}) or {}
+    else:
+        src = (fm.get('physical_flux') or {}).get('bottom', {}) or {}
+    return {'total_flux': src.get('total', None), 'diffusive_flux': src.get('diffusive', None),
+            'advective_flux': src.get('advective', None), 'uptake_flux': fm.get('uptake_flux', None)}
+
+
+def advdiff_case(case, mesh_size_dim=None, quiet=True):
+    """One (Pe, mu): sulcus reference, then the rectangle with the step mu(x) built from its mu_eff_open
+    (adv_diff_analysis.py:115-175, 201-260).  Returns the one or two CSV rows."""
+    Pe, mu_factor = case
+    params = create_base_parameters(Pe, mu_factor, mesh_size_dim)
+    params.validate()
+    params.nondim()
+    name = f"Pe_{Pe:.1f}_mu_{mu_factor:.1f}".replace('.', 'p')
+    sulc = _run(quiet, mode='adv-diff', study_type='AdvDiff Step Validation', config_name="Sulcus_" + name,
+                domain_type='sulcus', params=params)
+    me = sulc.get('mu_eff_comparison', {}) or {}
+    arc, sim, opn = me.get('mu_eff_arc'), me.get('mu_eff_sim'), me.get('mu_eff_open')
+    fs = extract_flux_data(sulc, 'sulcus')
+    avg_s = sulc.get('mass_metrics', {}).get('average_concentration', {}).get('total')
+    rows = [{'Pe': Pe, 'mu_factor': mu_factor, 'domain_type': 'sulcus', 'surrogate_type': 'reference', **fs,
+             'mu_eff_arc': arc, 'mu_eff_sim': sim, 'mu_eff_open': opn, 'avg_conc': avg_s, 'CR': np.nan,
+             'Mu_base_nondim': sulc['params'].mu, 'Domain_Length_mm': sulc['params'].L_dim,
+             'Sulcus_Width_mm': sulc['params'].sulci_w_dim}]
+    if opn is None:
+        return rows
+    pr = create_base_parameters(Pe, mu_factor, mesh_size_dim)
+    pr.validate()
+    pr.nondim()
+    xl, xr = pr.L / 2 - pr.sulci_w / 2, pr.L / 2 + pr.sulci_w / 2
+    mu_step = StepUptakeOpen(mu_base=float(mu_factor), mu_eff_target=float(opn), sulcus_left_x=xl, sulcus_right_x=xr,
+                             L_c=STEP_PARAMS['L_c'] or (0.1 * pr.sulci_w), Gamma=STEP_PARAMS['Gamma'],
+                             degree=STEP_PARAMS['degree'])
+    pr.mu = mu_step
+    pr.mu_dim = mu_step
+    rect = _run(quiet, mode='adv-diff', study_type='AdvDiff Step Validation', config_name="Rect_step_open_" + name,
+                domain_type='rectangular', params=pr, mu_variable=True)
+    fr = extract_flux_data(rect, 'rectangular')
+    avg_r = (rect.get('mass_metrics', {}) or {}).get('average_concentration')
+    rows.append({'Pe': Pe, 'mu_factor': mu_factor, 'domain_type': 'rectangular', 'surrogate_type': 'step_open', **fr,
+                 'mu_eff_arc': arc, 'mu_eff_sim': sim, 'mu_eff_open': opn, 'avg_conc': avg_r,
+                 'CR': (avg_s / avg_r) if (avg_s is not None and avg_r not in (None, 0.0)) else np.nan})
+    return rows
+
+
+def run_advdiff_step_validation(output_dir=None, pe_values=None, mu_factors=None, mesh_size_dim=None, rank=None,
+                                world=None, quiet=True):
+    """Reference ``run_advdiff_step_validation``: 3 Pe x 3 mu x {sulcus, step rectangle} = 18 solves (+ 1 Stokes solve
+    per geometry: the flow depends on the geometry only).  Rank 0 writes ``advdiff_validation_step_pe_x_mu.csv``."""
+    rank, world = _world(rank, world)
+    pe_values = list(PE_VALUES if pe_values is None else pe_values)
+    mu_factors = list(MU_FACTORS_ADV if mu_factors is None else mu_factors)
+    cases = [(Pe, mu) for Pe in pe_values for mu in mu_factors]
+    done = run_sharded(cases, lambda c: advdiff_case(c, mesh_size_dim, quiet), rank, world)
+    df = _frame([r for _, rows in done for r in rows], ['Pe', 'mu_factor', 'domain_type'])
+    df['flux_error_pct'] = np.nan                          # adv_diff_analysis.py:266-279
+    df['flux_ratio'] = np.nan
+    for Pe in pe_values:
+        for mu in mu_factors:
+            ref = (df['Pe'] == Pe) & (df['mu_factor'] == mu) & (df['domain_type'] == 'sulcus')
+            rec = (df['Pe'] == Pe) & (df['mu_factor'] == mu) & (df['domain_type'] == 'rectangular') & \
+                  (df['surrogate_type'] == 'step_open')
+            if not ref.any() or not rec.any():
+                continue
+            rf = df.loc[ref, 'total_flux'].iloc[0]
+            df.loc[rec, 'flux_ratio'] = df.loc[rec, 'total_flux'] / (rf if rf != 0 else 1.0)
+            df.loc[rec, 'flux_error_pct'] = 100.0 * (df.loc[rec, 'total_flux'] - rf) / (abs(rf) if rf != 0 else 1.0)
+    meta = {'study_type': 'AdvDiff Validation (Pe x mu) - Step mu only', 'timestamp': time.strftime("%Y-%m-%dT%H:%M:%S"),
+            'Pe_values': pe_values, 'mu_factors': mu_factors, 'reference_geometry': REFERENCE_GEOMETRY,
+            'parameters': {'D_dim': D_DIM, 'mu_dim_base': MU_DIM_BASE}, 'n_gpus': world}
+    _save(df, output_dir, "advdiff_validation_step_pe_x_mu.csv", meta, rank)
+    return df
+
+
+# ====================================================================== Phase A: mu sweep and aspect-ratio study
+REGIMES = {'small_uptake': [0.1, 0.25, 0.5, 0.75, 1.0, 1.25, 1.5, 2.0, 2.5, 3.0],          # no_advection_analysis_A.py:1276-1292
+           'moderate_uptake': [5.0, 7.5, 10.0, 12.5, 15.0],
+           'high_uptake': [50.0, 75.0, 100.0, 125.0, 150.0]}
+
+
+def _mu_eff_columns(result):
+    row = {}
+    if 'mu_eff_comparison' in result:                      # no_advection_analysis_A.py:64-90
+        d = result['mu_eff_comparison']
+        r, e = d.get('ratios', {}), d.get('errors_vs_sim', {})
+        row.update({'Mu_Eff_Simulation': d.get('mu_eff_sim'), 'Mu_Eff_Analytical': d.get('mu_eff_arc'),
+                    'Mu_Eff_Enhanced': d.get('mu_eff_enh'), 'Mu_Eff_Opening': d.get('mu_eff_open'),
+                    'Ratio_Sim': r.get('sim'), 'Ratio_Analytical': r.get('arc'), 'Ratio_Enhanced': r.get('enh'),
+                    'Ratio_Opening': r.get('open'), 'Relative_Error_Analytical': e.get('arc'),
+                    'Relative_Error_Enhanced': e.get('enh'), 'Relative_Error_Opening': e.get('open')})
+    if 'mass_metrics' in result:
+        row['Total_Mass'] = result['mass_metrics'].get('total_mass')
+    if 'flux_metrics' in result:
+        fm = result['flux_metrics'] or {}
+        mouth = ((fm.get('sulcus_specific') or {}).get('physical_flux') or {}).get('sulcus_opening') or {}
+        row['Mouth_Flux_Total'] = mouth.get('total')
+    return row
+
+
+def extract_mu_sweep_data(result, config_name, peclet_num=0):
+    """no_advection_analysis_A.py:51-105 (same columns, same order)."""
+    row = {'Config': config_name, 'Regime': result.get('regime', 'unknown'), 'Mu_Factor': result.get('mu_factor', 1.0),
+           'Mu_dim': result.get('mu_dim_used'), 'Mu': result.get('mu_used'), 'Baseline_Mu_dim': result.get('baseline_mu_dim')}
+    row.update(_mu_eff_columns(result))
+    return row
+
+
+def extract_aspect_ratio_data(result, config_name, aspect_ratio_type, width, depth, aspect_ratio):
+    """no_advection_analysis_A.py:107-164."""
+    row = {'Config': config_name, 'Aspect_Ratio_Type': aspect_ratio_type, 'Width': width, 'Depth': depth,
+           'Aspect_Ratio': aspect_ratio}
+    if 'parameters' in result or hasattr(result, 'mu'):
+        row['Mu'] = result.get('mu_used') or result.get('mu', 0)
+    row.update(_mu_eff_columns(result))
+    return row
+
+
+def _slim(result, **extra):
+    """What the row extractors read from a run_simulation result (fields stay on the rank that computed them)."""
+    out = {k: result[k] for k in ('mu_eff_comparison', 'mass_metrics', 'flux_metrics') if k in result}
+    out.update(extra)
+    return out
+
+
+def run_mu_sweep(output_dir=None, regimes: Optional[Dict[str, List[float]]] = None, w_dim=0.25, h_dim=0.25,
+                 mesh_size_dim=0.02, rank=None, world=None, quiet=True):
+    """Reference ``run_mu_sweep``: 20 mu values in three uptake regimes on the 0.25 x 0.25 mm sulcus; the mesh,
+    patterns and multigrid hierarchy are built once and reused by every mu.  Rank 0 writes
+    ``mu_parameter_sweep_results.csv``."""
+    rank, world = _world(rank, world)
+    regimes = REGIMES if regimes is None else regimes
+    base = float(getattr(Parameters, 'MU_DIM_NO_ADV'))
+    cases = [(reg, f) for reg, fs in regimes.items() for f in fs]
+
+    def one(case):
+        reg, factor = case
+        p = Parameters(mode='no-adv', mesh_size_dim=mesh_size_dim)
+        p.sulci_w_dim, p.sulci_h_dim = w_dim, h_dim
+        p.mu_dim = base * factor
+        p.validate()
+        p.nondim()
+        name = f"{reg}_mu_{factor:.1f}x"
+        res = _run(quiet, mode='no-adv', study_type="Phase A/Mu Parameter Sweep Simulations", config_name=name,
+                   domain_type='sulcus', params=p)
+        return extract_mu_sweep_data(_slim(res, regime=reg, mu_factor=factor, mu_dim_used=p.mu_dim, mu_used=p.mu,
+                                           baseline_mu_dim=base), name)
+    done = run_sharded(cases, one, rank, world)
+    df = _frame([row for _, row in done])
+    _save(df, output_dir, "mu_parameter_sweep_results.csv", None, rank)
+    return df
+
+
+def aspect_ratio_cases(max_width=1.0):
+    """The (type, AR, depth, width) list of no_advection_analysis_A.py:1355-1392."""
+    micro = np.logspace(np.log10(0.01), np.log10(0.10), 10)
+    meso = np.array([0.12, 0.15, 0.20, 0.25, 0.35, 0.50, 0.75, 1.00])
+    macro = np.array([1.50, 2.00, 2.50, 3.00, 3.50, 4.00, 4.50, 5.00])
+    depths = sorted(set(np.round(np.concatenate([micro, meso, macro]), 4)))
+    out = []
+    for name, ar in {'h_equals_w': 1.0, 'h_equals_2w': 2.0, 'h_equals_half_w': 0.5}.items():
+        for h in depths:
+            w = h / ar
+            if w > max_width:
+                continue
+            out.append((name, ar, float(h), float(w)))
+    return out
+
+
+def run_aspect_ratio_analysis(output_dir=None, cases=None, mesh_size_dim=0.02, rank=None, world=None, quiet=True):
+    """Reference ``run_aspect_ratio_analysis``.  Rank 0 writes ``aspect_ratio_analysis_results.csv``."""
+    rank, world = _world(rank, world)
+    cases = aspect_ratio_cases() if cases is None else list(cases)
+
+    def one(case):
+        name, ar, h, w = case
+        p = Parameters(mode='no-adv', mesh_size_dim=mesh_size_dim)
+        p.sulci_w_dim, p.sulci_h_dim = w, h
+        p.validate()
+        p.nondim()
+        cfg = f"{name}_h{h}"
+        res = _run(quiet, mode='no-adv', study_type="Phase A/Aspect Ratio Study Simulations", config_name=cfg,
+                   domain_type='sulcus', params=p)
+        return extract_aspect_ratio_data(_slim(res), cfg, name, w, h, ar)
+    done = run_sharded(cases, one, rank, world)
+    df = _frame([row for _, row in done])
+    _save(df, output_dir, "aspect_ratio_analysis_results.csv", None, rank)
+    return df

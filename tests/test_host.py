@@ -297,3 +297,23 @@ def test_oracle_point_evaluation_known_answers():
     # the mouth-level line of compute_velocity_metrics stays inside the channel on its whole length
     s, _ = co.line_profile(om, vals, 1e-6, 'h', (0, 10.0), 100)
     assert len(s) == 100
+
+
+def test_study_case_lists_match_reference_csvs():
+    """The case enumerations of sulcusfem/studies.py reproduce the keys of the reference's checked-in CSVs
+    (tests/golden/study_columns.json, made by tests/golden/make_study_columns.py from /root/reference)."""
+    import json
+    import os
+    from sulcusfem import studies
+    from sulcusfem.parameters import Parameters, create_geometry_variations
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'study_columns.json')))
+    ar = g['aspect_ratio_analysis_results.csv']
+    assert [f"{n}_h{h}" for n, _, h, _ in studies.aspect_ratio_cases()] == ar['configs']
+    mu = g['mu_parameter_sweep_results.csv']
+    assert [f"{r}_mu_{f:.1f}x" for r, fs in studies.REGIMES.items() for f in fs] == mu['configs']
+    pb = g['no_adv_mu_sweep_results.csv']
+    geos = create_geometry_variations(Parameters(mode='no-adv'), max_width=1.0)
+    assert sorted(geos) == pb['geometries'] and studies.MU_FACTORS_PHASE_B == pb['mu_factors']
+    assert len(geos) * len(studies.MU_FACTORS_PHASE_B) == pb['n_rows']
+    ad = g['advdiff_validation_step_pe_x_mu.csv']
+    assert sorted([float(p), float(m)] for p in studies.PE_VALUES for m in studies.MU_FACTORS_ADV) == ad['cases']
