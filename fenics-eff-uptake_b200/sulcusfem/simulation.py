@@ -20,6 +20,29 @@ from .solvers import (advdiff_solver, advdiff_solver_variable_mu, pure_diffusion
 
 _MESH_CACHE = {}
 MESH_OPTIONS = {'mesher': 'delaunay', 'uniform_refinements': 0}
+# ParaView export (reference simulation.py:137-138,165,300-311): off by default -- set to a directory (the
+# reference's top-level "Results") to get <dir>/<Mode> Simulations/<study>/<config>/ParaView Files/{velocity,
+# pressure,concentration}.pvd exactly where the reference puts them
+EXPORT_BASE_DIR = None
+_MODE_DIRS = {'adv-diff': 'Adv-Diff', 'no-adv': 'No Advection', 'no-uptake': 'No Uptake'}
+
+
+def _paraview_dir(mode, study_type, config_name):
+    if EXPORT_BASE_DIR is None:
+        return None
+    import os
+    d = os.path.join(EXPORT_BASE_DIR, f"{_MODE_DIRS.get(mode, mode.replace('-', ' ').title())} Simulations",
+                     study_type, config_name, "ParaView Files")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def _export(paraview_dir, name, f):
+    if paraview_dir is not None and f is not None:
+        import os
+        from .export import File
+        f.name_ = name
+        File(os.path.join(paraview_dir, name + ".pvd")) << f
 
 
 def _simulation_generate_mesh(params, domain_type, mesh_dir=None, paraview_dir=None):
@@ -108,9 +131,13 @@ def run_simulation(mode, study_type, config_name, domain_type, params, mu_variab
     valid_domain_types = ['sulcus', 'rectangular']
     if domain_type not in valid_domain_types:
         raise ValueError(f"Invalid domain type '{domain_type}'. Must be one of: {valid_domain_types}")
+    paraview_dir = _paraview_dir(mode, study_type, config_name)
     mesh_results = _simulation_generate_mesh(params, domain_type)
     u, p = _simulation_generate_vel(mode, domain_type, params, mesh_results)
+    _export(paraview_dir, "velocity", u)
+    _export(paraview_dir, "pressure", p)
     c = _simulation_generate_conc(u, mode, domain_type, params, mesh_results, mu_variable=mu_variable)
+    _export(paraview_dir, "concentration", c)
     results = _simulation_post_process(domain_type, params, mesh_results, c, u, p)
     print(f"\n✓ Simulation completed in {time.time() - start_time:.1f}s")
     return results

@@ -317,3 +317,36 @@ def test_study_case_lists_match_reference_csvs():
     assert len(geos) * len(studies.MU_FACTORS_PHASE_B) == pb['n_rows']
     ad = g['advdiff_validation_step_pe_x_mu.csv']
     assert sorted([float(p), float(m)] for p in studies.PE_VALUES for m in studies.MU_FACTORS_ADV) == ad['cases']
+
+
+def test_paraview_export_round_trip(tmp_path):
+    """File(path) << f (reference simulation.py:137-138,165): .pvd collection + .vtu with vertex values, read back
+    bit-exactly."""
+    import xml.etree.ElementTree as ET
+    from sulcusfem import fem
+    from sulcusfem.export import File
+    mesh = hm.rectangle_mesh(2.0, 1.0, 4, 3)
+    X = dm.p2_dof_coordinates(mesh)
+    c = fem.Function(fem.FunctionSpace(mesh, 'CG', 2), np.sin(X[:, 0]) + X[:, 1] / 3.0)
+    u = fem.Function(fem.VectorFunctionSpace(mesh, 'P', 2), np.concatenate([X[:, 1] * (1 - X[:, 1]), 0.1 * X[:, 0]]))
+    f = File(str(tmp_path / 'pv' / 'concentration.pvd'))
+    f << c
+    f << (c, 2.5)
+    File(str(tmp_path / 'pv' / 'velocity.pvd')) << u
+    coll = ET.parse(tmp_path / 'pv' / 'concentration.pvd').getroot().find('Collection').findall('DataSet')
+    assert [d.get('file') for d in coll] == ['concentration000000.vtu', 'concentration000001.vtu']
+    assert float(coll[1].get('timestep')) == 2.5
+    piece = ET.parse(tmp_path / 'pv' / 'concentration000000.vtu').getroot().find('UnstructuredGrid').find('Piece')
+    assert int(piece.get('NumberOfPoints')) == mesh.num_vertices and int(piece.get('NumberOfCells')) == mesh.num_cells
+    pts = np.array(piece.find('Points').find('DataArray').text.split(), dtype=float).reshape(-1, 3)
+    assert np.array_equal(pts[:, :2], mesh.coords) and not pts[:, 2].any()
+    conn = np.array(piece.find('Cells').findall('DataArray')[0].text.split(), dtype=int).reshape(-1, 3)
+    assert np.array_equal(conn, mesh.cells)
+    vals = np.array(piece.find('PointData').find('DataArray').text.split(), dtype=float)
+    assert np.array_equal(vals, c.values[:mesh.num_vertices])
+    pv = ET.parse(tmp_path / 'pv' / 'velocity000000.vtu').getroot().find('UnstructuredGrid').find('Piece')
+    v3 = np.array(pv.find('PointData').find('DataArray').text.split(), dtype=float).reshape(-1, 3)
+    n2 = len(u.values) // 2
+    assert np.array_equal(v3[:, 0], u.values[:mesh.num_vertices]) and np.array_equal(v3[:, 1], u.values[n2:n2 + mesh.num_vertices])
+    with pytest.raises(ValueError):
+        File(str(tmp_path / 'x.xdmf'))
