@@ -1,13 +1,10 @@
 mkdir -p gpurun_out
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err; echo "bench rc=$?"; tail -c 400 gpurun_out/bench_r1_final.err
+python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"; tail -c 500 gpurun_out/bench_n2.err
 python -c "
 import json
-r = json.load(open('gpurun_out/bench_r1_final.json'))
-print('ms/step', r['ms_per_step'], 'e2e ms', r['e2e']['ms_per_step'], 'frac', r['roofline']['frac'], 'launches', r['gpu_launches'])
+r = json.loads([l for l in open('gpurun_out/bench_n2.json') if l.startswith('{')][-1])
+print('n_gpus', r['n_gpus'], 'value', r['value'], 'ms/step', r['ms_per_step'], 'e2e', r['e2e']['value'], 'frac', r['roofline']['frac'])
 "
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu"
-$CMD > gpurun_out/plain_short.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 200000 --csv --log-file gpurun_out/launches_sell.csv $CMD > gpurun_out/ncu_list_sell.log 2>&1
-echo "ncu list rc=$?"; tail -2 gpurun_out/ncu_list_sell.log; wc -l gpurun_out/launches_sell.csv
-ncu --set full --clock-control none --import-source on -k regex:k_sell_stream -s 400 -c 12 -o gpurun_out/prof_bench_sell $CMD > gpurun_out/ncu_full_sell.log 2>&1
-echo "ncu full rc=$?"; tail -2 gpurun_out/ncu_full_sell.log
-gzip -f gpurun_out/launches_sell.csv
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 2>&1 | tail -2 | cut -c1-400
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/dd_bench.py --refine 3 --replicate-below 200000 2>&1 | grep "^{" | tail -1 > gpurun_out/dd2_r3_sell.json; cut -c1-700 gpurun_out/dd2_r3_sell.json
