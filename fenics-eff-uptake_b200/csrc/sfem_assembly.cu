@@ -166,52 +166,88 @@ __global__ void __launch_bounds__(kThreads) k_elem_p1_mass(int nc, const double*
 
 // ------------------------------------------------------------------ Taylor-Hood Stokes
 // a = grad u:grad v - div(v) p - q div(u); cell layout [ux x6, uy x6, p x3]; 15x15 row-major.
-__global__ void __launch_bounds__(128) k_elem_th(int nc, const double* __restrict__ geo, double* __restrict__ E) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
-    const TriGeom g = load_geom(geo, nc, c);
+// One thread computes one cell, but a thread-per-cell store of 225 doubles at a stride of 1800 bytes makes every
+// store instruction touch 32 different lines (measured: 0.62 TB/s).  The element matrices of a warp's 32 cells are
+// therefore staged through shared memory in three row groups (rows 0-5, 6-11, 12-14) and written out cell by
+// cell as contiguous 720 / 360-byte runs, 32 consecutive doubles per store instruction.
+constexpr int kThWarps = 4;
+constexpr int kThStride = 91;          // 90 staged doubles per cell + 1: odd stride, conflict-free column writes
+
+__device__ __forceinline__ void th_copy_out(const double* __restrict__ ws, double* __restrict__ dst, int len, int ncell,
+                                            int lane) {
+  for (int cell = 0; cell < ncell; ++cell)
+    for (int k = lane; k < len; k += 32) dst[(size_t)cell * 225 + k] = ws[cell * kThStride + k];
+}
+
+__global__ void __launch_bounds__(kThWarps * 32, 2) k_elem_th(int nc, const double* __restrict__ geo, double* __restrict__ E) {
+  extern __shared__ double th_stage[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* ws = th_stage + (size_t)warp * 32 * kThStride;
+  double* mine = ws + lane * kThStride;
+  for (long long base = ((long long)blockIdx.x * kThWarps + warp) * 32; base < nc; base += (long long)gridDim.x * kThWarps * 32) {
+    const int c = (int)base + lane;
+    const bool valid = c < nc;
+    const int ncell = (nc - base) < 32 ? (int)(nc - base) : 32;
     double K[36], Bx[18], By[18];
 #pragma unroll
     for (int k = 0; k < 36; ++k) K[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < 18; ++k) { Bx[k] = 0.0; By[k] = 0.0; }
-    const double wk = g.adet / 6.0;
+    if (valid) {
+      const TriGeom g = load_geom(geo, nc, c);
+      const double wk = g.adet / 6.0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      double Gx[6], Gy[6];
-      const double l[3] = {kQ2[q][0], kQ2[q][1], kQ2[q][2]};
-      p2_grads(g, l[0], l[1], l[2], Gx, Gy);
+      for (int q = 0; q < 3; ++q) {
+        double Gx[6], Gy[6];
+        const double l[3] = {kQ2[q][0], kQ2[q][1], kQ2[q][2]};
+        p2_grads(g, l[0], l[1], l[2], Gx, Gy);
 #pragma unroll
-      for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) K[i * 6 + j] = fma(wk, fma(Gx[i], Gx[j], Gy[i] * Gy[j]), K[i * 6 + j]);
+          for (int j = 0; j < 6; ++j) K[i * 6 + j] = fma(wk, fma(Gx[i], Gx[j], Gy[i] * Gy[j]), K[i * 6 + j]);
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 3; ++k)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          Bx[k * 6 + j] = fma(-wk * l[k], Gx[j], Bx[k * 6 + j]);
-          By[k * 6 + j] = fma(-wk * l[k], Gy[j], By[k * 6 + j]);
-        }
+          for (int j = 0; j < 6; ++j) {
+            Bx[k * 6 + j] = fma(-wk * l[k], Gx[j], Bx[k * 6 + j]);
+            By[k * 6 + j] = fma(-wk * l[k], Gy[j], By[k * 6 + j]);
+          }
+      }
     }
-    double* out = E + (size_t)c * 225;
+    double* out = E + (size_t)base * 225;
+    // rows 0..5 (u_x test functions): [K row | 0 | Bx column]
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
-      for (int j = 0; j < 6; ++j) {
-        out[i * 15 + j] = K[i * 6 + j];
-        out[i * 15 + 6 + j] = 0.0;
-        out[(6 + i) * 15 + j] = 0.0;
-        out[(6 + i) * 15 + 6 + j] = K[i * 6 + j];
-      }
-      for (int k = 0; k < 3; ++k) {
-        out[i * 15 + 12 + k] = Bx[k * 6 + i];
-        out[(6 + i) * 15 + 12 + k] = By[k * 6 + i];
-      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { mine[i * 15 + j] = K[i * 6 + j]; mine[i * 15 + 6 + j] = 0.0; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mine[i * 15 + 12 + k] = Bx[k * 6 + i];
     }
+    __syncwarp();
+    th_copy_out(ws, out, 90, ncell, lane);
+    __syncwarp();
+    // rows 6..11 (u_y test functions): [0 | K row | By column]
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { mine[i * 15 + j] = 0.0; mine[i * 15 + 6 + j] = K[i * 6 + j]; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mine[i * 15 + 12 + k] = By[k * 6 + i];
+    }
+    __syncwarp();
+    th_copy_out(ws, out + 90, 90, ncell, lane);
+    __syncwarp();
+    // rows 12..14 (pressure test functions): [Bx row | By row | 0]
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
-      for (int j = 0; j < 6; ++j) {
-        out[(12 + k) * 15 + j] = Bx[k * 6 + j];
-        out[(12 + k) * 15 + 6 + j] = By[k * 6 + j];
-      }
-      for (int m = 0; m < 3; ++m) out[(12 + k) * 15 + 12 + m] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { mine[k * 15 + j] = Bx[k * 6 + j]; mine[k * 15 + 6 + j] = By[k * 6 + j]; }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) mine[k * 15 + 12 + m] = 0.0;
     }
+    __syncwarp();
+    th_copy_out(ws, out + 180, 45, ncell, lane);
+    __syncwarp();
   }
 }
 
@@ -355,7 +391,13 @@ int sfem_elem_p1_advdiff(int nc, const double* geo, const int* cellverts, double
 int sfem_elem_th_stokes(int nc, const double* geo, double* E, void* stream) {
   if (nc <= 0) return SFEM_OK;
   Prof prof(PC_ELEM, (double)nc * (48.0 + 1800.0), (cudaStream_t)stream);
-  k_elem_th<<<grid_for(nc, 128, 16), 128, 0, (cudaStream_t)stream>>>(nc, geo, E);
+  constexpr int smem = kThWarps * 32 * kThStride * (int)sizeof(double);
+  static thread_local bool configured = false;
+  if (!configured) {
+    SFEM_CUDA(cudaFuncSetAttribute(k_elem_th, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  k_elem_th<<<grid_for(nc, kThWarps * 32, 2), kThWarps * 32, smem, (cudaStream_t)stream>>>(nc, geo, E);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

@@ -26,6 +26,7 @@ for name, rel in FILES.items():
         entry['mu_factors'] = sorted(set(float(r[hdr.index('mu_factor')]) for r in rows[1:]))
     if name.startswith('advdiff'):
         entry['cases'] = sorted(set((float(r[hdr.index('Pe')]), float(r[hdr.index('mu_factor')])) for r in rows[1:]))
+        entry['rows'] = [dict(zip(hdr, r)) for r in rows[1:]]          # the reference's own results (dolfin on Gmsh meshes)
     out[name] = entry
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'study_columns.json'), 'w') as f:
     json.dump(out, f, indent=1)

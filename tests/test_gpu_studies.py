@@ -61,3 +61,34 @@ def test_phase_a_schemas(tmp_path):
     da = studies.run_aspect_ratio_analysis(str(tmp_path), cases=cases, mesh_size_dim=H)
     assert list(da.columns) == GOLD['aspect_ratio_analysis_results.csv']['columns']
     assert len(da) == 3 and os.path.exists(tmp_path / 'aspect_ratio_analysis_results.csv')
+
+
+@pytest.mark.timeout(900)
+def test_advdiff_validation_against_reference_csv_at_reference_resolution():
+    """The reference's own numbers (dolfin 2019.1 on Gmsh meshes, h = 0.02; checked-in CSV
+    Advection-Diffusion/Results Data/advdiff_validation_step_pe_x_mu.csv) against this path on its own h = 0.02
+    meshes, rows (Pe, mu) = (1, 1) and (10, 1).  The meshes differ (Gmsh's cannot be regenerated), so agreement is
+    at mesh-discretisation tolerance.  Measured on B200 (profiles/r01_reference_csv_agreement.md): average
+    concentration 1.4e-6 ... 9e-5, uptake flux 1.8e-6 ... 5.4e-5, y=0 / bottom flux (corner singularities at the
+    inlet / floor) 1.8e-3 ... 2.8e-3, mu_eff_sim 1.8e-3 ... 2.8e-3, mu_eff_open 1e-3 ... 8.4e-3, mu_eff_arc bit-exact;
+    the bounds below leave a factor 2-4 of margin."""
+    from sulcusfem import studies
+    ref = {(float(r['Pe']), float(r['mu_factor']), r['domain_type']): r
+           for r in GOLD['advdiff_validation_step_pe_x_mu.csv']['rows']}
+    df = studies.run_advdiff_step_validation(None, pe_values=[1.0, 10.0], mu_factors=[1.0], mesh_size_dim=0.02)
+    report = []
+    for _, row in df.iterrows():
+        want = ref[(float(row['Pe']), float(row['mu_factor']), row['domain_type'])]
+        for key, tol in (('avg_conc', 3e-4), ('uptake_flux', 2e-4), ('total_flux', 6e-3), ('diffusive_flux', 6e-3),
+                         ('mu_eff_arc', 1e-15), ('mu_eff_sim', 6e-3), ('mu_eff_open', 2e-2)):
+            got, w = float(row[key]), float(want[key])
+            rel = abs(got - w) / abs(w)
+            report.append((row['Pe'], row['domain_type'], key, got, w, rel))
+            assert rel < tol, (row['Pe'], row['domain_type'], key, got, w, rel)
+        if row['domain_type'] == 'rectangular':
+            # the surrogate's flux error: reference +0.022 % (Pe = 1), +0.010 % (Pe = 10)
+            report.append((row['Pe'], 'rect', 'flux_error_pct', float(row['flux_error_pct']), float(want['flux_error_pct']), 0.0))
+            assert abs(float(row['flux_error_pct'])) < 0.1
+            assert abs(float(row['CR']) - float(want['CR'])) < 5e-3
+    for r in report:
+        print("REFCSV", *r)
