@@ -34,6 +34,7 @@ import numpy as np  # noqa: E402
 
 W_SULCUS, D_SULCUS, L_CH, H_CH = 0.5, 1.0, 10.0, 1.0
 PE, MU = 40.0, 1.0
+RTOL, STOKES_RTOL = 1e-13, 1e-12          # = sulcusfem.solvers.RTOL / STOKES_RTOL (the API path's defaults; checked in main)
 CAT_NAMES = ['spmv', 'spmv_dot', 'cheb_step', 'resid_d0', 'elem', 'gather', 'vec', 'other', 'spmv_staged']
 
 
@@ -97,7 +98,8 @@ def workload_config(args):
                         f"w={W_SULCUS} d={D_SULCUS} Pe={PE:g} mu={MU:g}, synthetic Delaunay mesh h={args.h} "
                         f"+ {args.refine} uniform refinements",
             "h": args.h, "refine": args.refine, "l2": "flushed between steps (512 MiB memset + 512 MiB read of a second buffer)",
-            "krylov_rtol": 1e-13, "parallelism": f"case-sharded x{args.gpus} (no collectives)"}
+            "krylov_rtol": {"scalar_true_residual": RTOL, "stokes_preconditioned_residual": STOKES_RTOL,
+                            "basis": "fields within 1e-10 relative L2 of the LU solution with >= 2.5x (scalar) / 100x (Stokes) margin, profiles/r01_tolerance_study.md"}, "parallelism": f"case-sharded x{args.gpus} (no collectives)"}
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -152,6 +154,8 @@ def run_gpu(args, rank, world):
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
     ctx = Context.get()
     lib = ctx.lib
+    from sulcusfem import solvers as _sv
+    assert (_sv.RTOL, _sv.STOKES_RTOL) == (RTOL, STOKES_RTOL), "bench.py tolerances differ from the API defaults"
     mu = MU + 0.05 * rank                      # every rank: its own sweep case
     t_setup = time.perf_counter()
     mr = build_mesh(args.h, args.refine)
@@ -173,9 +177,9 @@ def run_gpu(args, rank, world):
 
     def step():
         stokes.assemble(bc_mode=1)
-        ux, uy, p = stokes.solve(rtol=1e-14)
+        ux, uy, p = stokes.solve(rtol=STOKES_RTOL)
         scalar.assemble(D, ux, uy, mu_const=mu, bc_values={1: 1.0, 2: 0.0})
-        c = scalar.solve('fgmres', rtol=1e-13)
+        c = scalar.solve('fgmres', rtol=RTOL)
         F, M = plan.evaluate(c, ux, uy, D=D, mu_const=mu)
         info['stokes'], info['advdiff'] = dict(stokes.last_info), dict(scalar.last_info)
         return F, M

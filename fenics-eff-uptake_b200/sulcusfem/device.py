@@ -542,7 +542,7 @@ class StokesProblem:
         capi.check(lib.sfem_elem_p1_mass(self.nc, P(self.geo), P(E), ctx.stream), 'sfem_elem_p1_mass')
         capi.check(lib.sfem_gather_csr(self.Mp.nnz, P(cp), P(cc), P(E), P(self.Mp.vals), ctx.stream), 'sfem_gather_csr')
 
-    def solve(self, rtol=1e-14, maxit=2000):
+    def solve(self, rtol=1e-12, maxit=2000):
         ctx, lib = self.ctx, self.ctx.lib
         torch = _torch()
         if getattr(self, 'bc_mode', None) != 1:
