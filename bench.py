@@ -354,7 +354,7 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--h', type=float, default=0.02)
     ap.add_argument('--refine', type=int, default=int(os.environ.get('SFEM_BENCH_REFINE', 2)))
-    ap.add_argument('--cpu-h', type=float, default=0.04)
+    ap.add_argument('--cpu-h', type=float, default=0.03)    # ~10 s of single-thread CPU work per step (168 k dofs)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
