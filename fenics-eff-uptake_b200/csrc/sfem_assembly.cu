@@ -25,7 +25,9 @@ __device__ __forceinline__ TriGeom load_geom(const double* __restrict__ geo, int
   const double x0 = geo[0 * (size_t)nc + c], y0 = geo[1 * (size_t)nc + c];
   const double x1 = geo[2 * (size_t)nc + c], y1 = geo[3 * (size_t)nc + c];
   const double x2 = geo[4 * (size_t)nc + c], y2 = geo[5 * (size_t)nc + c];
-  const double det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+  // explicit roundings: the compiler may not pick a different multiply-add contraction in different kernels, so every
+  // kernel that inlines this helper sees bit-identical geometry
+  const double det = fma(x1 - x0, y2 - y0, -__dmul_rn(x2 - x0, y1 - y0));
   const double inv = 1.0 / det;
   TriGeom g;
   g.gx[0] = (y1 - y2) * inv; g.gy[0] = (x2 - x1) * inv;
@@ -50,9 +52,10 @@ __device__ __forceinline__ void p2_grads(const TriGeom& g, double l0, double l1,
   Gx[0] = a0 * g.gx[0]; Gy[0] = a0 * g.gy[0];
   Gx[1] = a1 * g.gx[1]; Gy[1] = a1 * g.gy[1];
   Gx[2] = a2 * g.gx[2]; Gy[2] = a2 * g.gy[2];
-  Gx[3] = 4.0 * (l2 * g.gx[1] + l1 * g.gx[2]); Gy[3] = 4.0 * (l2 * g.gy[1] + l1 * g.gy[2]);
-  Gx[4] = 4.0 * (l2 * g.gx[0] + l0 * g.gx[2]); Gy[4] = 4.0 * (l2 * g.gy[0] + l0 * g.gy[2]);
-  Gx[5] = 4.0 * (l1 * g.gx[0] + l0 * g.gx[1]); Gy[5] = 4.0 * (l1 * g.gy[0] + l0 * g.gy[1]);
+  // (explicit fma / rounded products, see load_geom)
+  Gx[3] = 4.0 * fma(l2, g.gx[1], __dmul_rn(l1, g.gx[2])); Gy[3] = 4.0 * fma(l2, g.gy[1], __dmul_rn(l1, g.gy[2]));
+  Gx[4] = 4.0 * fma(l2, g.gx[0], __dmul_rn(l0, g.gx[2])); Gy[4] = 4.0 * fma(l2, g.gy[0], __dmul_rn(l0, g.gy[2]));
+  Gx[5] = 4.0 * fma(l1, g.gx[0], __dmul_rn(l0, g.gx[1])); Gy[5] = 4.0 * fma(l1, g.gy[0], __dmul_rn(l0, g.gy[1]));
 }
 
 // degree-2 rule: 3 interior points, weights 1/6 (reference area 1/2)
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(128) k_elem_p2(int nc, const double* __restric
     double Ke[36];
 #pragma unroll
     for (int k = 0; k < 36; ++k) Ke[k] = 0.0;
-    const double wk = D * g.adet / 6.0;
+    const double wk = __ddiv_rn(__dmul_rn(D, g.adet), 6.0);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       double Gx[6], Gy[6];
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(128) k_elem_p2(int nc, const double* __restric
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) Ke[i * 6 + j] = fma(wk, fma(Gx[i], Gx[j], Gy[i] * Gy[j]), Ke[i * 6 + j]);
+        for (int j = 0; j < 6; ++j) Ke[i * 6 + j] = fma(wk, fma(Gx[i], Gx[j], __dmul_rn(Gy[i], Gy[j])), Ke[i * 6 + j]);
     }
     if (ADV) {
       double vx[6], vy[6];
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(kThWarps * 32, 2) k_elem_th(int nc, const doub
     for (int k = 0; k < 18; ++k) { Bx[k] = 0.0; By[k] = 0.0; }
     if (valid) {
       const TriGeom g = load_geom(geo, nc, c);
-      const double wk = g.adet / 6.0;
+      const double wk = __ddiv_rn(g.adet, 6.0);
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         double Gx[6], Gy[6];
@@ -204,13 +207,13 @@ __global__ void __launch_bounds__(kThWarps * 32, 2) k_elem_th(int nc, const doub
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j < 6; ++j) K[i * 6 + j] = fma(wk, fma(Gx[i], Gx[j], Gy[i] * Gy[j]), K[i * 6 + j]);
+          for (int j = 0; j < 6; ++j) K[i * 6 + j] = fma(wk, fma(Gx[i], Gx[j], __dmul_rn(Gy[i], Gy[j])), K[i * 6 + j]);
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
-            Bx[k * 6 + j] = fma(-wk * l[k], Gx[j], Bx[k * 6 + j]);
-            By[k * 6 + j] = fma(-wk * l[k], Gy[j], By[k * 6 + j]);
+            Bx[k * 6 + j] = fma(-__dmul_rn(wk, l[k]), Gx[j], Bx[k * 6 + j]);
+            By[k * 6 + j] = fma(-__dmul_rn(wk, l[k]), Gy[j], By[k * 6 + j]);
           }
       }
     }
@@ -251,6 +254,52 @@ __global__ void __launch_bounds__(kThWarps * 32, 2) k_elem_th(int nc, const doub
   }
 }
 
+// Divergence blocks only: EB[c][k][comp * 6 + j] = -int l_k d(phi_j)/dx_comp  (3 x 12 per cell: the B rows of the
+// cell's three pressure dofs against [u_x x6 | u_y x6]); the same numbers, in the same order of operations, as the
+// Bx / By entries of k_elem_th.  With the P2 stiffness kernel (D = 1) for K this is everything the block-form Stokes
+// solver needs -- 72 doubles per cell instead of 225.  Staged through shared memory like k_elem_th.
+constexpr int kDivStride = 37;
+
+__global__ void __launch_bounds__(kThWarps * 32) k_elem_th_div(int nc, const double* __restrict__ geo, double* __restrict__ EB) {
+  __shared__ double stage[kThWarps * 32 * kDivStride];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* ws = stage + warp * 32 * kDivStride;
+  double* mine = ws + lane * kDivStride;
+  for (long long base = ((long long)blockIdx.x * kThWarps + warp) * 32; base < nc; base += (long long)gridDim.x * kThWarps * 32) {
+    const int c = (int)base + lane;
+    const int ncell = (nc - base) < 32 ? (int)(nc - base) : 32;
+    double Bx[18], By[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) { Bx[k] = 0.0; By[k] = 0.0; }
+    if (c < nc) {
+      const TriGeom g = load_geom(geo, nc, c);
+      const double wk = __ddiv_rn(g.adet, 6.0);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        double Gx[6], Gy[6];
+        const double l[3] = {kQ2[q][0], kQ2[q][1], kQ2[q][2]};
+        p2_grads(g, l[0], l[1], l[2], Gx, Gy);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            Bx[k * 6 + j] = fma(-__dmul_rn(wk, l[k]), Gx[j], Bx[k * 6 + j]);
+            By[k * 6 + j] = fma(-__dmul_rn(wk, l[k]), Gy[j], By[k * 6 + j]);
+          }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { mine[k * 12 + j] = Bx[k * 6 + j]; mine[k * 12 + 6 + j] = By[k * 6 + j]; }
+    __syncwarp();
+    double* out = EB + (size_t)base * 36;
+    for (int cell = 0; cell < ncell; ++cell)
+      for (int k = lane; k < 36; k += 32) out[(size_t)cell * 36 + k] = ws[cell * kDivStride + k];
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------ Robin facets
 // P2 trace basis on a facet parametrised by t in [0,1] from vertex a to vertex b: [a, b, mid]
 template <int NDOF>
@@ -286,6 +335,20 @@ __global__ void __launch_bounds__(kThreads) k_facet_robin(int nf, const double* 
     }
     double* out = F + (size_t)f * (NDOF * NDOF);
     for (int k = 0; k < NDOF * NDOF; ++k) out[k] = M[k];
+  }
+}
+
+// vals[k] = 0 for every entry whose row or column is flagged (Dirichlet elimination of the rectangular Stokes
+// blocks: bc columns of B, bc rows of B^T)
+__global__ void __launch_bounds__(kThreads) k_csr_zero_flagged(int nrows, const int* __restrict__ rowptr, const int* __restrict__ cols,
+                                                               double* __restrict__ vals, const unsigned char* __restrict__ row_flag,
+                                                               const unsigned char* __restrict__ col_flag) {
+  const int lane = threadIdx.x & 3;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; row < nrows;
+       row += ((long long)gridDim.x * blockDim.x) >> 2) {
+    const bool rz = row_flag != nullptr && row_flag[row];
+    for (int k = rowptr[row] + lane; k < rowptr[row + 1]; k += 4)
+      if (rz || (col_flag != nullptr && col_flag[cols[k]])) vals[k] = 0.0;
   }
 }
 
@@ -398,6 +461,23 @@ int sfem_elem_th_stokes(int nc, const double* geo, double* E, void* stream) {
     configured = true;
   }
   k_elem_th<<<grid_for(nc, kThWarps * 32, 2), kThWarps * 32, smem, (cudaStream_t)stream>>>(nc, geo, E);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_elem_th_div(int nc, const double* geo, double* EB, void* stream) {
+  if (nc <= 0) return SFEM_OK;
+  Prof prof(PC_ELEM, (double)nc * (48.0 + 288.0), (cudaStream_t)stream);
+  k_elem_th_div<<<grid_for(nc, kThWarps * 32, 8), kThWarps * 32, 0, (cudaStream_t)stream>>>(nc, geo, EB);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_csr_zero_flagged(int nrows, const int* rowptr, const int* cols, double* vals, const unsigned char* row_flag,
+                          const unsigned char* col_flag, void* stream) {
+  if (nrows <= 0 || (row_flag == nullptr && col_flag == nullptr)) return SFEM_OK;
+  sell_mark_dirty(vals);
+  k_csr_zero_flagged<<<grid_for(nrows, kThreads / 4), kThreads, 0, (cudaStream_t)stream>>>(nrows, rowptr, cols, vals, row_flag, col_flag);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

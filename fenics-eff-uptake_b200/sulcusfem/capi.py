@@ -49,6 +49,8 @@ SIGNATURES = {
     'sfem_elem_p2_advdiff': (_i, [_i, _p, _p, _d, _p, _p, _p, _p]),
     'sfem_elem_p1_advdiff': (_i, [_i, _p, _p, _d, _p, _p, _i, _p, _p]),
     'sfem_elem_th_stokes': (_i, [_i, _p, _p, _p]),
+    'sfem_elem_th_div': (_i, [_i, _p, _p, _p]),
+    'sfem_csr_zero_flagged': (_i, [_i, _p, _p, _p, _p, _p, _p]),
     'sfem_elem_p1_mass': (_i, [_i, _p, _p, _p]),
     'sfem_facet_p2_robin': (_i, [_i, _p, _p, _d, _p, _i, _p, _p]),
     'sfem_facet_p1_robin': (_i, [_i, _p, _p, _d, _p, _i, _p, _p]),

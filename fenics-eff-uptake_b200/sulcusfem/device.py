@@ -427,37 +427,28 @@ class StokesProblem:
         self.nv = nv = mesh.num_vertices
         self.n = 2 * n2 + nv
         self.nc = mesh.num_cells
-        cd = dm.th_cell_dofs(mesh)
-        self.pattern = dm.build_pattern(self.n, self.n, [(cd, cd)])
-        pat = self.pattern
-        self.A = DeviceCsr(ctx, self.n, self.n, pat.rowptr, pat.cols, sell=False)   # parity / export only: the solver iterates on the block views
-        self.contrib_ptr = ctx.up(pat.contrib_ptr, np.int32)
-        self.contrib_code = ctx.up(pat.contrib_code, np.int32)
-        self.E = ctx.zeros(pat.buffer_len)
+        self._full = None                      # full Taylor-Hood CSR + gather map: built on first use (parity / export)
         self.geo = ctx.up(cell_geometry(mesh), np.float64)
         # velocity block: scalar stiffness hierarchy with the velocity Dirichlet set, 2 interleaved RHS
         self.vel = ScalarProblem(mesh, bc_markers, dirichlet_ids=tuple(velocity_ids), robin_id=None,
                                  hierarchy=hierarchy, ctx=ctx, nb=2)
-        # ---- block views of the assembled matrix: slot maps TH CSR -> K / B / B^T (host, once)
-        rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(pat.rowptr.astype(np.int64)))
-        cols = pat.cols.astype(np.int64)
-        kslot = np.flatnonzero((rows < n2) & (cols < n2))
-        Kp = self.vel.fine.pattern
-        if len(kslot) != Kp.nnz or not np.array_equal(cols[kslot], Kp.cols):
-            raise capi.SulcusFemError("Taylor-Hood velocity block does not match the P2 scalar pattern")
-        self.k_slot = ctx.up(kslot, np.int32)
-
-        def sub_csr(sel, new_rows, new_cols, nrows, ncols):
-            slot = np.flatnonzero(sel)
-            r, c = new_rows[slot], new_cols[slot]
-            order = np.lexsort((c, r))
-            slot, r, c = slot[order], r[order], c[order]
-            rp = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=nrows))]).astype(np.int32)
-            return DeviceCsr(ctx, nrows, ncols, rp, c.astype(np.int32)), ctx.up(slot, np.int32)
-        il_rows = 2 * (rows % n2) + rows // n2          # interleaved velocity numbering (valid for rows < 2 n2)
-        il_cols = 2 * (cols % n2) + cols // n2
-        self.BT, self.bt_slot = sub_csr((rows < 2 * n2) & (cols >= 2 * n2), il_rows, cols - 2 * n2, 2 * n2, nv)
-        self.B, self.b_slot = sub_csr((rows >= 2 * n2) & (cols < 2 * n2), rows - 2 * n2, il_cols, nv, 2 * n2)
+        # ---- divergence blocks assembled directly (host plan, once): B (nv x 2 n2) and B^T (2 n2 x nv) with the
+        # velocity columns / rows in interleaved numbering, both gathered from ONE element buffer EB [nc][3][12]
+        # (sfem_elem_th_div: rows = the cell's pressure dofs, columns = [u_x x6 | u_y x6])
+        c2 = dm.p2_cell_dofs(mesh).astype(np.int64)
+        il = np.concatenate([2 * c2, 2 * c2 + 1], axis=1)                       # [nc, 12] interleaved velocity dofs
+        c1v = dm.p1_cell_dofs(mesh).astype(np.int64)                            # [nc, 3]
+        pb = dm.build_pattern(nv, 2 * n2, [(c1v, il)])                          # codes: cell*36 + k*12 + m
+        pbt = dm.build_pattern(2 * n2, nv, [(il, c1v)])                         # codes: cell*36 + m*3 + k  -> remap
+        loc = pbt.contrib_code.astype(np.int64) % 36
+        bt_code = (pbt.contrib_code.astype(np.int64) - loc) + (loc % 3) * 12 + loc // 3
+        self.B = DeviceCsr(ctx, nv, 2 * n2, pb.rowptr, pb.cols)
+        self.BT = DeviceCsr(ctx, 2 * n2, nv, pbt.rowptr, pbt.cols)
+        self._b_map = (ctx.up(pb.contrib_ptr, np.int32), ctx.up(pb.contrib_code, np.int32))
+        self._bt_map = (ctx.up(pbt.contrib_ptr, np.int32), ctx.up(bt_code, np.int32))
+        self.EB = ctx.zeros(36 * self.nc)
+        self.g_il = ctx.zeros(self.n)           # Dirichlet values in solver layout [u interleaved | p = 0]
+        self.flag_il = None                     # uint8 [2 n2]: interleaved velocity Dirichlet flags
         # pressure mass matrix (P1)
         c1 = dm.p1_cell_dofs(mesh)
         mp = dm.build_pattern(nv, nv, [(c1, c1)])
@@ -512,6 +503,17 @@ class StokesProblem:
         self.bc_flag_host = flag
         self.bc_flag = self.ctx.up(flag, np.uint8)
         self.bc_val.copy_(self.ctx.up(g, np.float64))
+        # solver layout (interleaved velocity): flags, values, scratch for the block elimination
+        n2 = self.n2
+        fil = np.empty(2 * n2, dtype=np.uint8)
+        fil[0::2], fil[1::2] = flag[:n2], flag[n2:2 * n2]
+        gil = np.zeros(self.n)
+        gil[0:2 * n2:2], gil[1:2 * n2:2] = g[:n2], g[n2:2 * n2]
+        self.flag_il = self.ctx.up(fil, np.uint8)
+        self.flag_il_bool = self.flag_il.bool()
+        self.g_il.copy_(self.ctx.up(gil, np.float64))
+        self._zero_n2 = self.ctx.zeros(n2)
+        self._scratch_n2 = self.ctx.zeros(n2)
         return g
 
     def _to_solver_layout(self, blocked, out):
@@ -519,28 +521,113 @@ class StokesProblem:
         capi.check(lib.sfem_vec_interleave2(n2, P(blocked[:n2]), P(blocked[n2:2 * n2]), P(out), ctx.stream), 'interleave')
         out[2 * n2:].copy_(blocked[2 * n2:])
 
-    def assemble(self, bc_mode=1):
-        """Assemble the Taylor-Hood matrix (+ Dirichlet); with ``bc_mode=1`` (symmetric elimination) also
-        refresh the block views and the preconditioner used by :meth:`solve`."""
+    # ------------------------------------------------------------------ full Taylor-Hood matrix (lazy)
+    def _ensure_full(self):
+        """dolfin's clique pattern of the mixed space (225 entries per cell, structural zeros included), its gather
+        map and the slot maps to the block views.  The solver never needs it; it is built on first use for parity
+        checks / export of the assembled matrix."""
+        if self._full is not None:
+            return self._full
+        ctx, n2, nv = self.ctx, self.n2, self.nv
+        cd = dm.th_cell_dofs(self.mesh)
+        pat = dm.build_pattern(self.n, self.n, [(cd, cd)])
+        A = DeviceCsr(ctx, self.n, self.n, pat.rowptr, pat.cols, sell=False)
+        rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(pat.rowptr.astype(np.int64)))
+        cols = pat.cols.astype(np.int64)
+        kslot = np.flatnonzero((rows < n2) & (cols < n2))
+        Kp = self.vel.fine.pattern
+        if len(kslot) != Kp.nnz or not np.array_equal(cols[kslot], Kp.cols):
+            raise capi.SulcusFemError("Taylor-Hood velocity block does not match the P2 scalar pattern")
+
+        def sub_slots(sel, new_rows, new_cols, want):
+            slot = np.flatnonzero(sel)
+            r, c = new_rows[slot], new_cols[slot]
+            order = np.lexsort((c, r))
+            if len(slot) != want.nnz or not np.array_equal(c[order], want.cols[:want.nnz].cpu().numpy()):
+                raise capi.SulcusFemError("Taylor-Hood divergence block does not match the directly built pattern")
+            return ctx.up(slot[order], np.int32)
+        il_rows = 2 * (rows % n2) + rows // n2          # interleaved velocity numbering (valid for rows < 2 n2)
+        il_cols = 2 * (cols % n2) + cols // n2
+        self._full = dict(
+            pattern=pat, A=A, contrib_ptr=ctx.up(pat.contrib_ptr, np.int32), contrib_code=ctx.up(pat.contrib_code, np.int32),
+            E=ctx.zeros(pat.buffer_len), k_slot=ctx.up(kslot, np.int32),
+            bt_slot=sub_slots((rows < 2 * n2) & (cols >= 2 * n2), il_rows, cols - 2 * n2, self.BT),
+            b_slot=sub_slots((rows >= 2 * n2) & (cols < 2 * n2), rows - 2 * n2, il_cols, self.B))
+        return self._full
+
+    @property
+    def pattern(self):
+        return self._ensure_full()['pattern']
+
+    @property
+    def A(self):
+        return self._ensure_full()['A']
+
+    def _assemble_preconditioner(self):
+        # coarse velocity levels + pressure mass matrix
         ctx, lib = self.ctx, self.ctx.lib
-        capi.check(lib.sfem_elem_th_stokes(self.nc, P(self.geo), P(self.E), ctx.stream), 'sfem_elem_th_stokes')
-        capi.check(lib.sfem_gather_csr(self.A.nnz, P(self.contrib_ptr), P(self.contrib_code), P(self.E), P(self.A.vals),
-                                       ctx.stream), 'sfem_gather_csr')
-        self.rhs.zero_()
-        capi.check(lib.sfem_apply_dirichlet(self.n, self.A.nnz, P(self.A.rowptr), P(self.A.cols), P(self.A.vals), P(self.rhs),
-                                            P(self.bc_flag), P(self.bc_val), bc_mode, ctx.stream), 'sfem_apply_dirichlet')
-        self.bc_mode = bc_mode
-        if bc_mode != 1:
-            return
-        K = self.vel.fine.A
-        capi.check(lib.sfem_csr_extract(K.nnz, P(self.k_slot), P(self.A.vals), P(K.vals), ctx.stream), 'sfem_csr_extract')
-        capi.check(lib.sfem_csr_extract(self.B.nnz, P(self.b_slot), P(self.A.vals), P(self.B.vals), ctx.stream), 'sfem_csr_extract')
-        capi.check(lib.sfem_csr_extract(self.BT.nnz, P(self.bt_slot), P(self.A.vals), P(self.BT.vals), ctx.stream), 'sfem_csr_extract')
-        # preconditioner pieces: coarse velocity levels + pressure mass matrix
         self.vel.assemble(1.0, robin=False, fine=False)
         cp, cc, E = self._mp
         capi.check(lib.sfem_elem_p1_mass(self.nc, P(self.geo), P(E), ctx.stream), 'sfem_elem_p1_mass')
         capi.check(lib.sfem_gather_csr(self.Mp.nnz, P(cp), P(cc), P(E), P(self.Mp.vals), ctx.stream), 'sfem_gather_csr')
+
+    def assemble(self, bc_mode=1, full=None):
+        """Assemble the Stokes system (+ Dirichlet).
+
+        ``bc_mode=1`` (symmetric elimination; what :meth:`solve` needs), ``full=False`` (default): the block views
+        K, B, B^T are assembled DIRECTLY -- 72 element entries per cell instead of the 225 of the mixed-space
+        matrix -- and eliminated in place; the right-hand side is lifted with two SpMVs.  The numbers are the ones
+        the full path produces (same element arithmetic, same gather order): the tests compare them bit for bit.
+        ``full=True`` (forced for ``bc_mode=0``, dolfin's identity-row mode): assemble the Taylor-Hood matrix with
+        dolfin's clique pattern into :attr:`A`, apply the conditions there and extract the blocks."""
+        ctx, lib = self.ctx, self.ctx.lib
+        torch = _torch()
+        if full is None:
+            full = bc_mode != 1
+        self.bc_mode = bc_mode
+        if full or bc_mode != 1:
+            F = self._ensure_full()
+            A = F['A']
+            capi.check(lib.sfem_elem_th_stokes(self.nc, P(self.geo), P(F['E']), ctx.stream), 'sfem_elem_th_stokes')
+            capi.check(lib.sfem_gather_csr(A.nnz, P(F['contrib_ptr']), P(F['contrib_code']), P(F['E']), P(A.vals),
+                                           ctx.stream), 'sfem_gather_csr')
+            self.rhs.zero_()
+            capi.check(lib.sfem_apply_dirichlet(self.n, A.nnz, P(A.rowptr), P(A.cols), P(A.vals), P(self.rhs),
+                                                P(self.bc_flag), P(self.bc_val), bc_mode, ctx.stream), 'sfem_apply_dirichlet')
+            if bc_mode != 1:
+                return
+            K = self.vel.fine.A
+            capi.check(lib.sfem_csr_extract(K.nnz, P(F['k_slot']), P(A.vals), P(K.vals), ctx.stream), 'sfem_csr_extract')
+            capi.check(lib.sfem_csr_extract(self.B.nnz, P(F['b_slot']), P(A.vals), P(self.B.vals), ctx.stream), 'sfem_csr_extract')
+            capi.check(lib.sfem_csr_extract(self.BT.nnz, P(F['bt_slot']), P(A.vals), P(self.BT.vals), ctx.stream), 'sfem_csr_extract')
+            self._to_solver_layout(self.rhs, self.rhs_il)
+            self._assemble_preconditioner()
+            return
+        # ---- direct block assembly
+        n2, nv = self.n2, self.nv
+        f = self.vel.fine
+        K = f.A
+        f.assemble(1.0, robin=False)                                  # un-eliminated scalar stiffness (P2 kernel, D = 1)
+        capi.check(lib.sfem_elem_th_div(self.nc, P(self.geo), P(self.EB), ctx.stream), 'sfem_elem_th_div')
+        for M, (cp, cc) in ((self.B, self._b_map), (self.BT, self._bt_map)):
+            capi.check(lib.sfem_gather_csr(M.nnz, P(cp), P(cc), P(self.EB), P(M.vals), ctx.stream), 'sfem_gather_csr')
+        # lifting  b = -[K g_u ; B g_u]  (g_u = Dirichlet values, zero elsewhere), then b = g on the Dirichlet rows
+        r = self.rhs_il
+        r.zero_()
+        K.spmv(self.g_il[:2 * n2], y=r[:2 * n2], b=r[:2 * n2], mode=1, nb=2)      # r_u = 0 - K g_u (both components)
+        self.B.spmv(self.g_il[:2 * n2], y=r[2 * n2:], b=r[2 * n2:], mode=1)        # r_p = 0 - B g_u
+        torch.where(self.flag_il_bool, self.g_il[:2 * n2], r[:2 * n2], out=r[:2 * n2])
+        # symmetric elimination of the blocks
+        capi.check(lib.sfem_apply_dirichlet(n2, K.nnz, P(K.rowptr), P(K.cols), P(K.vals), P(self._scratch_n2), P(f.bc_flag),
+                                            P(self._zero_n2), 1, ctx.stream), 'sfem_apply_dirichlet')
+        capi.check(lib.sfem_csr_zero_flagged(nv, P(self.B.rowptr), P(self.B.cols), P(self.B.vals), None, P(self.flag_il),
+                                             ctx.stream), 'sfem_csr_zero_flagged')
+        capi.check(lib.sfem_csr_zero_flagged(2 * n2, P(self.BT.rowptr), P(self.BT.cols), P(self.BT.vals), P(self.flag_il), None,
+                                             ctx.stream), 'sfem_csr_zero_flagged')
+        # blocked copy of the right-hand side (public layout [ux | uy | p])
+        capi.check(lib.sfem_vec_deinterleave2(n2, P(r), P(self.rhs[:n2]), P(self.rhs[n2:2 * n2]), ctx.stream), 'deinterleave')
+        self.rhs[2 * n2:].copy_(r[2 * n2:])
+        self._assemble_preconditioner()
 
     def solve(self, rtol=1e-12, maxit=2000):
         ctx, lib = self.ctx, self.ctx.lib
@@ -548,9 +635,7 @@ class StokesProblem:
         if getattr(self, 'bc_mode', None) != 1:
             raise capi.SulcusFemError("StokesProblem.solve needs assemble(bc_mode=1)")
         n2 = self.n2
-        self._to_solver_layout(self.rhs, self.rhs_il)
-        self.x.copy_(self.bc_val * self.bc_flag.to(torch.float64))
-        self._to_solver_layout(self.x, self.x_il)
+        self.x_il.copy_(self.g_il)                                    # initial guess: Dirichlet values, zero elsewhere
         info = (C.c_double * 4)()
         rc = lib.sfem_stokes_solve(self.handle, P(self.rhs_il), P(self.x_il), float(rtol), int(maxit), info, ctx.stream)
         capi.check(rc, 'sfem_stokes_solve')

@@ -350,3 +350,52 @@ def test_paraview_export_round_trip(tmp_path):
     assert np.array_equal(v3[:, 0], u.values[:mesh.num_vertices]) and np.array_equal(v3[:, 1], u.values[n2:n2 + mesh.num_vertices])
     with pytest.raises(ValueError):
         File(str(tmp_path / 'x.xdmf'))
+
+
+def test_direct_divergence_block_maps_match_mixed_space_extraction():
+    """Host plan of the direct Stokes block assembly (device.StokesProblem): gathering B and B^T from the 3 x 12
+    divergence element buffer gives exactly the entries (same order, same summation order) that the mixed-space
+    matrix, assembled with dolfin's clique pattern and cut into blocks, holds."""
+    mesh = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.2, 'sulcus')
+    n2, nv, nc = dm.p2_num_dofs(mesh), mesh.num_vertices, mesh.num_cells
+    n = 2 * n2 + nv
+    rng = np.random.default_rng(3)
+    EB = rng.random((nc, 3, 12))
+    # the same numbers placed in a 15 x 15 Taylor-Hood element matrix (rows/cols [ux x6, uy x6, p x3])
+    E = np.zeros((nc, 15, 15))
+    E[:, 12:, :12] = EB
+    E[:, :12, 12:] = EB.transpose(0, 2, 1)
+    cd = dm.th_cell_dofs(mesh)
+    pat = dm.build_pattern(n, n, [(cd, cd)])
+
+    def gather(p, buf):
+        out = np.zeros(p.nnz)
+        for s_ in range(p.nnz):                        # fixed order, like k_gather
+            acc = 0.0
+            for k in range(p.contrib_ptr[s_], p.contrib_ptr[s_ + 1]):
+                acc += buf[p.contrib_code[k]]
+            out[s_] = acc
+        return out
+    A = gather(pat, E.ravel())
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(pat.rowptr.astype(np.int64)))
+    cols = pat.cols.astype(np.int64)
+    # direct plans, exactly as StokesProblem.__init__ builds them
+    c2 = dm.p2_cell_dofs(mesh).astype(np.int64)
+    il = np.concatenate([2 * c2, 2 * c2 + 1], axis=1)
+    c1v = dm.p1_cell_dofs(mesh).astype(np.int64)
+    pb = dm.build_pattern(nv, 2 * n2, [(c1v, il)])
+    pbt = dm.build_pattern(2 * n2, nv, [(il, c1v)])
+    loc = pbt.contrib_code.astype(np.int64) % 36
+    pbt.contrib_code = ((pbt.contrib_code.astype(np.int64) - loc) + (loc % 3) * 12 + loc // 3).astype(np.int32)
+    Bd, BTd = gather(pb, EB.ravel()), gather(pbt, EB.ravel())
+    # blocks cut out of the mixed-space matrix, velocity in interleaved numbering, sorted by (row, col)
+    il_rows = 2 * (rows % n2) + rows // n2
+    il_cols = 2 * (cols % n2) + cols // n2
+    for sel, r_, c_, p, got in (((rows >= 2 * n2) & (cols < 2 * n2), rows - 2 * n2, il_cols, pb, Bd),
+                                ((rows < 2 * n2) & (cols >= 2 * n2), il_rows, cols - 2 * n2, pbt, BTd)):
+        slot = np.flatnonzero(sel)
+        order = np.lexsort((c_[slot], r_[slot]))
+        slot = slot[order]
+        assert len(slot) == p.nnz and np.array_equal(c_[slot], p.cols)
+        assert np.array_equal(np.bincount(r_[slot], minlength=p.nrows), np.diff(p.rowptr))
+        assert np.array_equal(A[slot], got)            # bit for bit

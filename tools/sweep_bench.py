@@ -1,0 +1,62 @@
+"""Sweep throughput (BASELINE configs[3]: independent mu / Pe cases): solves per second through the study drivers.
+
+    python tools/sweep_bench.py [--h 0.02]            (under torchrun: cases are dealt round-robin to the ranks)
+
+Two reference studies at the reference's resolution:
+  * Phase A mu sweep -- 20 mu values on ONE geometry (0.25 x 0.25 mm sulcus): mesh, patterns, hierarchy and device
+    problems are built once, every further mu is assemble + CG solve + functionals;
+  * adv-diff Pe x mu validation -- 9 sulcus + 9 step-rectangle solves on two meshes, one Stokes solve per mesh.
+Wall clock around the driver calls (host mesh generation and set-up included -- that is what a user waits for), plus the
+marginal time per case once the geometry is cached.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'fenics-eff-uptake_b200'))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--h', type=float, default=0.02)
+    args = ap.parse_args()
+    import torch
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"))
+    from sulcusfem import studies, simulation
+    out = {'n_gpus': world, 'h': args.h}
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        return r, time.perf_counter() - t
+    # Phase A mu sweep: first call builds the geometry, second call (same cases) runs on the cached one
+    df, t_cold = timed(lambda: studies.run_mu_sweep(None, mesh_size_dim=args.h))
+    df, t_warm = timed(lambda: studies.run_mu_sweep(None, mesh_size_dim=args.h))
+    out['mu_sweep'] = {'cases': len(df), 'wall_s_first': t_cold, 'wall_s_cached_geometry': t_warm,
+                       'solves_per_s_first': len(df) / t_cold, 'solves_per_s_cached_geometry': len(df) / t_warm,
+                       'ms_per_case_cached_geometry': 1e3 * t_warm / max(len(df) / world, 1)}
+    df2, t2 = timed(lambda: studies.run_advdiff_step_validation(None, mesh_size_dim=args.h))
+    df2, t2w = timed(lambda: studies.run_advdiff_step_validation(None, mesh_size_dim=args.h))
+    out['advdiff_validation'] = {'solves': len(df2), 'wall_s_first': t2, 'wall_s_cached_geometry': t2w,
+                                 'solves_per_s_first': len(df2) / t2, 'solves_per_s_cached_geometry': len(df2) / t2w}
+    if rank == 0:
+        print(json.dumps(out))
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', f'sweep_bench_n{world}.json'), 'w') as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == '__main__':
+    main()
