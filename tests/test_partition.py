@@ -122,6 +122,18 @@ def _gloo_worker(rank, world, port, out):
     dist.all_reduce(d)
     yg = A @ xg
     ok = np.allclose(y, yg[lp.owned], rtol=1e-13) and abs(d.item() - yg @ yg) <= 1e-12 * (yg @ yg)
+    # sweep sharding (study drivers): every rank runs its round-robin share, all ranks receive all rows in case order
+    from sulcusfem.sweep import run_sharded
+    cases = [('g%d' % i, 0.1 * i) for i in range(7)]
+    ran = []
+
+    def run_case(c):
+        ran.append(c)
+        return {'geometry': c[0], 'value': c[1] ** 2, 'rank': rank}
+    got = run_sharded(cases, run_case, rank, world)
+    ok = ok and ran == [c for i, c in enumerate(cases) if i % world == rank]
+    ok = ok and [i for i, _ in got] == list(range(len(cases)))
+    ok = ok and all(r['geometry'] == cases[i][0] and r['rank'] == i % world for i, r in got)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
