@@ -6,6 +6,7 @@ files with the reference's exact column names -- without the plotting / menu lay
     adv_diff_analysis.py:177-300       run_advdiff_step_...  run_advdiff_step_validation  advdiff_validation_step_pe_x_mu.csv
     no_advection_analysis_A.py:1257-1347  run_mu_sweep       run_mu_sweep             mu_parameter_sweep_results.csv
     no_advection_analysis_A.py:1349-1452  run_aspect_ratio_analysis  run_aspect_ratio_analysis  aspect_ratio_analysis_results.csv
+    no_uptake_analysis.py:50-313,921-975  run_geometry_study  run_geometry_study      geometry_comparison_results.csv
 
 The reference runs every case serially; the cases are independent, so each driver deals them round-robin to the
 ranks (one process per GPU, ``sweep.run_sharded``) and gathers only the small row dictionaries -- no data-path
@@ -357,4 +358,149 @@ def run_aspect_ratio_analysis(output_dir=None, cases=None, mesh_size_dim=0.02, r
     done = run_sharded(cases, one, rank, world)
     df = _frame([row for _, row in done])
     _save(df, output_dir, "aspect_ratio_analysis_results.csv", None, rank)
+    return df
+
+
+# ====================================================================== no-uptake geometry comparison (mu = 0)
+def format_filename_value(value):
+    """plotting.py:249-253."""
+    if abs(value - round(value)) < 0.001:
+        return f"{value:.0f}"
+    return f"{value:.1f}".replace('.', 'p') if value >= 1.0 else f"{value:.3f}".replace('.', 'p')
+
+
+def _no_uptake_params(pe, mesh_size_dim, w_dim=None, h_dim=None):
+    """no_uptake_analysis.py:114-127, 945-951 (same order of assignments)."""
+    p = Parameters(mode='no-uptake', mesh_size_dim=mesh_size_dim)
+    if w_dim is not None:
+        p.sulci_w_dim, p.sulci_h_dim = w_dim, h_dim
+    else:
+        p.mu_dim = 0.0
+    p.U_ref_dim = pe * p.D_dim / p.H_dim
+    p.validate()
+    p.nondim()
+    p.D_dim = p.U_ref_dim * p.H_dim / p.Pe
+    return p
+
+
+def _vel_cols(vm, sulcus):
+    """The reference reads 'max_ux_sulcus_level' (no_uptake_analysis.py:229-232), a key its current
+    compute_velocity_metrics no longer produces (the line is called 'mouth_level' now, analysis.py:748) although the
+    checked-in CSV still carries the values; the mouth-level line is used for those two columns."""
+    vm = vm if isinstance(vm, dict) else {}
+    g = vm.get
+    return {'Max_Ux_mid_channel': g('max_ux_mid_channel'), 'Avg_Ux_mid_channel': g('avg_ux_mid_channel'),
+            'Max_Ux_sulcus_level': g('max_ux_sulcus_level', g('max_ux_mouth_level')) if sulcus else None,
+            'Avg_Ux_sulcus_level': g('avg_ux_sulcus_level', g('avg_ux_mouth_level')) if sulcus else None}
+
+
+def _common_cols(params, domain, w=None, h=None):
+    D_dim = params.U_ref_dim * params.H_dim / params.Pe
+    return {'Domain': domain, 'Mode': params.mode, 'Peclet': params.Pe, 'U_ref': getattr(params, 'U_ref', None),
+            'Sulcus Width (mm)': w, 'Sulcus Depth (mm)': h,
+            'Aspect_Ratio': (h / w) if (w and w > 0) else None, 'U_ref (Dim)': params.U_ref_dim, 'Diff Coef (Dim)': D_dim,
+            'Delta (mm)': D_dim / params.U_ref_dim}
+
+
+def extract_simulation_data(result):
+    """Sulcus row of geometry_comparison_results.csv (no_uptake_analysis.py:146-236)."""
+    params = result.get('params')
+    if not params:
+        return None
+    row = _common_cols(params, 'sulcus', getattr(params, 'sulci_w_dim', None), getattr(params, 'sulci_h_dim', None))
+    mm = result.get('mass_metrics', {})
+    if isinstance(mm, dict):
+        avg = mm.get('average_concentration', {})
+        d = isinstance(avg, dict)
+        row.update({'Total Mass': mm.get('total_mass'), 'Sulcus Mass': mm.get('sulcus_mass'),
+                    'Main Channel Mass': mm.get('rectangle_mass'), 'Avg Concentration': avg.get('total') if d else avg,
+                    'Sulcus Avg Concentration': avg.get('sulcus_region') if d else None,
+                    'Main Channel Avg Concentration': avg.get('rectangle_region') if d else None})
+    fm = result.get('flux_metrics', {})
+    extra = {}
+    if isinstance(fm, dict):
+        spf = fm.get('sulcus_specific', {}).get('physical_flux', {})
+        row['Mouth_Flux_Total'] = spf.get('sulcus_opening', {}).get('total')
+        pf = fm.get('physical_flux', {})
+        row['Inlet-Outlet Flux'] = pf.get('left', {}).get('total', 0) + pf.get('right', {}).get('total', 0)
+        extra = spf.get('sulcus_opening_extra', {})
+    if isinstance(extra, dict):
+        row.update({'Mouth E_L1': extra.get('E_L1'), 'Mouth E_avg': extra.get('E_avg'), 'Mouth Q_in': extra.get('Q_in'),
+                    'Mouth Q_out': extra.get('Q_out'), 'Mouth Net Check': extra.get('net_check'),
+                    'Mouth Length': extra.get('length')})
+    row.update(_vel_cols(result.get('vel_metrics', {}), True))
+    return row
+
+
+def extract_rectangular_data(result):
+    """Rectangle row (no_uptake_analysis.py:50-107), columns in the order of the sulcus rows."""
+    params = result.get('params')
+    if not params:
+        return None
+    mm = result.get('mass_metrics', {})
+    fm = result.get('flux_metrics', {})
+    pf = fm.get('physical_flux', {}) if isinstance(fm, dict) else {}
+    inlet = pf.get('left', {}).get('total', 0) if isinstance(pf.get('left'), dict) else 0
+    outlet = pf.get('right', {}).get('total', 0) if isinstance(pf.get('right'), dict) else 0
+    row = _common_cols(params, 'rectangle')
+    row.update({'Total Mass': mm.get('total_mass'), 'Sulcus Mass': None, 'Main Channel Mass': mm.get('total_mass', None),
+                'Avg Concentration': mm.get('average_concentration', None), 'Sulcus Avg Concentration': None,
+                'Main Channel Avg Concentration': mm.get('average_concentration', None), 'Mouth_Flux_Total': None,
+                'Inlet-Outlet Flux': inlet + outlet, 'Mouth E_L1': None, 'Mouth E_avg': None, 'Mouth Q_in': None,
+                'Mouth Q_out': None, 'Mouth Net Check': None, 'Mouth Length': None})
+    row.update(_vel_cols(result.get('vel_metrics', {}), False))
+    return row
+
+
+def add_ratio_metrics(df):
+    """no_uptake_analysis.py:262-313 on the DataFrame (sulcus rows against the rectangle baseline of the same Pe)."""
+    rect = df[df['Domain'] == 'rectangle'].groupby('Peclet').agg({'Avg Concentration': 'mean', 'Max_Ux_mid_channel': 'mean',
+                                                                  'Avg_Ux_mid_channel': 'mean'})
+    for col in ('Concentration_Ratio', 'Channel_Conc_Ratio', 'Intradomain_Enrichment', 'VR_mid_avg', 'VR_mid_max',
+                'VR_intradomain_avg', 'VR_intradomain_max'):
+        df[col] = np.nan
+    num = lambda s: df.loc[mask, s].astype(float)          # noqa: E731
+    for pe in rect.index:
+        mask = (df['Domain'] == 'sulcus') & (df['Peclet'] == pe)
+        if not mask.any():
+            continue
+        df.loc[mask, 'Concentration_Ratio'] = num('Avg Concentration') / rect.loc[pe, 'Avg Concentration']
+        df.loc[mask, 'Channel_Conc_Ratio'] = num('Main Channel Avg Concentration') / rect.loc[pe, 'Avg Concentration']
+        df.loc[mask, 'VR_mid_avg'] = num('Avg_Ux_mid_channel') / rect.loc[pe, 'Avg_Ux_mid_channel']
+        df.loc[mask, 'VR_mid_max'] = num('Max_Ux_mid_channel') / rect.loc[pe, 'Max_Ux_mid_channel']
+        df.loc[mask, 'Intradomain_Enrichment'] = num('Sulcus Avg Concentration') / num('Main Channel Avg Concentration')
+        df.loc[mask, 'VR_intradomain_avg'] = num('Avg_Ux_sulcus_level') / num('Avg_Ux_mid_channel')
+        df.loc[mask, 'VR_intradomain_max'] = num('Max_Ux_sulcus_level') / num('Max_Ux_mid_channel')
+    return df
+
+
+def run_geometry_study(output_dir=None, peclet_numbers=(0.1, 1.0, 10.0), geometries: Optional[Dict] = None,
+                       mesh_size_dim=0.02, rank=None, world=None, quiet=True):
+    """Reference ``run_geometry_study`` (no_uptake_analysis.py:921-975): mu = 0, every geometry x every Pe on the
+    sulcus plus one rectangle baseline per Pe (23 x 3 + 3 = 72 rows by default), ratio columns added.  The Stokes flow of
+    a geometry is solved once and reused by its Pe values.  Rank 0 writes ``geometry_comparison_results.csv``."""
+    rank, world = _world(rank, world)
+    peclet_numbers = list(peclet_numbers)
+    configs = geometries if geometries is not None else create_geometry_variations(Parameters(mode='no-uptake'), max_width=1.0)
+    # a geometry's Pe values stay on one rank (they share the mesh and the Stokes solution)
+    cases = [('sulcus', k, cfg) for k, cfg in configs.items()] + [('rectangle', None, None)]
+
+    def one(case):
+        kind, key, cfg = case
+        rows = []
+        for pe in peclet_numbers:
+            if kind == 'sulcus':
+                p = _no_uptake_params(pe, mesh_size_dim, cfg['sulci_w_dim'], cfg['sulci_h_dim'])
+                res = _run(quiet, mode='no-uptake', study_type="Geometry Comparison",
+                           config_name=f"{key}_Pe{format_filename_value(pe)}", domain_type='sulcus', params=p)
+                rows.append(extract_simulation_data(res))
+            else:
+                p = _no_uptake_params(pe, mesh_size_dim)
+                res = _run(quiet, mode='no-uptake', study_type='Rectangular Baselines',
+                           config_name=f'rect_Pe{format_filename_value(pe)}', domain_type='rectangular', params=p)
+                rows.append(extract_rectangular_data(res))
+        return rows
+    done = run_sharded(cases, one, rank, world)
+    df = add_ratio_metrics(_frame([r for _, rows in done for r in rows]))
+    _save(df, output_dir, "geometry_comparison_results.csv", None, rank)
     return df

@@ -12,6 +12,7 @@ FILES = {
     'advdiff_validation_step_pe_x_mu.csv': 'Advection-Diffusion/Results Data/advdiff_validation_step_pe_x_mu.csv',
     'mu_parameter_sweep_results.csv': 'No Advection - Phase A/Mu Parameter Sweep Analysis/mu_parameter_sweep_results.csv',
     'aspect_ratio_analysis_results.csv': 'No Advection - Phase A/Aspect Ratio Study Analysis/aspect_ratio_analysis_results.csv',
+    'geometry_comparison_results.csv': 'No Uptake Simulations/Geometry Comparison Analysis/geometry_comparison_results.csv',
 }
 out = {}
 for name, rel in FILES.items():
@@ -24,6 +25,8 @@ for name, rel in FILES.items():
     if name.startswith('no_adv_mu_sweep'):
         entry['geometries'] = sorted(set(r[hdr.index('geometry')] for r in rows[1:]))
         entry['mu_factors'] = sorted(set(float(r[hdr.index('mu_factor')]) for r in rows[1:]))
+    if name.startswith('geometry_comparison'):
+        entry['rows'] = [dict(zip(hdr, r)) for r in rows[1:]]
     if name.startswith('advdiff'):
         entry['cases'] = sorted(set((float(r[hdr.index('Pe')]), float(r[hdr.index('mu_factor')])) for r in rows[1:]))
         entry['rows'] = [dict(zip(hdr, r)) for r in rows[1:]]          # the reference's own results (dolfin on Gmsh meshes)

@@ -92,3 +92,26 @@ def test_advdiff_validation_against_reference_csv_at_reference_resolution():
             assert abs(float(row['CR']) - float(want['CR'])) < 5e-3
     for r in report:
         print("REFCSV", *r)
+
+
+def test_no_uptake_geometry_study_schema_and_physics(tmp_path):
+    """run_geometry_study (no_uptake_analysis.py:921-975): schema of geometry_comparison_results.csv, mu = 0 physics
+    (no flux leaves through the walls: inlet + outlet flux ~ 0; uniform c = 1 would be the Pe -> 0 limit)."""
+    from sulcusfem import studies
+    from sulcusfem.parameters import Parameters, create_geometry_variations
+    geos = create_geometry_variations(Parameters(mode='no-uptake'), max_width=1.0)
+    pick = {k: geos[k] for k in ('largest', 'square_small') if k in geos} or {k: geos[k] for k in list(geos)[:2]}
+    df = studies.run_geometry_study(str(tmp_path), peclet_numbers=(1.0, 10.0), geometries=pick, mesh_size_dim=H)
+    assert list(df.columns) == GOLD['geometry_comparison_results.csv']['columns']
+    assert list(df['Domain']) == ['sulcus'] * (2 * len(pick)) + ['rectangle'] * 2
+    assert os.path.exists(tmp_path / 'geometry_comparison_results.csv')
+    s = df[df['Domain'] == 'sulcus']
+    assert np.all(np.abs(s['Inlet-Outlet Flux'].astype(float)) < 5e-2)        # = minus the (weakly zero) wall flux: O(h^2)
+    assert np.all(np.abs(s['Mouth Net Check'].astype(float) - s['Mouth_Flux_Total'].astype(float)) < 1e-10)
+    assert np.all(s['Mouth Q_in'].astype(float) > 0) and np.all(s['Mouth Q_out'].astype(float) > 0)
+    assert np.allclose(s['Intradomain_Enrichment'].astype(float),
+                       s['Sulcus Avg Concentration'].astype(float) / s['Main Channel Avg Concentration'].astype(float))
+    r = df[df['Domain'] == 'rectangle']
+    # Poiseuille: max |u_x| on the mid-channel line is 1 (reference CSV: 1.0000000000002331)
+    assert np.all(np.abs(r['Max_Ux_mid_channel'].astype(float) - 1.0) < 1e-9)
+    assert np.all(np.isfinite(s['VR_mid_max'].astype(float)))

@@ -315,6 +315,9 @@ def test_study_case_lists_match_reference_csvs():
     geos = create_geometry_variations(Parameters(mode='no-adv'), max_width=1.0)
     assert sorted(geos) == pb['geometries'] and studies.MU_FACTORS_PHASE_B == pb['mu_factors']
     assert len(geos) * len(studies.MU_FACTORS_PHASE_B) == pb['n_rows']
+    gc = g['geometry_comparison_results.csv']
+    assert len(create_geometry_variations(Parameters(mode='no-uptake'), max_width=1.0)) * 3 + 3 == gc['n_rows']
+    assert studies.format_filename_value(0.1) == '0p100' and studies.format_filename_value(10.0) == '10'
     ad = g['advdiff_validation_step_pe_x_mu.csv']
     assert sorted([float(p), float(m)] for p in studies.PE_VALUES for m in studies.MU_FACTORS_ADV) == ad['cases']
 
