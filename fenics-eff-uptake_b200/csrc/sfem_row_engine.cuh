@@ -1,6 +1,7 @@
-// Software-pipelined CSR row engine shared by the FP64 SpMV family (sfem_spmv.cu) and the FP32-storage
-// multigrid preconditioner (sfem_mg32.cu).  TV = storage type of the matrix values, TX = storage type of
-// the vectors; all arithmetic is FP64.
+// Software-pipelined CSR row engine of the FP64 SpMV family (sfem_spmv.cu); its accumulator / gather helpers are
+// also used by the sliced-ELL engine (sfem_spmv_sell.cu).  TV = storage type of the matrix values, TX = storage type
+// of the vectors (both double in the shipped kernels; an FP32-storage preconditioner was measured and dropped, see
+// profiles/r01_spmv_microbench.md); all arithmetic is FP64.
 #pragma once
 #include "sfem_common.cuh"
 

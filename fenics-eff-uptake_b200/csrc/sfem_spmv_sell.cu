@@ -46,7 +46,7 @@ namespace {
 constexpr int kSellThreads = 256;
 constexpr int kSellBlocksPerSm = 4;
 
-// The warp ranges are balanced by steps on the host: parts[k] = first slice of fine part k (kSellFineParts per
+// The warp ranges are balanced by steps on the host: parts[k] = first slice of fine part k (kSellFine per
 // SM-resident warp slot), and a kernel whose occupancy is MINB blocks per SM merges 12 / MINB fine parts per warp.
 constexpr int kSellFine = 12;      // fine parts per (SM x warp slot of a 256-thread block); divisible by 2, 3, 4, 6
 
