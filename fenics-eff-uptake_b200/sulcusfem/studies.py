@@ -504,3 +504,59 @@ def run_geometry_study(output_dir=None, peclet_numbers=(0.1, 1.0, 10.0), geometr
     df = add_ratio_metrics(_frame([r for _, rows in done for r in rows]))
     _save(df, output_dir, "geometry_comparison_results.csv", None, rank)
     return df
+
+
+# ---- concentration line profiles of selected geometries (no_uptake_analysis.py:315-436, 977-1015)
+def collect_profile_rows(result, geometry_key=None):
+    """One tidy row per sample of result['mass_metrics']['profiles_full'] (horizontal lines, like the reference:
+    no_uptake_analysis.py:315-359); columns = those of the reference's profiles_samples_<geometry>.csv."""
+    rows = []
+    if not result:
+        return rows
+    params = result.get('params', {})
+    mm = result.get('mass_metrics') or {}
+    full, meta = mm.get('profiles_full') or {}, mm.get('profiles_meta') or {}
+    domain = result.get('domain_type', 'unknown')
+    config = result.get('config_name', result.get('geometry'))
+    pe = getattr(params, 'Pe', None)
+    x_rng, y_rng, n_points = meta.get('x_range'), meta.get('y_range'), meta.get('n_points')
+    for name, payload in (full.get('horizontal') or {}).items():
+        y = float(payload['y'])
+        for i, (xx, cc) in enumerate(zip(np.asarray(payload['x']), np.asarray(payload['c']))):
+            rows.append({'Domain': domain, 'Geometry': geometry_key or result.get('geometry'), 'Config': config, 'Peclet': pe,
+                         'LineType': 'horizontal', 'LineName': name, 'Index': i, 'x': float(xx), 'y': y, 'c': float(cc),
+                         'n_points': n_points, 'x_min': None if x_rng is None else float(x_rng[0]),
+                         'x_max': None if x_rng is None else float(x_rng[1]),
+                         'y_min': None if y_rng is None else float(y_rng[0]),
+                         'y_max': None if y_rng is None else float(y_rng[1])})
+    return rows
+
+
+def run_profile_export(output_dir=None, geometry_keys=('largest', 'square_small'), peclet_numbers=(0.1, 1.0, 10.0),
+                       mesh_size_dim=0.02, n_points=400, quiet=True):
+    """The selective profile step of ``run_geometry_study`` (no_uptake_analysis.py:977-1015): for the chosen
+    geometries and every Pe, run the no-uptake case, ``compute_conc_profiles`` (all eight lines in one device launch)
+    and write ``profiles_samples_<geometry>.csv`` / ``profiles_<geometry>.csv``.  Returns {geometry: (samples
+    DataFrame, statistics DataFrame)}."""
+    from .analysis import compute_conc_profiles
+    configs = create_geometry_variations(Parameters(mode='no-uptake'), max_width=1.0)
+    out = {}
+    for gkey in geometry_keys:
+        cfg = configs[gkey]
+        rows, stats = [], []
+        for pe in peclet_numbers:
+            p = _no_uptake_params(pe, mesh_size_dim, cfg['sulci_w_dim'], cfg['sulci_h_dim'])
+            res = _run(quiet, mode='no-uptake', study_type="Geometry Comparison",
+                       config_name=f"{gkey}_Pe{format_filename_value(pe)}", domain_type='sulcus', params=p)
+            res.update({'geometry': gkey, 'peclet': pe, 'domain_type': 'sulcus'})
+            compute_conc_profiles(res, n_points=n_points)
+            rows.extend(collect_profile_rows(res, geometry_key=gkey))
+            for name, st in ((res['mass_metrics'].get('profiles') or {}).get('horizontal') or {}).items():
+                stats.append({'Geometry': gkey, 'Peclet': pe, 'line_type': 'horizontal', 'name': name, 'x': None,
+                              'y': st.get('y'), 'min_c': st.get('min_c'), 'max_c': st.get('max_c'),
+                              'avg_c': st.get('avg_c'), 'n_samples': st.get('n_samples')})
+        df, dfs = _frame(rows), _frame(stats)
+        _save(df, output_dir, f"profiles_samples_{gkey}.csv")
+        _save(dfs, output_dir, f"profiles_{gkey}.csv")
+        out[gkey] = (df, dfs)
+    return out

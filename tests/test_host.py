@@ -402,3 +402,23 @@ def test_direct_divergence_block_maps_match_mixed_space_extraction():
         assert len(slot) == p.nnz and np.array_equal(c_[slot], p.cols)
         assert np.array_equal(np.bincount(r_[slot], minlength=p.nrows), np.diff(p.rowptr))
         assert np.array_equal(A[slot], got)            # bit for bit
+
+
+def test_profile_rows_schema_matches_reference_csv():
+    """collect_profile_rows (no_uptake_analysis.py:315-359): the tidy rows carry the columns of the reference's
+    profiles_samples_<geometry>.csv, in order."""
+    import json
+    import os
+    from sulcusfem import studies
+
+    class P:
+        Pe = 1.0
+    res = {'params': P(), 'domain_type': 'sulcus', 'geometry': 'largest',
+           'mass_metrics': {'profiles_full': {'horizontal': {'mid_channel': {'y': 0.5, 'x': [0.0, 5.0, 10.0], 'c': [1.0, 0.5, 0.0]}},
+                                              'vertical': {'x_mid': {'x': 5.0, 'y': [0.0, 1.0], 'c': [0.4, 0.6]}}},
+                            'profiles_meta': {'n_points': 3, 'x_range': (0.0, 10.0), 'y_range': None}}}
+    rows = studies.collect_profile_rows(res, geometry_key='largest')
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'profile_samples.json')))
+    assert [list(r.keys()) for r in rows] == [gold['columns']] * 3          # horizontal lines only, like the reference
+    assert [r['Index'] for r in rows] == [0, 1, 2] and rows[1]['c'] == 0.5 and rows[0]['y_min'] is None
+    assert studies.collect_profile_rows(None) == []
