@@ -25,11 +25,9 @@ for name, rel in FILES.items():
     if name.startswith('no_adv_mu_sweep'):
         entry['geometries'] = sorted(set(r[hdr.index('geometry')] for r in rows[1:]))
         entry['mu_factors'] = sorted(set(float(r[hdr.index('mu_factor')]) for r in rows[1:]))
-    if name.startswith('geometry_comparison'):
-        entry['rows'] = [dict(zip(hdr, r)) for r in rows[1:]]
+    entry['rows'] = [dict(zip(hdr, r)) for r in rows[1:]]          # the reference's own results (dolfin on Gmsh meshes)
     if name.startswith('advdiff'):
         entry['cases'] = sorted(set((float(r[hdr.index('Pe')]), float(r[hdr.index('mu_factor')])) for r in rows[1:]))
-        entry['rows'] = [dict(zip(hdr, r)) for r in rows[1:]]          # the reference's own results (dolfin on Gmsh meshes)
     out[name] = entry
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'study_columns.json'), 'w') as f:
     json.dump(out, f, indent=1)
