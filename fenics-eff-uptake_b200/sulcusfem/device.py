@@ -48,9 +48,23 @@ class Context:
         return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
 
     def up(self, arr, dtype):
+        """Host array -> device tensor.  Arrays that live in pinned memory (the fields :meth:`down` returned, i.e. the
+        ``Function.values`` a previous solve produced) are copied asynchronously at full PCIe rate on the current
+        stream; anything else goes through the blocking pageable path."""
         torch = _torch()
         a = np.ascontiguousarray(arr, dtype=dtype)
-        return torch.from_numpy(a).to(self.device, non_blocking=False)
+        t = torch.from_numpy(a)
+        if a is arr and t.numel() >= (1 << 15) and t.is_pinned():
+            return t.to(self.device, non_blocking=True)          # stream-ordered; `arr` is kept alive by its owner
+        return t.to(self.device, non_blocking=False)
+
+    def down(self, t):
+        """Device tensor -> numpy array backed by PINNED host memory (torch's caching host allocator), so the
+        download runs at full PCIe rate and a later :meth:`up` of the same array does too."""
+        torch = _torch()
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=False)
+        return h.numpy()
 
     def zeros(self, n, dtype=None):
         torch = _torch()

@@ -137,7 +137,7 @@ def _post(prob, x, fix_nonfinite):
 
 
 def _to_function(C, prob, x):
-    f = Function(C, x.cpu().numpy())
+    f = Function(C, prob.ctx.down(x))
     f._dev = (x.clone(),)
     f.solver_info = dict(prob.last_info)
     return f
@@ -233,9 +233,9 @@ def stokes_solver(mesh_results, W, L_domain, H, mesh_type="sulcus"):
         if not np.isfinite(prob.last_info['relres']) or prob.last_info['relres'] > 1e-9:
             raise RuntimeError(f"MINRES stalled: {prob.last_info}")
         n2 = prob.n2
-        u = Function(VectorFunctionSpace(mesh, 'P', 2), prob.x[:2 * n2].cpu().numpy())
+        u = Function(VectorFunctionSpace(mesh, 'P', 2), prob.ctx.down(prob.x[:2 * n2]))
         u._dev = (ux.clone(), uy.clone())
-        pf = Function(FunctionSpace(mesh, 'P', 1), p.cpu().numpy())
+        pf = Function(FunctionSpace(mesh, 'P', 1), prob.ctx.down(p))
         u.solver_info = pf.solver_info = dict(prob.last_info)
         print(f"✓ Stokes solver completed using outlet point constraint for {mesh_type} mesh")
         return u, pf
