@@ -109,6 +109,17 @@ class MeshGenerator:
         return None
 
 
+def generate_mesh_job(kwargs, with_hierarchy=True):
+    """Worker-process entry of ``simulation.prefetch_meshes``: mesh + markers (+ multigrid hierarchy) of one geometry.
+    Pure host work (numpy / Qhull); nothing here touches CUDA or torch, so it is safe in spawned processes."""
+    out = MeshGenerator(**kwargs).generate_mesh()
+    hier = None
+    if with_hierarchy and out:
+        from .hierarchy import build_hierarchy
+        hier = build_hierarchy(out['mesh'])
+    return out, hier
+
+
 class Measure:
     """Descriptor of an integration measure: kind ('ds' | 'dS' | 'dx') + the marker set it reads."""
 

@@ -45,11 +45,68 @@ def _export(paraview_dir, name, f):
         File(os.path.join(paraview_dir, name + ".pvd")) << f
 
 
-def _simulation_generate_mesh(params, domain_type, mesh_dir=None, paraview_dir=None):
-    print("\n Generating mesh...")
+def _mesh_key(params, domain_type):
     mp = params.get_mesh_generator_params()
     key = (domain_type, mp['width'], mp['height'], mp['sulcus_depth'], mp['sulcus_width'], mp['mesh_size'],
            mp['refinement_factor'], MESH_OPTIONS['mesher'], MESH_OPTIONS['uniform_refinements'])
+    return key, mp
+
+
+def prefetch_meshes(jobs, workers=None, with_hierarchy=True):
+    """Build the meshes (Delaunay + smoothing), markers and multigrid hierarchies of many geometries in parallel
+    worker processes and put them into the per-geometry cache ``run_simulation`` reads.
+
+    ``jobs``: iterable of ``(params, domain_type)``.  The host work per geometry (seconds at h = 0.02) dwarfs the
+    milliseconds a case costs on the GPU once its geometry is cached, and it is embarrassingly parallel over
+    geometries, so a study hands all its geometries here first.  Returns the number of meshes built.  The results
+    are the ones the in-process generator produces (same code, deterministic), so a sweep gives bit-identical fields
+    with and without prefetching."""
+    import os
+    todo = {}
+    for params, domain_type in jobs:
+        key, mp = _mesh_key(params, domain_type)
+        if key not in _MESH_CACHE and key not in todo:
+            mp['output_dir'] = None
+            mp['domain_type'] = domain_type
+            todo[key] = dict(mp, **MESH_OPTIONS)
+    if not todo:
+        return 0
+    if workers is None:
+        world = int(os.environ.get('WORLD_SIZE', '1') or 1)
+        workers = max(1, min(len(todo), (os.cpu_count() or 1) // max(world, 1), 16))
+    from .mesh import generate_mesh_job
+    if workers <= 1 or len(todo) == 1:
+        results = {k: generate_mesh_job(kw, with_hierarchy) for k, kw in todo.items()}
+    else:
+        import multiprocessing as mp_
+        import warnings
+        from concurrent.futures import ProcessPoolExecutor
+        results = {}
+        try:
+            # spawn: the parent may hold a CUDA context, which must not be forked
+            with ProcessPoolExecutor(max_workers=workers, mp_context=mp_.get_context('spawn')) as ex:
+                futs = {k: ex.submit(generate_mesh_job, kw, with_hierarchy) for k, kw in todo.items()}
+                for k, f in futs.items():
+                    results[k] = f.result()
+        except Exception as e:          # e.g. no importable __main__ (python -c / stdin): spawned workers cannot start
+            warnings.warn(f"parallel mesh prefetch unavailable ({type(e).__name__}: {e}); meshing in-process")
+            for k, kw in todo.items():
+                if k not in results:
+                    results[k] = generate_mesh_job(kw, with_hierarchy)
+    for k, (mesh_results, hier) in results.items():
+        _MESH_CACHE[k] = mesh_results
+        if hier is not None and mesh_results:
+            cache = getattr(mesh_results['mesh'], '_sfem_cache', None)
+            if cache is None:
+                cache = {}
+                mesh_results['mesh']._sfem_cache = cache
+            cache.setdefault('hierarchy', hier)
+    return len(results)
+
+
+def _simulation_generate_mesh(params, domain_type, mesh_dir=None, paraview_dir=None):
+    print("\n Generating mesh...")
+    key, mp = _mesh_key(params, domain_type)
     if key not in _MESH_CACHE:
         mp['output_dir'] = mesh_dir
         mp['domain_type'] = domain_type

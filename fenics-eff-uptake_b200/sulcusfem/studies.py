@@ -51,6 +51,16 @@ def _run(quiet, **kw):
         return run_simulation(**kw)
 
 
+def _prefetch(jobs, rank=0, world=1, enable=True):
+    """Hand the (params, domain_type) pairs of this rank's cases to ``simulation.prefetch_meshes`` (parallel host
+    meshing); ``jobs`` is a list of lists, one per case, in case order."""
+    if not enable:
+        return 0
+    from .simulation import prefetch_meshes
+    mine = [j for i, case_jobs in enumerate(jobs) if i % world == rank for j in case_jobs]
+    return prefetch_meshes(mine)
+
+
 def _frame(rows: List[dict], sort: Optional[Sequence[str]] = None):
     import pandas as pd
     df = pd.DataFrame(rows)
@@ -126,7 +136,7 @@ def phase_b_case(case, mesh_size_dim=0.02, quiet=True):
 
 
 def run_no_adv_mu_sweep(output_dir=None, mu_factors: Iterable[float] = None, geometries: Optional[Dict] = None,
-                        mesh_size_dim=0.02, rank=None, world=None, quiet=True):
+                        mesh_size_dim=0.02, rank=None, world=None, quiet=True, prefetch=True):
     """Reference ``run_no_adv_mu_sweep`` (23 geometries x 3 mu x {sulcus, rectangle} = 138 solves by default).
     Returns the DataFrame with the reference's columns; rank 0 writes ``no_adv_mu_sweep_results.csv``."""
     rank, world = _world(rank, world)
@@ -134,6 +144,9 @@ def run_no_adv_mu_sweep(output_dir=None, mu_factors: Iterable[float] = None, geo
     configs = geometries if geometries is not None else create_geometry_variations(Parameters(mode='no-adv'), max_width=1.0)
     cases = [(mu, g, cfg) for mu in mu_factors for g, cfg in configs.items()]
     t0 = time.time()
+    _prefetch([[(_params_no_adv(mu, cfg['sulci_w_dim'], cfg['sulci_h_dim'], mesh_size_dim), 'sulcus'),
+                (_params_no_adv(mu, cfg['sulci_w_dim'], cfg['sulci_h_dim'], mesh_size_dim), 'rectangular')]
+               for mu, _, cfg in cases], rank, world, prefetch)
     done = run_sharded(cases, lambda c: phase_b_case(c, mesh_size_dim, quiet), rank, world)
     df = _frame([row for _, row in done], ['mu_factor', 'geometry'])
     p0 = Parameters(mode='no-adv')
@@ -340,10 +353,20 @@ def aspect_ratio_cases(max_width=1.0):
     return out
 
 
-def run_aspect_ratio_analysis(output_dir=None, cases=None, mesh_size_dim=0.02, rank=None, world=None, quiet=True):
+def run_aspect_ratio_analysis(output_dir=None, cases=None, mesh_size_dim=0.02, rank=None, world=None, quiet=True,
+                              prefetch=True):
     """Reference ``run_aspect_ratio_analysis``.  Rank 0 writes ``aspect_ratio_analysis_results.csv``."""
     rank, world = _world(rank, world)
     cases = aspect_ratio_cases() if cases is None else list(cases)
+
+    def params_of(case):
+        _, _, h, w = case
+        p = Parameters(mode='no-adv', mesh_size_dim=mesh_size_dim)
+        p.sulci_w_dim, p.sulci_h_dim = w, h
+        p.validate()
+        p.nondim()
+        return p
+    _prefetch([[(params_of(c), 'sulcus')] for c in cases], rank, world, prefetch)
 
     def one(case):
         name, ar, h, w = case
@@ -475,7 +498,7 @@ def add_ratio_metrics(df):
 
 
 def run_geometry_study(output_dir=None, peclet_numbers=(0.1, 1.0, 10.0), geometries: Optional[Dict] = None,
-                       mesh_size_dim=0.02, rank=None, world=None, quiet=True):
+                       mesh_size_dim=0.02, rank=None, world=None, quiet=True, prefetch=True):
     """Reference ``run_geometry_study`` (no_uptake_analysis.py:921-975): mu = 0, every geometry x every Pe on the
     sulcus plus one rectangle baseline per Pe (23 x 3 + 3 = 72 rows by default), ratio columns added.  The Stokes flow of
     a geometry is solved once and reused by its Pe values.  Rank 0 writes ``geometry_comparison_results.csv``."""
@@ -484,6 +507,9 @@ def run_geometry_study(output_dir=None, peclet_numbers=(0.1, 1.0, 10.0), geometr
     configs = geometries if geometries is not None else create_geometry_variations(Parameters(mode='no-uptake'), max_width=1.0)
     # a geometry's Pe values stay on one rank (they share the mesh and the Stokes solution)
     cases = [('sulcus', k, cfg) for k, cfg in configs.items()] + [('rectangle', None, None)]
+    pe0 = peclet_numbers[0]
+    _prefetch([[(_no_uptake_params(pe0, mesh_size_dim, cfg['sulci_w_dim'], cfg['sulci_h_dim']), 'sulcus')] if kind == 'sulcus'
+               else [(_no_uptake_params(pe0, mesh_size_dim), 'rectangular')] for kind, _, cfg in cases], rank, world, prefetch)
 
     def one(case):
         kind, key, cfg = case

@@ -422,3 +422,40 @@ def test_profile_rows_schema_matches_reference_csv():
     assert [list(r.keys()) for r in rows] == [gold['columns']] * 3          # horizontal lines only, like the reference
     assert [r['Index'] for r in rows] == [0, 1, 2] and rows[1]['c'] == 0.5 and rows[0]['y_min'] is None
     assert studies.collect_profile_rows(None) == []
+
+
+def test_prefetch_meshes_parallel_matches_in_process_generation():
+    """simulation.prefetch_meshes: geometries meshed in spawned worker processes land in the per-geometry cache with
+    their multigrid hierarchy attached, bit-identical to in-process generation; cached geometries are not rebuilt."""
+    from sulcusfem import simulation
+    from sulcusfem.parameters import Parameters
+    from sulcusfem.mesh import MeshGenerator
+
+    def params(w, h):
+        p = Parameters(mode='no-adv', mesh_size_dim=0.1)
+        p.sulci_w_dim, p.sulci_h_dim = w, h
+        p.validate()
+        p.nondim()
+        return p
+    saved = dict(simulation._MESH_CACHE)
+    simulation._MESH_CACHE.clear()
+    try:
+        jobs = [(params(0.5, 1.0), 'sulcus'), (params(0.25, 0.25), 'sulcus'), (params(0.5, 1.0), 'rectangular'),
+                (params(0.5, 1.0), 'sulcus')]                                    # one duplicate
+        assert simulation.prefetch_meshes(jobs, workers=2) == 3
+        assert simulation.prefetch_meshes(jobs, workers=2) == 0                 # all cached now
+        for p, dom in jobs[:3]:
+            key, mp = simulation._mesh_key(p, dom)
+            got = simulation._MESH_CACHE[key]
+            mp['output_dir'], mp['domain_type'] = None, dom
+            want = MeshGenerator(**mp, **simulation.MESH_OPTIONS).generate_mesh()
+            assert np.array_equal(got['mesh'].coords, want['mesh'].coords) and np.array_equal(got['mesh'].cells, want['mesh'].cells)
+            assert np.array_equal(got['bc_markers'].values, want['bc_markers'].values)
+            hier = got['mesh']._sfem_cache['hierarchy']
+            assert hier.meshes[0] is got['mesh']                                 # identity survives the pickle round trip
+            ref = hy.build_hierarchy(want['mesh'])
+            assert [m.num_vertices for m in hier.meshes] == [m.num_vertices for m in ref.meshes]
+            assert all(np.array_equal(a.vals, b.vals) for a, b in zip(hier.transfers, ref.transfers))
+    finally:
+        simulation._MESH_CACHE.clear()
+        simulation._MESH_CACHE.update(saved)
