@@ -159,3 +159,45 @@ def test_sulcus_config1_against_reference_csv(golden):
     # internal identities of analysis.py:283-296
     seg = fl['sulcus_specific']['physical_flux']
     assert abs(seg['y0_flux']['total'] - seg['y0_combined']['total']) < 1e-10
+
+
+@pytest.mark.timeout(600)
+def test_oracle_against_reference_csvs_at_reference_resolution():
+    """The CPU oracle on this repo's h = 0.02 meshes against the reference's own numbers (dolfin on Gmsh meshes of the
+    same h; rows of the checked-in Phase A / Phase B CSVs in tests/golden/study_columns.json).  The no-advection
+    integral quantities are mesh-insensitive, so the agreement is far tighter than on the coarse meshes used above:
+    it pins the oracle -- and, through the GPU parity tests, the CUDA path -- to real reference output."""
+    import json
+    import os
+    from sulcusfem.unstructured import mesh_domain
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'study_columns.json')))
+    pb = {(r['geometry'], float(r['mu_factor'])): r for r in gold['no_adv_mu_sweep_results.csv']['rows']}
+    ar = {r['Config']: r for r in gold['aspect_ratio_analysis_results.csv']['rows']}
+    # sulcus 0.5 x 1.0 mm ("reference" geometry), mu = 1 and 0.1
+    m = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.02, 'sulcus')
+    mk = hm.build_markers(m, 10.0, 1.0, 4.75, 5.25, 'sulcus')
+    om = co.Mesh(m.coords, m.cells)
+    omk = {k: v.values for k, v in mk.items()}
+    for mu in (1.0, 0.1):
+        c, _, _ = co.solve_concentration(om, omk['bc_markers'], 1.0, mu=mu)
+        mm = co.mass_metrics(om, c, 'sulcus', omk['domain_markers'])
+        want = float(pb[('reference', mu)]['avg_conc_sulc'])
+        assert abs(mm['average_concentration']['total'] - want) / want < 1e-5, (mu, mm['average_concentration']['total'], want)
+        if mu == 1.0:
+            row = ar['h_equals_2w_h1.0']
+            assert abs(mm['total_mass'] - float(row['Total_Mass'])) / float(row['Total_Mass']) < 1e-5
+            fl = co.flux_metrics(om, omk, 'sulcus', 1.0, c, mu=mu)
+            me = co.mu_eff_metrics(fl, 10.0, 1.0, 0.5, mu)
+            assert me['mu_eff_arc'] == float(row['Mu_Eff_Analytical']) and me['mu_eff_enh'] == float(row['Mu_Eff_Enhanced'])
+            assert abs(me['mu_eff_sim'] - float(row['Mu_Eff_Simulation'])) / float(row['Mu_Eff_Simulation']) < 1e-2
+            assert abs(fl['sulcus_specific']['physical_flux']['y0_flux']['total'] - float(pb[('reference', mu)]['flux_sulc_y0'])) \
+                / float(pb[('reference', mu)]['flux_sulc_y0']) < 1e-2
+    # rectangle
+    mr = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.02, 'rectangular')
+    mkr = hm.build_markers(mr, 10.0, 1.0, 4.75, 5.25, 'rectangular')
+    omr = co.Mesh(mr.coords, mr.cells)
+    for mu in (1.0, 0.1):
+        c, _, _ = co.solve_concentration(omr, mkr['bc_markers'].values, 1.0, mu=mu)
+        avg = co.mass_metrics(omr, c, 'rectangular')['average_concentration']
+        want = float(pb[('reference', mu)]['avg_conc_rect'])
+        assert abs(avg - want) / want < 2e-8, (mu, avg, want)
