@@ -190,30 +190,22 @@ class ScalarLevel:
         self.ctx, self.mesh, self.degree = ctx, mesh, degree
         nc = mesh.num_cells
         self.nc = nc
-        if degree == 2:
-            cd = dm.p2_cell_dofs(mesh)
-            self.n = dm.p2_num_dofs(mesh)
-        else:
-            cd = dm.p1_cell_dofs(mesh)
-            self.n = mesh.num_vertices
+        self.n, cd, f, fd, self.pattern = dm.scalar_level_plan(mesh, bc_markers, degree, robin_id)
         self.ndof_cell = cd.shape[1]
-        fam = [(cd, cd)]
+        nfam = 1
         self.nf = 0
         if robin_id is not None:
-            f, _, _ = dm.boundary_facets(mesh, bc_markers, robin_id)
-            fd = dm.p2_facet_dofs(mesh, f) if degree == 2 else mesh.edges[f].astype(np.int32)
-            fam.append((fd, fd))
+            nfam = 2
             self.nf = len(f)
             self.fgeo = ctx.up(facet_geometry(mesh, f), np.float64) if self.nf else None
             self.fdofs = ctx.up(np.ascontiguousarray(fd.T), np.int32) if self.nf else None
             self.robin_facets = f
-        self.pattern = dm.build_pattern(self.n, self.n, fam)
         pat = self.pattern
         self.A = DeviceCsr(ctx, self.n, self.n, pat.rowptr, pat.cols)
         self.contrib_ptr = ctx.up(pat.contrib_ptr, np.int32)
         self.contrib_code = ctx.up(pat.contrib_code, np.int32)
         self.E = ctx.zeros(max(pat.buffer_len, 1))
-        self.facet_base = pat.family_base[1] if len(fam) > 1 else pat.buffer_len
+        self.facet_base = pat.family_base[1] if nfam > 1 else pat.buffer_len
         self.geo = ctx.up(cell_geometry(mesh), np.float64)
         self.celldofs = ctx.up(np.ascontiguousarray(cd.T), np.int32)
         # Dirichlet data (later ids overwrite earlier ones on shared dofs, like a list of dolfin bcs)
@@ -449,13 +441,7 @@ class StokesProblem:
         # ---- divergence blocks assembled directly (host plan, once): B (nv x 2 n2) and B^T (2 n2 x nv) with the
         # velocity columns / rows in interleaved numbering, both gathered from ONE element buffer EB [nc][3][12]
         # (sfem_elem_th_div: rows = the cell's pressure dofs, columns = [u_x x6 | u_y x6])
-        c2 = dm.p2_cell_dofs(mesh).astype(np.int64)
-        il = np.concatenate([2 * c2, 2 * c2 + 1], axis=1)                       # [nc, 12] interleaved velocity dofs
-        c1v = dm.p1_cell_dofs(mesh).astype(np.int64)                            # [nc, 3]
-        pb = dm.build_pattern(nv, 2 * n2, [(c1v, il)])                          # codes: cell*36 + k*12 + m
-        pbt = dm.build_pattern(2 * n2, nv, [(il, c1v)])                         # codes: cell*36 + m*3 + k  -> remap
-        loc = pbt.contrib_code.astype(np.int64) % 36
-        bt_code = (pbt.contrib_code.astype(np.int64) - loc) + (loc % 3) * 12 + loc // 3
+        pb, pbt, bt_code, mp = dm.stokes_block_plans(mesh)
         self.B = DeviceCsr(ctx, nv, 2 * n2, pb.rowptr, pb.cols)
         self.BT = DeviceCsr(ctx, 2 * n2, nv, pbt.rowptr, pbt.cols)
         self._b_map = (ctx.up(pb.contrib_ptr, np.int32), ctx.up(pb.contrib_code, np.int32))
@@ -464,8 +450,6 @@ class StokesProblem:
         self.g_il = ctx.zeros(self.n)           # Dirichlet values in solver layout [u interleaved | p = 0]
         self.flag_il = None                     # uint8 [2 n2]: interleaved velocity Dirichlet flags
         # pressure mass matrix (P1)
-        c1 = dm.p1_cell_dofs(mesh)
-        mp = dm.build_pattern(nv, nv, [(c1, c1)])
         self.Mp = DeviceCsr(ctx, nv, nv, mp.rowptr, mp.cols)
         self._mp = (ctx.up(mp.contrib_ptr, np.int32), ctx.up(mp.contrib_code, np.int32), ctx.zeros(mp.buffer_len))
         # coarse pressure correction of the Schur-complement preconditioner (lubrication operator)

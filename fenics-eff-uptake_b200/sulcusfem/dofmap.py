@@ -136,6 +136,57 @@ def build_pattern(nrows: int, ncols: int,
     return CsrPattern(nrows, ncols, rowptr, c, contrib_ptr, contrib_code, bases, base)
 
 
+def memo_pattern(mesh: HostMesh, key, nrows: int, ncols: int, families) -> CsrPattern:
+    """``build_pattern`` memoised on the mesh object (``mesh._pattern_cache``).  Patterns are pure functions of the mesh
+    and the family definition named by ``key``; the cache travels with the mesh when it is pickled, which is how the
+    worker processes of ``simulation.prefetch_meshes`` hand finished patterns to the solving process."""
+    cache = mesh.__dict__.setdefault('_pattern_cache', {})
+    pat = cache.get(key)
+    if pat is None or pat.nrows != nrows or pat.ncols != ncols:
+        pat = build_pattern(nrows, ncols, families)
+        cache[key] = pat
+    return pat
+
+
+def scalar_level_plan(mesh: HostMesh, bc_markers: np.ndarray, degree: int, robin_id: Optional[int]):
+    """Host plan of one scalar Lagrange level (device.ScalarLevel): cell dofs, Robin facets and their dofs, and the
+    CSR pattern + gather map (memoised).  Returns ``(n, cd, facets, facet_dofs, pattern)``; facets / facet_dofs are
+    None without a Robin boundary."""
+    if degree == 2:
+        cd, n = p2_cell_dofs(mesh), p2_num_dofs(mesh)
+    else:
+        cd, n = p1_cell_dofs(mesh), int(mesh.num_vertices)
+    fam = [(cd, cd)]
+    f = fd = None
+    key = ('scalar', int(degree), None)
+    if robin_id is not None:
+        f, _, _ = boundary_facets(mesh, bc_markers, robin_id)
+        fd = p2_facet_dofs(mesh, f) if degree == 2 else mesh.edges[f].astype(np.int32)
+        fam.append((fd, fd))
+        import hashlib                       # (not hash(): that is salted per process, and the cache crosses processes)
+        digest = hashlib.blake2b(np.ascontiguousarray(f).tobytes(), digest_size=8).hexdigest()
+        key = ('scalar', int(degree), (int(robin_id), len(f), digest))
+    return n, cd, f, fd, memo_pattern(mesh, key, n, n, fam)
+
+
+def stokes_block_plans(mesh: HostMesh):
+    """Host plans of the directly assembled Stokes blocks (device.StokesProblem): patterns + gather maps of
+    B (nv x 2 n2) and B^T (2 n2 x nv), velocity in interleaved numbering, both reading ONE element buffer
+    EB [nc][3][12] (rows = the cell's pressure dofs, columns = [u_x x6 | u_y x6]), and of the P1 pressure mass matrix.
+    Returns ``(pb, pbt, bt_code, pmass)``; ``bt_code`` = the gather codes of B^T re-addressed to B's buffer layout."""
+    n2, nv = p2_num_dofs(mesh), int(mesh.num_vertices)
+    c2 = p2_cell_dofs(mesh).astype(np.int64)
+    il = np.concatenate([2 * c2, 2 * c2 + 1], axis=1)                       # [nc, 12] interleaved velocity dofs
+    c1v = p1_cell_dofs(mesh).astype(np.int64)                               # [nc, 3]
+    pb = memo_pattern(mesh, ('stokes_B',), nv, 2 * n2, [(c1v, il)])         # codes: cell*36 + k*12 + m
+    pbt = memo_pattern(mesh, ('stokes_BT',), 2 * n2, nv, [(il, c1v)])       # codes: cell*36 + m*3 + k  -> remap
+    loc = pbt.contrib_code.astype(np.int64) % 36
+    bt_code = ((pbt.contrib_code.astype(np.int64) - loc) + (loc % 3) * 12 + loc // 3).astype(np.int32)
+    c1 = p1_cell_dofs(mesh)
+    pmass = memo_pattern(mesh, ('p1_mass',), nv, nv, [(c1, c1)])
+    return pb, pbt, bt_code, pmass
+
+
 def transpose_csr(nrows, ncols, rowptr, cols, vals=None):
     """CSR transpose; returns (rowptr_t, cols_t, perm) with ``vals_t = vals[perm]``."""
     rowptr = np.asarray(rowptr, dtype=np.int64)

@@ -109,14 +109,36 @@ class MeshGenerator:
         return None
 
 
-def generate_mesh_job(kwargs, with_hierarchy=True):
-    """Worker-process entry of ``simulation.prefetch_meshes``: mesh + markers (+ multigrid hierarchy) of one geometry.
-    Pure host work (numpy / Qhull); nothing here touches CUDA or torch, so it is safe in spawned processes."""
+def precompute_device_plans(mesh_results, hier, stokes=True):
+    """Build (and memoise on the mesh objects) every CSR pattern + gather map the device problems of this geometry
+    will ask for: the P2 system level and the P1 multigrid levels of the concentration problem (Robin id 4) and, with
+    ``stokes``, of the velocity block (no Robin boundary), plus the Stokes divergence / pressure-mass plans.  Mirrors
+    the level loop of ``device.ScalarProblem`` / ``device.StokesProblem``; a key that is not asked for later costs
+    nothing but the time spent here."""
+    from . import dofmap as dm
+    from .hierarchy import level_markers
+    mesh = mesh_results['mesh']
+    bm = mesh_results['bc_markers'].values
+    for robin in ((4, None) if stokes else (4,)):
+        dm.scalar_level_plan(mesh, bm, 2, robin)
+        for m in hier.meshes:
+            mk = bm if m is mesh else level_markers(m)['bc_markers'].values
+            dm.scalar_level_plan(m, mk, 1, robin)
+    if stokes:
+        dm.stokes_block_plans(mesh)
+
+
+def generate_mesh_job(kwargs, with_hierarchy=True, plans=None):
+    """Worker-process entry of ``simulation.prefetch_meshes``: mesh + markers (+ multigrid hierarchy, + the host plans
+    of the device problems: ``plans`` = None / 'scalar' / 'stokes') of one geometry.  Pure host work (numpy / Qhull);
+    nothing here touches CUDA or torch, so it is safe in spawned processes."""
     out = MeshGenerator(**kwargs).generate_mesh()
     hier = None
     if with_hierarchy and out:
         from .hierarchy import build_hierarchy
         hier = build_hierarchy(out['mesh'])
+        if plans:
+            precompute_device_plans(out, hier, stokes=(plans == 'stokes'))
     return out, hier
 
 

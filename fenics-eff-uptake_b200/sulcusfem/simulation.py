@@ -52,7 +52,7 @@ def _mesh_key(params, domain_type):
     return key, mp
 
 
-def prefetch_meshes(jobs, workers=None, with_hierarchy=True):
+def prefetch_meshes(jobs, workers=None, with_hierarchy=True, with_plans=True):
     """Build the meshes (Delaunay + smoothing), markers and multigrid hierarchies of many geometries in parallel
     worker processes and put them into the per-geometry cache ``run_simulation`` reads.
 
@@ -60,15 +60,20 @@ def prefetch_meshes(jobs, workers=None, with_hierarchy=True):
     milliseconds a case costs on the GPU once its geometry is cached, and it is embarrassingly parallel over
     geometries, so a study hands all its geometries here first.  Returns the number of meshes built.  The results
     are the ones the in-process generator produces (same code, deterministic), so a sweep gives bit-identical fields
-    with and without prefetching."""
+    with and without prefetching.  With ``with_plans`` the workers also build the CSR patterns and gather maps the
+    device problems will need (memoised on the mesh objects, ``dofmap.memo_pattern``), leaving only uploads and the
+    sliced-ELL plans to the solving process."""
     import os
-    todo = {}
+    todo, plans = {}, {}
     for params, domain_type in jobs:
         key, mp = _mesh_key(params, domain_type)
         if key not in _MESH_CACHE and key not in todo:
             mp['output_dir'] = None
             mp['domain_type'] = domain_type
             todo[key] = dict(mp, **MESH_OPTIONS)
+            plans[key] = 'scalar' if getattr(params, 'mode', None) == 'no-adv' else 'stokes'
+        elif key in todo and getattr(params, 'mode', None) != 'no-adv':
+            plans[key] = 'stokes'
     if not todo:
         return 0
     if workers is None:
@@ -76,7 +81,7 @@ def prefetch_meshes(jobs, workers=None, with_hierarchy=True):
         workers = max(1, min(len(todo), (os.cpu_count() or 1) // max(world, 1), 16))
     from .mesh import generate_mesh_job
     if workers <= 1 or len(todo) == 1:
-        results = {k: generate_mesh_job(kw, with_hierarchy) for k, kw in todo.items()}
+        results = {k: generate_mesh_job(kw, with_hierarchy, plans.get(k) if with_plans else None) for k, kw in todo.items()}
     else:
         import multiprocessing as mp_
         import warnings
@@ -85,14 +90,15 @@ def prefetch_meshes(jobs, workers=None, with_hierarchy=True):
         try:
             # spawn: the parent may hold a CUDA context, which must not be forked
             with ProcessPoolExecutor(max_workers=workers, mp_context=mp_.get_context('spawn')) as ex:
-                futs = {k: ex.submit(generate_mesh_job, kw, with_hierarchy) for k, kw in todo.items()}
+                futs = {k: ex.submit(generate_mesh_job, kw, with_hierarchy, plans.get(k) if with_plans else None)
+                        for k, kw in todo.items()}
                 for k, f in futs.items():
                     results[k] = f.result()
         except Exception as e:          # e.g. no importable __main__ (python -c / stdin): spawned workers cannot start
             warnings.warn(f"parallel mesh prefetch unavailable ({type(e).__name__}: {e}); meshing in-process")
             for k, kw in todo.items():
                 if k not in results:
-                    results[k] = generate_mesh_job(kw, with_hierarchy)
+                    results[k] = generate_mesh_job(kw, with_hierarchy, plans.get(k) if with_plans else None)
     for k, (mesh_results, hier) in results.items():
         _MESH_CACHE[k] = mesh_results
         if hier is not None and mesh_results:

@@ -382,14 +382,11 @@ def test_direct_divergence_block_maps_match_mixed_space_extraction():
     A = gather(pat, E.ravel())
     rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(pat.rowptr.astype(np.int64)))
     cols = pat.cols.astype(np.int64)
-    # direct plans, exactly as StokesProblem.__init__ builds them
-    c2 = dm.p2_cell_dofs(mesh).astype(np.int64)
-    il = np.concatenate([2 * c2, 2 * c2 + 1], axis=1)
-    c1v = dm.p1_cell_dofs(mesh).astype(np.int64)
-    pb = dm.build_pattern(nv, 2 * n2, [(c1v, il)])
-    pbt = dm.build_pattern(2 * n2, nv, [(il, c1v)])
-    loc = pbt.contrib_code.astype(np.int64) % 36
-    pbt.contrib_code = ((pbt.contrib_code.astype(np.int64) - loc) + (loc % 3) * 12 + loc // 3).astype(np.int32)
+    # direct plans, the ones StokesProblem.__init__ uses
+    pb, pbt, bt_code, _ = dm.stokes_block_plans(mesh)
+    import copy
+    pbt = copy.copy(pbt)
+    pbt.contrib_code = bt_code
     Bd, BTd = gather(pb, EB.ravel()), gather(pbt, EB.ravel())
     # blocks cut out of the mixed-space matrix, velocity in interleaved numbering, sorted by (row, col)
     il_rows = 2 * (rows % n2) + rows // n2
@@ -456,6 +453,16 @@ def test_prefetch_meshes_parallel_matches_in_process_generation():
             ref = hy.build_hierarchy(want['mesh'])
             assert [m.num_vertices for m in hier.meshes] == [m.num_vertices for m in ref.meshes]
             assert all(np.array_equal(a.vals, b.vals) for a, b in zip(hier.transfers, ref.transfers))
+            # the workers also built the device problems' patterns + gather maps: memoised on the mesh objects under
+            # the keys the solving process will ask for, identical to a fresh build
+            cache = got['mesh']._pattern_cache
+            n, cd, f, fd, pat = dm.scalar_level_plan(got['mesh'], got['bc_markers'].values, 2, 4)
+            assert any(k[:2] == ('scalar', 2) and k[2] is not None for k in cache) and cache[[k for k in cache if k[:2] == ('scalar', 2) and k[2] is not None][0]] is pat
+            fresh = dm.build_pattern(n, n, [(cd, cd), (fd, fd)])
+            for name in ('rowptr', 'cols', 'contrib_ptr', 'contrib_code'):
+                assert np.array_equal(getattr(pat, name), getattr(fresh, name))
+            assert ('stokes_B',) not in cache                                   # no-adv jobs: scalar plans only
+            assert all(('scalar', 1, k[2]) in m._pattern_cache for m in hier.meshes for k in [next(iter(m._pattern_cache))])
     finally:
         simulation._MESH_CACHE.clear()
         simulation._MESH_CACHE.update(saved)
