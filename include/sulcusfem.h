@@ -124,9 +124,11 @@ int sfem_elem_th_stokes(int nc, const double* geo, double* E, void* stream);
 /* Divergence blocks of the same form only: EB [nc][3][12], EB[c][k][comp*6 + j] = -int l_k d(phi_j)/dx_comp -- the
  * rows of the cell's three pressure dofs against [u_x x6 | u_y x6], bit-identical to the corresponding entries of
  * sfem_elem_th_stokes.  Together with sfem_elem_p2_advdiff(D = 1, no velocity) for K this feeds the block-form solver
- * directly (72 doubles per cell instead of 225; the full matrix is then only assembled for export / parity). */
+ * directly (72 doubles per cell instead of 225; the full matrix is then only assembled for export / parity).
+ * replaces: tabulate_tensor of the  - div(v) p - q div(u)  terms of solvers.py:291-293 */
 int sfem_elem_th_div(int nc, const double* geo, double* EB, void* stream);
-/* vals[k] = 0 where row_flag[row] or col_flag[col] (either may be NULL): Dirichlet elimination of rectangular blocks */
+/* vals[k] = 0 where row_flag[row] or col_flag[col] (either may be NULL): Dirichlet elimination of rectangular blocks.
+ * replaces: DirichletBC.apply on the velocity-pressure coupling blocks inside solve(), solvers.py:262-264,298 */
 int sfem_csr_zero_flagged(int nrows, const int* rowptr, const int* cols, double* vals, const unsigned char* row_flag,
                           const unsigned char* col_flag, void* stream);
 /* P1 mass element matrices (pressure Schur-complement preconditioner); E [nc][9]. */
