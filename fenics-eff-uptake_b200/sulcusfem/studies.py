@@ -120,8 +120,12 @@ def phase_b_case(case, mesh_size_dim=0.02, quiet=True):
                 params=_params_no_adv(mu, gcfg['sulci_w_dim'], gcfg['sulci_h_dim'], mesh_size_dim))
     rect = _run(quiet, mode='no-adv', study_type="mu Sweep", config_name=f"Rect_{name}", domain_type='rectangular',
                 params=_params_no_adv(mu, gcfg['sulci_w_dim'], gcfg['sulci_h_dim'], mesh_size_dim))
-    conc_s, conc_r = _avg_conc_of(sulc, 'sulcus'), _avg_conc_of(rect, 'rectangular')
-    flux_s, flux_r = _flux_of(sulc, 'sulcus'), _flux_of(rect, 'rectangular')
+    return phase_b_row(gkey, gcfg, mu, _avg_conc_of(sulc, 'sulcus'), _avg_conc_of(rect, 'rectangular'),
+                       _flux_of(sulc, 'sulcus'), _flux_of(rect, 'rectangular'))
+
+
+def phase_b_row(gkey, gcfg, mu, conc_s, conc_r, flux_s, flux_r):
+    """CSV row of one (mu, geometry) pair from the four extracted numbers (no_advection_analysis_B.py:147-172)."""
     CR = (conc_s / conc_r) if (conc_s is not None and conc_r not in (None, 0)) else np.nan
     if flux_s is None or not np.isfinite(flux_s) or np.isclose(flux_s, 0.0):
         flux_ratio = flux_err = np.nan
@@ -230,17 +234,10 @@ def advdiff_case(case, mesh_size_dim=None, quiet=True):
     return rows
 
 
-def run_advdiff_step_validation(output_dir=None, pe_values=None, mu_factors=None, mesh_size_dim=None, rank=None,
-                                world=None, quiet=True):
-    """Reference ``run_advdiff_step_validation``: 3 Pe x 3 mu x {sulcus, step rectangle} = 18 solves (+ 1 Stokes solve
-    per geometry: the flow depends on the geometry only).  Rank 0 writes ``advdiff_validation_step_pe_x_mu.csv``."""
-    rank, world = _world(rank, world)
-    pe_values = list(PE_VALUES if pe_values is None else pe_values)
-    mu_factors = list(MU_FACTORS_ADV if mu_factors is None else mu_factors)
-    cases = [(Pe, mu) for Pe in pe_values for mu in mu_factors]
-    done = run_sharded(cases, lambda c: advdiff_case(c, mesh_size_dim, quiet), rank, world)
-    df = _frame([r for _, rows in done for r in rows], ['Pe', 'mu_factor', 'domain_type'])
-    df['flux_error_pct'] = np.nan                          # adv_diff_analysis.py:266-279
+def add_surrogate_errors(df, pe_values, mu_factors):
+    """flux_error_pct / flux_ratio of the step surrogate against the sulcus row of the same (Pe, mu)
+    (adv_diff_analysis.py:266-279)."""
+    df['flux_error_pct'] = np.nan
     df['flux_ratio'] = np.nan
     for Pe in pe_values:
         for mu in mu_factors:
@@ -252,6 +249,20 @@ def run_advdiff_step_validation(output_dir=None, pe_values=None, mu_factors=None
             rf = df.loc[ref, 'total_flux'].iloc[0]
             df.loc[rec, 'flux_ratio'] = df.loc[rec, 'total_flux'] / (rf if rf != 0 else 1.0)
             df.loc[rec, 'flux_error_pct'] = 100.0 * (df.loc[rec, 'total_flux'] - rf) / (abs(rf) if rf != 0 else 1.0)
+    return df
+
+
+def run_advdiff_step_validation(output_dir=None, pe_values=None, mu_factors=None, mesh_size_dim=None, rank=None,
+                                world=None, quiet=True):
+    """Reference ``run_advdiff_step_validation``: 3 Pe x 3 mu x {sulcus, step rectangle} = 18 solves (+ 1 Stokes solve
+    per geometry: the flow depends on the geometry only).  Rank 0 writes ``advdiff_validation_step_pe_x_mu.csv``."""
+    rank, world = _world(rank, world)
+    pe_values = list(PE_VALUES if pe_values is None else pe_values)
+    mu_factors = list(MU_FACTORS_ADV if mu_factors is None else mu_factors)
+    cases = [(Pe, mu) for Pe in pe_values for mu in mu_factors]
+    done = run_sharded(cases, lambda c: advdiff_case(c, mesh_size_dim, quiet), rank, world)
+    df = _frame([r for _, rows in done for r in rows], ['Pe', 'mu_factor', 'domain_type'])
+    df = add_surrogate_errors(df, pe_values, mu_factors)
     meta = {'study_type': 'AdvDiff Validation (Pe x mu) - Step mu only', 'timestamp': time.strftime("%Y-%m-%dT%H:%M:%S"),
             'Pe_values': pe_values, 'mu_factors': mu_factors, 'reference_geometry': REFERENCE_GEOMETRY,
             'parameters': {'D_dim': D_DIM, 'mu_dim_base': MU_DIM_BASE}, 'n_gpus': world}

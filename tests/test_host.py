@@ -466,3 +466,55 @@ def test_prefetch_meshes_parallel_matches_in_process_generation():
     finally:
         simulation._MESH_CACHE.clear()
         simulation._MESH_CACHE.update(saved)
+
+
+def test_ratio_metrics_reproduce_reference_csv_columns():
+    """studies.add_ratio_metrics (no_uptake_analysis.py:262-313) applied to the base columns of the reference's
+    checked-in geometry_comparison_results.csv reproduces its seven ratio columns."""
+    import json
+    import os
+    import pandas as pd
+    from sulcusfem import studies
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'study_columns.json')))['geometry_comparison_results.csv']
+    ratio = ['Concentration_Ratio', 'Channel_Conc_Ratio', 'Intradomain_Enrichment', 'VR_mid_avg', 'VR_mid_max',
+             'VR_intradomain_avg', 'VR_intradomain_max']
+    num = [c for c in g['columns'] if c not in ('Domain', 'Mode')]
+    df = pd.DataFrame(g['rows'])
+    for c in num:
+        df[c] = pd.to_numeric(df[c], errors='coerce')
+    want = df[ratio].to_numpy(dtype=float)
+    got = studies.add_ratio_metrics(df.drop(columns=ratio).copy())
+    assert list(got.columns) == g['columns']
+    G = got[ratio].to_numpy(dtype=float)
+    sul = (df['Domain'] == 'sulcus').to_numpy()
+    assert np.all(np.isnan(G[~sul])) and np.all(np.isnan(want[~sul]))
+    assert np.allclose(G[sul], want[sul], rtol=1e-13, atol=0.0)
+
+
+def test_derived_study_columns_reproduce_reference_csvs():
+    """Derived columns of the Phase B and adv-diff validation CSVs (CR, flux_ratio, flux_error_pct) recomputed from
+    the base columns of the reference's checked-in files with studies.phase_b_row / add_surrogate_errors."""
+    import json
+    import os
+    import pandas as pd
+    from sulcusfem import studies
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'study_columns.json')))
+    for r in g['no_adv_mu_sweep_results.csv']['rows']:
+        row = studies.phase_b_row(r['geometry'], {'sulci_w_dim': float(r['width_mm']), 'sulci_h_dim': float(r['depth_mm']),
+                                                  'aspect_ratio': float(r['aspect_ratio'])}, float(r['mu_factor']),
+                                  float(r['avg_conc_sulc']), float(r['avg_conc_rect']), float(r['flux_sulc_y0']),
+                                  float(r['flux_rect_bottom']))
+        assert list(row) == g['no_adv_mu_sweep_results.csv']['columns']
+        for k in ('CR', 'flux_ratio', 'flux_error_pct'):
+            assert abs(row[k] - float(r[k])) <= 1e-12 * max(1.0, abs(float(r[k]))), (r['geometry'], k)
+    ad = g['advdiff_validation_step_pe_x_mu.csv']
+    df = pd.DataFrame(ad['rows'])
+    for c in ad['columns']:
+        if c not in ('domain_type', 'surrogate_type'):
+            df[c] = pd.to_numeric(df[c], errors='coerce')
+    want = df[['flux_error_pct', 'flux_ratio']].to_numpy(dtype=float)
+    got = studies.add_surrogate_errors(df.drop(columns=['flux_error_pct', 'flux_ratio']).copy(), studies.PE_VALUES,
+                                       studies.MU_FACTORS_ADV)
+    assert list(got.columns) == ad['columns']
+    G = got[['flux_error_pct', 'flux_ratio']].to_numpy(dtype=float)
+    assert np.array_equal(np.isnan(G), np.isnan(want)) and np.allclose(G[~np.isnan(G)], want[~np.isnan(want)], rtol=1e-12)
