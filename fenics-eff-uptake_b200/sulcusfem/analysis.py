@@ -116,6 +116,38 @@ def compute_uptake_flux_bottom(c, measures, mu_val):
     return float(F[_G['bottom'], _UPT])
 
 
+def compute_uptake_flux_segments(c, measures, mu_val):
+    """Uptake flux mu c over the external bottom segments bottom_left / sulcus / bottom_right and their sum
+    (reference analysis.py:313-333); read from the functionals of the last ``compute_flux_metrics`` on ``c``."""
+    F, _ = c._functionals_any
+    bl, su, br = (float(F[_G[k], _UPT]) for k in ('bottom_left', 'sulcus', 'bottom_right'))
+    return {'bottom_left': bl, 'sulcus': su, 'bottom_right': br, 'total': bl + su + br}
+
+
+def sample_mu_along_bottom(results, n_points=500, y_at_bottom=0.0, save_csv_path=None):
+    """Sample the Robin coefficient mu(x) along the bottom wall (reference analysis.py:838-882, same keys): mu may be
+    a float, a ``Constant`` or a ``UserExpression`` such as ``StepUptakeOpen``.  Host-only (it evaluates the
+    coefficient, not a field)."""
+    params = results.get('params', None)
+    mesh = results.get('mesh_results', {}).get('mesh', None)
+    if params is None or mesh is None:
+        raise ValueError("results must contain 'params' and 'mesh_results[mesh]'")
+    mu_obj = getattr(params, 'mu', None)
+    coords = mesh.coordinates()
+    xs = np.linspace(float(coords[:, 0].min()), float(coords[:, 0].max()), int(n_points))
+    mus = evaluate_expression(mu_obj, np.stack([xs, np.full(len(xs), float(y_at_bottom))], axis=1))
+    trapz = getattr(np, 'trapezoid', None) or np.trapz
+    out = {'x': xs, 'mu': mus,
+           'mu_mean': float(trapz(mus, xs) / (xs[-1] - xs[0]) if len(xs) > 1 else mus.mean()),
+           'mu_min': float(np.min(mus)), 'mu_max': float(np.max(mus))}
+    if save_csv_path:
+        import os
+        import pandas as pd
+        os.makedirs(os.path.dirname(save_csv_path), exist_ok=True)
+        pd.DataFrame({'x': xs, 'mu': mus}).to_csv(save_csv_path, index=False)
+    return out
+
+
 # ====================================================================== mass metrics
 def compute_mass_metrics(c, measures, domain_type):
     """Reference analysis.py:677-719."""

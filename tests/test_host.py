@@ -1,4 +1,6 @@
 """CPU: host-side logic (meshes, markers, DOF maps, sparsity, gather maps, hierarchy, front-end objects)."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -518,3 +520,33 @@ def test_derived_study_columns_reproduce_reference_csvs():
     assert list(got.columns) == ad['columns']
     G = got[['flux_error_pct', 'flux_ratio']].to_numpy(dtype=float)
     assert np.array_equal(np.isnan(G), np.isnan(want)) and np.allclose(G[~np.isnan(G)], want[~np.isnan(want)], rtol=1e-12)
+
+
+def test_sample_mu_along_bottom(tmp_path):
+    """analysis.sample_mu_along_bottom (reference analysis.py:838-882): constant and StepUptakeOpen coefficients."""
+    from sulcusfem import analysis
+    from sulcusfem.fem import Constant
+    from sulcusfem.parameters import StepUptakeOpen
+
+    class P:
+        pass
+    mesh = hm.rectangle_mesh(10.0, 1.0, 20, 2)
+    p = P()
+    p.mu = 0.7
+    out = analysis.sample_mu_along_bottom({'params': p, 'mesh_results': {'mesh': mesh}}, n_points=11)
+    assert np.array_equal(out['x'], np.linspace(0, 10, 11)) and np.all(out['mu'] == 0.7) and out['mu_mean'] == pytest.approx(0.7)
+    p.mu = Constant(1.5)
+    assert analysis.sample_mu_along_bottom({'params': p, 'mesh_results': {'mesh': mesh}}, 5)['mu_max'] == 1.5
+    step = StepUptakeOpen(mu_base=1.0, mu_eff_target=1.77, sulcus_left_x=4.75, sulcus_right_x=5.25, L_c=0.05, Gamma=5.0)
+    p.mu = step
+    path = tmp_path / 'mu' / 'mu_samples.csv'
+    out = analysis.sample_mu_along_bottom({'params': p, 'mesh_results': {'mesh': mesh}}, n_points=2001, save_csv_path=str(path))
+    assert out['mu_min'] == 1.0 and out['mu_max'] == 1.77
+    assert 1.0 < out['mu_mean'] < 1.0 + 0.77 * 0.5 / 10.0               # base + (open - base) * (less than w / L)
+    mid = out['mu'][np.abs(out['x'] - 5.0) < 1e-9][0]
+    assert mid == out['mu_max'] and os.path.exists(path)
+    v = np.zeros(1)
+    step.eval(v, np.array([5.0, 0.0]))
+    assert v[0] == mid
+    with pytest.raises(ValueError):
+        analysis.sample_mu_along_bottom({'params': None})
