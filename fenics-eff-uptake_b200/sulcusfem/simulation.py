@@ -185,6 +185,40 @@ def _simulation_post_process(domain_type, params, mesh_results, c, u, p):
     return results
 
 
+def _simulation_save_results(results, filename):
+    """JSON summary of one run (reference simulation.py:235-262: same keys -- params, mass_metrics, flux_metrics,
+    mesh_info, mu_eff_comparison).  In the reference this call always ends in its ``except`` branch because
+    ``Parameters.to_dict`` raises; here ``to_dict`` works, so the file is written.  numpy scalars and
+    arrays inside the metric dictionaries are converted to plain Python."""
+    import json
+
+    def plain(o):
+        import numpy as np
+        if isinstance(o, dict):
+            return {str(k): plain(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return [plain(v) for v in o]
+        if isinstance(o, np.ndarray):
+            return o.tolist()
+        if isinstance(o, np.generic):
+            return o.item()
+        return o
+    try:
+        mesh = (results.get('mesh_results', {}) or {}).get('mesh')
+        mesh_info = {}
+        if mesh:
+            mesh_info = {'num_vertices': int(mesh.num_vertices), 'num_cells': int(mesh.num_cells), 'hmin': mesh.hmin(),
+                         'hmax': mesh.hmax()}
+        out = {'params': plain(results['params'].to_dict()), 'mass_metrics': plain(results['mass_metrics']),
+               'flux_metrics': plain(results['flux_metrics']), 'mesh_info': mesh_info,
+               'mu_eff_comparison': plain(results.get('mu_eff_comparison', None))}
+        with open(filename, 'w') as f:
+            json.dump(out, f, indent=4)
+        print(f"✓ Results saved to {filename}")
+    except Exception as e:
+        print(f"Error saving results: {e}")
+
+
 def run_simulation(mode, study_type, config_name, domain_type, params, mu_variable=False):
     """Run one case; same arguments and result dictionary as the reference's ``run_simulation``."""
     start_time = time.time()

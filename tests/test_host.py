@@ -550,3 +550,24 @@ def test_sample_mu_along_bottom(tmp_path):
     assert v[0] == mid
     with pytest.raises(ValueError):
         analysis.sample_mu_along_bottom({'params': None})
+
+
+def test_simulation_save_results_json(tmp_path):
+    """simulation._simulation_save_results (reference simulation.py:235-262): keys of the JSON summary."""
+    import json
+    from sulcusfem import simulation
+    from sulcusfem.parameters import Parameters
+    p = Parameters(mode='no-adv', mesh_size_dim=0.1)
+    p.validate()
+    p.nondim()
+    mesh = hm.rectangle_mesh(10.0, 1.0, 10, 2)
+    res = {'params': p, 'mesh_results': {'mesh': mesh},
+           'mass_metrics': {'total_mass': np.float64(1.5), 'profiles_full': {'x': np.arange(3.0)}},
+           'flux_metrics': {'uptake_flux': 0.25, 'physical_flux': {'left': {'total': np.float64(-1.0)}}}}
+    path = tmp_path / 'results.json'
+    simulation._simulation_save_results(res, str(path))
+    out = json.load(open(path))
+    assert set(out) == {'params', 'mass_metrics', 'flux_metrics', 'mesh_info', 'mu_eff_comparison'}
+    assert out['mesh_info']['num_cells'] == mesh.num_cells and out['mass_metrics']['total_mass'] == 1.5
+    assert out['mass_metrics']['profiles_full']['x'] == [0.0, 1.0, 2.0] and out['mu_eff_comparison'] is None
+    assert out['params']['mode'] == 'no-adv' if 'mode' in out['params'] else True
