@@ -50,10 +50,10 @@ def build_mesh(h, refine):
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def oracle_step(h, mu=MU):
+def oracle_step(h, mu=MU, mr=None, fields=False):
     """One step of the same workload on the CPU oracle (numpy assembly + SuperLU), timed."""
     from oracle import cpu_oracle as co
-    mr = build_mesh(h, 0)
+    mr = build_mesh(h, 0) if mr is None else mr
     mesh = mr['mesh']
     om = co.Mesh(mesh.coords, mesh.cells)
     bm = mr['bc_markers'].values
@@ -65,39 +65,56 @@ def oracle_step(h, mu=MU):
     co.mass_metrics(om, c, 'sulcus', mk['domain_markers'])
     dt = time.perf_counter() - t0
     ndof = 2 * om.n_p2 + om.nv + om.n_p2
+    if fields:
+        me = co.mu_eff_metrics(fl, L_CH, D_SULCUS, W_SULCUS, mu)
+        return dt, ndof, {'ux': ux, 'uy': uy, 'p': p, 'c': c, 'flux': fl, 'mu_eff': me}
     return dt, ndof, fl
 
 
 def run_reference(args, rank):
+    """The CPU arm: K timed (+ W warm-up) steps of the SAME step (Stokes + adv-diff + functionals) on the oracle
+    port, on a BOUNDED mesh of the same workload family (h = --cpu-h, no refinement) -- a sparse LU of the GPU arm's
+    6 M-dof mesh does not end within minutes.  `config` states the mesh this arm really solved; the GPU arm's
+    `same_mesh` records time the GPU on exactly this mesh (and check parity there)."""
     if rank != 0:
         return
     hs = args.cpu_h
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        oracle_step(hs)
+    mr = build_mesh(hs, 0)
+    for _ in range(args.warmup):
+        oracle_step(hs, mr=mr)
     times, ndof = [], 0
     for _ in range(args.steps):
-        dt, ndof, _ = oracle_step(hs)
+        dt, ndof, _ = oracle_step(hs, mr=mr)
         times.append(dt)
     val = ndof * len(times) / sum(times)
-    sample = (f"same adv-diff sulcus step (Stokes + adv-diff + functionals) on the h={hs} mesh, {ndof} dofs, "
+    sample = (f"same adv-diff sulcus step (Stokes + adv-diff + functionals) on the h={hs} unrefined mesh, {ndof} dofs, "
               f"numpy assembly + scipy SuperLU, 1 thread")
+    cfg = workload_config(args, h=hs, refine=0, dofs=ndof)
+    cfg["l2"] = "n/a (CPU)"
+    cfg["parallelism"] = "1 host thread (serial reference path)"
+    cfg["bounded_sample_of"] = {"h": args.h, "refine": args.refine,
+                                "why": "per-DOF throughput across UNEQUAL meshes when set against the GPU arm's headline value; "
+                                       "the same-mesh ratio is the GPU arm's same_mesh[] record for this h"}
     line = {
         "impl": "reference", "metric": "fem_dofs_per_s", "value": val, "unit": "DOFs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": val, "unit": "DOFs/s", "cores": 1, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "DOFs/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
         "e2e": {"value": val, "unit": "DOFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "dolfin/PETSc is not installable in this image; the CPU arm is the oracle port of the reference path",
     }
     print(json.dumps(line))
 
 
-def workload_config(args):
+def workload_config(args, h=None, refine=None, dofs=None):
+    h = args.h if h is None else h
+    refine = args.refine if refine is None else refine
     return {"workload": f"adv-diff sulcus (BASELINE configs[1]): Stokes TH + adv-diff P2 + functionals, "
-                        f"w={W_SULCUS} d={D_SULCUS} Pe={PE:g} mu={MU:g}, synthetic Delaunay mesh h={args.h} "
-                        f"+ {args.refine} uniform refinements",
-            "h": args.h, "refine": args.refine, "l2": "flushed between steps (512 MiB memset + 512 MiB read of a second buffer)",
+                        f"w={W_SULCUS} d={D_SULCUS} Pe={PE:g} mu={MU:g}, synthetic Delaunay mesh h={h} "
+                        f"+ {refine} uniform refinements",
+            "h": h, "refine": refine, "dofs": dofs, "l2": "flushed between steps (512 MiB memset + 512 MiB read of a second buffer)",
             "krylov_rtol": {"scalar_true_residual": RTOL, "stokes_preconditioned_residual": STOKES_RTOL,
                             "basis": "fields within 1e-10 relative L2 of the LU solution with >= 2.5x (scalar) / 100x (Stokes) margin, profiles/r01_tolerance_study.md"}, "parallelism": f"case-sharded x{args.gpus} (no collectives)"}
 
@@ -140,12 +157,152 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+class Case:
+    """One sulcus case on this rank's GPU: mesh, device problems, the device-resident step and the same step through
+    the reference-facing API (host in, host out)."""
+
+    def __init__(self, ctx, h, refine, mu):
+        import torch
+        from sulcusfem import dofmap as dm
+        from sulcusfem.device import FunctionalPlan, ScalarProblem, StokesProblem
+        from sulcusfem.hierarchy import build_hierarchy
+        self.ctx, self.h, self.refine, self.mu, self.D = ctx, h, refine, mu, 1.0 / PE
+        self.setup = {}
+        t0 = time.perf_counter()
+        self.mr = mr = build_mesh(h, refine)
+        self.mesh, self.bm = mr['mesh'], mr['bc_markers'].values
+        t1 = time.perf_counter()
+        self.hier = build_hierarchy(self.mesh)
+        t2 = time.perf_counter()
+        self.stokes = StokesProblem(self.mesh, self.bm, hierarchy=self.hier, ctx=ctx)
+        t3 = time.perf_counter()
+        self.scalar = ScalarProblem(self.mesh, self.bm, hierarchy=self.hier, ctx=ctx)
+        t4 = time.perf_counter()
+        self.plan = FunctionalPlan(self.mesh, mr, 'sulcus', ctx=ctx)
+        # the reference-facing API (e2e leg) finds the same device objects through the per-mesh cache
+        self.mesh._sfem_cache = {'hierarchy': self.hier, 'stokes': self.stokes, ('scalar', 4): self.scalar,
+                                 ('functionals', 'sulcus'): self.plan}
+        X = dm.p2_dof_coordinates(self.mesh)
+        d1 = dm.dirichlet_dofs_p2(self.mesh, self.bm, 1)
+        self.stokes.set_bcs({1: (4.0 * X[d1, 1] * (H_CH - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+        self.stokes._inflow_H = float(H_CH)
+        torch.cuda.synchronize()
+        t5 = time.perf_counter()
+        self.setup = {"mesh_markers_s": t1 - t0, "hierarchy_s": t2 - t1, "stokes_problem_s": t3 - t2,
+                      "scalar_problem_s": t4 - t3, "functionals_bcs_s": t5 - t4, "total_s": t5 - t0}
+        self.ndof = self.stokes.n + self.scalar.n
+        self.info = {}
+        self.api_ms = {}
+        self._spaces = None
+
+    def step(self):
+        st, sc, mu, D = self.stokes, self.scalar, self.mu, self.D
+        st.assemble(bc_mode=1)
+        ux, uy, p = st.solve(rtol=STOKES_RTOL)
+        sc.assemble(D, ux, uy, mu_const=mu, bc_values={1: 1.0, 2: 0.0})
+        c = sc.solve('fgmres', rtol=RTOL)
+        F, M = self.plan.evaluate(c, ux, uy, D=D, mu_const=mu)
+        self.info['stokes'], self.info['advdiff'] = dict(st.last_info), dict(sc.last_info)
+        return F, M
+
+    def api_step(self):
+        """Stokes -> adv-diff -> functionals through sulcusfem.solvers / analysis; returns (u, p, c, flux, mass)."""
+        import contextlib
+        import io
+        from sulcusfem import solvers, analysis
+        from sulcusfem.fem import Constant, FunctionSpace, MixedElement, VectorFunctionSpace
+        if self._spaces is None:
+            V = VectorFunctionSpace(self.mesh, "P", 2)
+            Q = FunctionSpace(self.mesh, "P", 1)
+            self._spaces = (FunctionSpace(self.mesh, MixedElement([V.ufl_element(), Q.ufl_element()])),
+                            FunctionSpace(self.mesh, "CG", 2))
+        Wsp, Csp = self._spaces
+        t = [time.perf_counter()]
+        with contextlib.redirect_stdout(io.StringIO()):
+            u, p = solvers.stokes_solver(self.mr, Wsp, L_CH, H_CH, 'sulcus')
+            t.append(time.perf_counter())
+            u._dev = None                                  # velocity re-enters from its host array (H2D)
+            c = solvers.advdiff_solver(self.mr, u, Csp, Constant(self.D), Constant(self.mu), 'sulcus')
+            t.append(time.perf_counter())
+            c._dev = None
+            fm = analysis.compute_flux_metrics(c, u, self.mr, 'sulcus', {}, self.D, self.mu)
+            mm = analysis.compute_mass_metrics(c, {}, 'sulcus')
+            t.append(time.perf_counter())
+        for name, a, b in (('stokes_solver', 0, 1), ('advdiff_solver', 1, 2), ('functionals', 2, 3)):
+            self.api_ms[name] = 1e3 * (t[b] - t[a])
+        return u, p, c, fm, mm
+
+    def bytes_per_step(self):
+        n2, nv = self.stokes.n2, self.stokes.nv
+        h2d = 8 * (2 * n2) + 8 * n2          # velocity components + concentration re-uploaded for the functionals
+        d2h = 8 * (2 * n2 + nv) + 8 * n2 + 8 * (self.plan.ngroups * 8 + self.plan.nmarkers * 2)
+        return h2d, d2h
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(b))
+
+
+def same_mesh_leg(ctx, h, flush_l2, reps=5):
+    """GPU and CPU oracle on the SAME unrefined mesh (h = 0.02 is the reference's default size, BASELINE configs[1]
+    as the reference itself runs it): device-timed and API-timed GPU step, the CPU step, their ratio, and the parity
+    of the API results against the oracle's LU fields (bars: fields 1e-10 relative L2, mu_eff 1e-8)."""
+    import torch
+    from types import SimpleNamespace
+    from sulcusfem import analysis
+    case = Case(ctx, h, 0, MU)
+    for _ in range(3):
+        case.step()
+    ts = []
+    for _ in range(reps):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); case.step(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    case.api_step()
+    te = []
+    for _ in range(reps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        u, p, c, fm, mm = case.api_step()
+        torch.cuda.synchronize()
+        te.append(1e3 * (time.perf_counter() - t0))
+    res = {'params': SimpleNamespace(L=L_CH, sulci_h=D_SULCUS, sulci_w=W_SULCUS, mu=MU), 'c': c, 'flux_metrics': fm}
+    me = analysis.compute_mu_eff_metrics(res)
+    cpu_s, ndof, o = oracle_step(h, mr=case.mr, fields=True)
+    n2 = case.stokes.n2
+    par = {"rel_l2_u": _rel(u.values, np.concatenate([o['ux'], o['uy']])), "rel_l2_p": _rel(p.values, o['p']),
+           "rel_l2_c": _rel(c.values, o['c']),
+           "mu_eff_sim_rel": abs(me['mu_eff_sim'] - o['mu_eff']['mu_eff_sim']) / abs(o['mu_eff']['mu_eff_sim']),
+           "mu_eff_open_rel": abs(me['mu_eff_open'] - o['mu_eff']['mu_eff_open']) / abs(o['mu_eff']['mu_eff_open']),
+           "uptake_rel": abs(fm['uptake_flux'] - o['flux']['uptake_flux']) / abs(o['flux']['uptake_flux']),
+           "bars": {"fields": 1e-10, "mu_eff": 1e-8, "uptake": 1e-9}}
+    par["ok"] = bool(par["rel_l2_u"] <= 1e-10 and par["rel_l2_c"] <= 1e-10 and par["mu_eff_sim_rel"] <= 1e-8
+                     and par["mu_eff_open_rel"] <= 1e-8 and par["uptake_rel"] <= 1e-9 and par["rel_l2_p"] <= 1e-9)
+    gpu_ms, e2e_ms = float(np.median(ts)), float(np.median(te))
+    rec = {"h": h, "refine": 0, "dofs": int(ndof), "gpu_ms": gpu_ms, "gpu_e2e_ms": e2e_ms, "cpu_ms": 1e3 * cpu_s,
+           "ratio": 1e3 * cpu_s / e2e_ms, "ratio_device_resident": 1e3 * cpu_s / gpu_ms,
+           "gpu_dofs_per_s_e2e": ndof / (e2e_ms / 1e3), "cpu_dofs_per_s": ndof / cpu_s,
+           "iterations": {"stokes_minres": case.info['stokes']['iterations'], "advdiff_fgmres": case.info['advdiff']['iterations']},
+           "setup_s": case.setup, "parity": par,
+           "note": "GPU = this repo's API path (host in / host out) and device-resident step; CPU = oracle port "
+                   "(numpy assembly + SuperLU + one extended-precision refinement), 1 thread; same mesh, same parameters"}
+    del case
+    return rec
+
+
+def run_dd_strong(args, case, rank, world, dist, flush_l2):
+    """Filled in below (config 5)."""
+    return None
+
+
 def run_gpu(args, rank, world):
     import torch
     import ctypes as C
-    from sulcusfem import capi, dofmap as dm
-    from sulcusfem.device import Context, FunctionalPlan, ScalarProblem, StokesProblem
-    from sulcusfem.hierarchy import build_hierarchy
+    from sulcusfem import capi
+    from sulcusfem.device import Context
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     dist = None
@@ -157,32 +314,12 @@ def run_gpu(args, rank, world):
     from sulcusfem import solvers as _sv
     assert (_sv.RTOL, _sv.STOKES_RTOL) == (RTOL, STOKES_RTOL), "bench.py tolerances differ from the API defaults"
     mu = MU + 0.05 * rank                      # every rank: its own sweep case
-    t_setup = time.perf_counter()
-    mr = build_mesh(args.h, args.refine)
-    mesh, bm = mr['mesh'], mr['bc_markers'].values
-    hier = build_hierarchy(mesh)
-    stokes = StokesProblem(mesh, bm, hierarchy=hier, ctx=ctx)
-    scalar = ScalarProblem(mesh, bm, hierarchy=hier, ctx=ctx)
-    plan = FunctionalPlan(mesh, mr, 'sulcus', ctx=ctx)
-    # the reference-facing API (e2e leg) finds the same device objects through the per-mesh cache
-    mesh._sfem_cache = {'hierarchy': hier, 'stokes': stokes, ('scalar', 4): scalar, ('functionals', 'sulcus'): plan}
-    X = dm.p2_dof_coordinates(mesh)
-    d1 = dm.dirichlet_dofs_p2(mesh, bm, 1)
-    stokes.set_bcs({1: (4.0 * X[d1, 1] * (H_CH - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
-    torch.cuda.synchronize()
-    t_setup = time.perf_counter() - t_setup
-    ndof = stokes.n + scalar.n
-    D = 1.0 / PE
-    info = {}
-
-    def step():
-        stokes.assemble(bc_mode=1)
-        ux, uy, p = stokes.solve(rtol=STOKES_RTOL)
-        scalar.assemble(D, ux, uy, mu_const=mu, bc_values={1: 1.0, 2: 0.0})
-        c = scalar.solve('fgmres', rtol=RTOL)
-        F, M = plan.evaluate(c, ux, uy, D=D, mu_const=mu)
-        info['stokes'], info['advdiff'] = dict(stokes.last_info), dict(scalar.last_info)
-        return F, M
+    case = Case(ctx, args.h, args.refine, mu)
+    mesh, stokes, scalar, plan = case.mesh, case.stokes, case.scalar, case.plan
+    t_setup = case.setup['total_s']
+    ndof = case.ndof
+    info = case.info
+    step = case.step
 
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
     flush2 = torch.ones(512 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device)
@@ -220,49 +357,26 @@ def run_gpu(args, rank, world):
     ms_total = float(t.item())
 
     # ---- e2e through the reference-facing API (host in, host out)
-    from sulcusfem import solvers, analysis
-    from sulcusfem.fem import Constant, FunctionSpace, MixedElement, VectorFunctionSpace
-    from sulcusfem.parameters import Parameters
-    V = VectorFunctionSpace(mesh, "P", 2)
-    Q = FunctionSpace(mesh, "P", 1)
-    Wsp = FunctionSpace(mesh, MixedElement([V.ufl_element(), Q.ufl_element()]))
-    Csp = FunctionSpace(mesh, "CG", 2)
-    import contextlib
-    import io
-
-    api_ms = {}
-
-    def api_step():
-        t = [time.perf_counter()]
-        with contextlib.redirect_stdout(io.StringIO()):
-            u, p = solvers.stokes_solver(mr, Wsp, L_CH, H_CH, 'sulcus')
-            t.append(time.perf_counter())
-            u._dev = None                                  # velocity re-enters from its host array (H2D)
-            c = solvers.advdiff_solver(mr, u, Csp, Constant(D), Constant(mu), 'sulcus')
-            t.append(time.perf_counter())
-            c._dev = None
-            fm = analysis.compute_flux_metrics(c, u, mr, 'sulcus', {}, D, mu)
-            mm = analysis.compute_mass_metrics(c, {}, 'sulcus')
-            t.append(time.perf_counter())
-        for name, a, b in (('stokes_solver', 0, 1), ('advdiff_solver', 1, 2), ('functionals', 2, 3)):
-            api_ms[name] = 1e3 * (t[b] - t[a])
-        return fm, mm
-    api_step()
+    api_ms = case.api_ms
+    case.api_step()
     barrier()
     t0 = time.perf_counter()
     n_e2e = max(1, min(args.steps, 3))
     for _ in range(n_e2e):
         flush_l2()
-        fm, mm = api_step()
+        _, _, _, fm, mm = case.api_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / n_e2e
     te = torch.tensor([e2e_s], dtype=torch.float64, device=ctx.device)
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    n2, nv = stokes.n2, stokes.nv
-    h2d = 8 * (2 * n2) + 8 * n2          # velocity components + concentration re-uploaded for the functionals
-    d2h = 8 * (2 * n2 + nv) + 8 * n2 + 8 * (plan.ngroups * 8 + plan.nmarkers * 2)
+    h2d, d2h = case.bytes_per_step()
+
+    # ---- config 5: the SAME step, one case domain-decomposed over all ranks (strong scaling), on the driver's clock
+    dd = None
+    if world > 1 and not args.no_dd:
+        dd = run_dd_strong(args, case, rank, world, dist, flush_l2)
 
     if rank != 0:
         return
@@ -319,12 +433,16 @@ def run_gpu(args, rank, world):
                 "by_category": per_cat, "profiled_step_kernel_ms": float(mss.sum()),
                 "note": "profiled step runs un-graphed with a CUDA event pair around every launch; traffic: see profiles/"}
 
-    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 only
-    cpu = None
-    if not args.no_cpu:
-        dt, nd, _ = oracle_step(args.cpu_h)
-        cpu = {"value": nd / dt, "unit": "DOFs/s", "cores": 1, "kind": "port",
-               "sample": f"one step of the same workload on the h={args.cpu_h} mesh ({nd} dofs): numpy assembly + SuperLU, {dt:.1f} s",
+    # ---- CPU baseline (oracle port) + same-mesh GPU legs with parity, rank 0 at N = 1 only
+    cpu, same = None, []
+    if not args.no_cpu and world == 1:
+        for hh in dict.fromkeys([args.same_h, args.cpu_h]):
+            same.append(same_mesh_leg(ctx, hh, flush_l2))
+        r0 = same[0]
+        cpu = {"value": r0["cpu_dofs_per_s"], "unit": "DOFs/s", "cores": 1, "kind": "port",
+               "sample": f"one step of the same workload on the unrefined h={r0['h']} mesh ({r0['dofs']} dofs; h=0.02 is the "
+                         f"reference's default mesh size): numpy assembly + SuperLU, {r0['cpu_ms'] / 1e3:.1f} s; the GPU on this "
+                         f"same mesh: same_mesh[0]",
                "host_cores": os.cpu_count()}
 
     value = world * ndof * args.steps / (ms_total / 1e3)
@@ -340,10 +458,16 @@ def run_gpu(args, rank, world):
                 "ms_per_step": 1e3 * e2e_s, "last_step_breakdown_ms": api_ms,
                 "api": "sulcusfem.solvers.stokes_solver + advdiff_solver + analysis.compute_*_metrics"},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "setup_s": t_setup,
+        "setup_s": t_setup, "setup_breakdown_s": case.setup,
+        "same_mesh": same, "dd_strong": dd,
         "functionals": {"uptake_flux": fm['uptake_flux'], "total_mass": mm['total_mass']},
     }
-    print(json.dumps(line))
+    line["config"]["dofs"] = ndof
+    print(json.dumps(line), flush=True)
+    bad = [r for r in same if not r["parity"]["ok"]]
+    if bad:
+        print("PARITY FAILURE in the same-mesh leg: " + json.dumps([r["parity"] for r in bad]), file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -354,8 +478,11 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--h', type=float, default=0.02)
     ap.add_argument('--refine', type=int, default=int(os.environ.get('SFEM_BENCH_REFINE', 2)))
-    ap.add_argument('--cpu-h', type=float, default=0.03)    # ~10 s of single-thread CPU work per step (168 k dofs)
+    ap.add_argument('--cpu-h', type=float, default=0.03)    # reference arm: ~4-9 s of single-thread CPU work per step (168 k dofs)
+    ap.add_argument('--same-h', type=float, default=0.02)   # same-mesh leg / cpu_baseline: the reference's default mesh size (385 k dofs)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-dd', action='store_true')         # N > 1: skip the domain-decomposed (config 5) leg
+    ap.add_argument('--dd-refine', default=os.environ.get('SFEM_BENCH_DD_REFINE', ''))   # extra refinements for the dd leg, e.g. "3"
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

@@ -245,6 +245,7 @@ void* sfem_dist_mailbox(sfem_dist_t h) { return h ? h->d.dev.mailbox[h->d.dev.ra
 /* makes h the communicator used by halo exchanges and the Krylov reductions of this process (NULL: none) */
 int sfem_dist_activate(sfem_dist_t h) {
   g_dist = h ? &h->d : nullptr;
+  graph_epoch_bump();
   return SFEM_OK;
 }
 
@@ -260,6 +261,7 @@ int sfem_dist_error(sfem_dist_t h) {
 void sfem_dist_destroy(sfem_dist_t h) {
   if (!h) return;
   if (g_dist == &h->d) g_dist = nullptr;
+  graph_epoch_bump();
   Dist& d = h->d;
   for (int q = 0; q < d.dev.nranks; ++q)
     if (d.peer_open[q]) cudaIpcCloseMemHandle(d.peer_base[q]);
@@ -320,6 +322,7 @@ void sfem_halo_destroy(sfem_halo_t hh) {
       if (it->second == &hh->h) { it = g_halos.erase(it); g_nhalos.fetch_sub(1); } else ++it;
     }
   }
+  graph_epoch_bump();
   for (void* p : hh->owned) cudaFree(p);
   delete hh;
 }
@@ -329,6 +332,7 @@ void sfem_halo_destroy(sfem_halo_t hh) {
 int sfem_halo_attach(const int* rowptr, sfem_halo_t hh) {
   if (!rowptr) { set_error("sfem_halo_attach: null matrix"); return SFEM_ERR_ARG; }
   std::lock_guard<std::mutex> lk(g_mu);
+  graph_epoch_bump();                       // exchanges are baked into captured launch sequences
   auto it = g_halos.find(rowptr);
   if (hh == nullptr) {
     if (it != g_halos.end()) { g_halos.erase(it); g_nhalos.fetch_sub(1); }

@@ -6,12 +6,20 @@
 // forked onto a private non-blocking stream and joined back with events.
 #pragma once
 #include "sfem_common.cuh"
+#include "sfem_internal.h"
+
+#include <vector>
 
 namespace sfem {
 
 bool profiling_active();      // sfem_vector.cu: per-launch profiler on -> graphs are bypassed
 bool graphs_enabled();        // env SFEM_GRAPHS (default on) and not profiling
 
+// Registry epoch: bumped whenever something a captured launch sequence depends on -- but that is not visible in the
+// pointers baked into it -- changes: a sliced-ELL / staged plan (un)registered, a halo pattern attached or detached,
+// the communicator (de)activated, a multigrid handle created or destroyed.  Every graph cache stores the epoch of
+// its capture and re-captures on mismatch, so a graph can never be replayed over freed or re-purposed buffers that
+// happen to sit at the same addresses (graph_epoch / graph_epoch_bump: sfem_internal.h, counter in sfem_vector.cu).
 struct GraphExec {
   cudaGraphExec_t exec = nullptr;
   long long nodes = 0;        // kernel launches recorded in the graph (for sfem_launch_count)
@@ -51,6 +59,29 @@ int graph_capture(cudaStream_t st, GraphExec& g, F&& body) {
   g.nodes = after - before;
   return SFEM_OK;
 }
+
+// Everything a captured Krylov iteration bakes in: the pointers, the sizes, the smoother degree, the communicator
+// size and the registry epoch.
+struct GraphKey {
+  const void* a[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  long long nnz = 0;
+  int n = 0, m = 0, degree = 0, nranks = 0;
+  unsigned long long epoch = 0;
+  bool operator==(const GraphKey& o) const {
+    for (int i = 0; i < 8; ++i)
+      if (a[i] != o.a[i]) return false;
+    return nnz == o.nnz && n == o.n && m == o.m && degree == o.degree && nranks == o.nranks && epoch == o.epoch;
+  }
+};
+struct GraphCache {
+  GraphKey key;
+  std::vector<GraphExec> g;
+  void invalidate(size_t n) {
+    for (auto& e : g) e.reset();
+    g.assign(n, GraphExec());
+  }
+  ~GraphCache() { for (auto& e : g) e.reset(); }
+};
 
 inline int graph_launch(GraphExec& g, cudaStream_t st) {
   SFEM_CUDA(cudaGraphLaunch(g.exec, st));

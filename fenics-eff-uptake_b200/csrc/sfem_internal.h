@@ -47,6 +47,8 @@ void sell_mark_dirty(const double* csr_vals);     // called by every entry that 
 int sell_ensure_all(cudaStream_t st);             // re-pack every dirty mirror (solver entries, before graph replays)
 
 // sfem_vector.cu
+unsigned long long graph_epoch();                 // see sfem_graph.h
+void graph_epoch_bump();
 int vec_set(int n, double a, double* x, cudaStream_t st);
 int vec_copy(int n, const double* x, double* y, cudaStream_t st);
 int vec_axpby(int n, double a, const double* x, double b, double* y, cudaStream_t st);

@@ -233,19 +233,8 @@ struct Poller {
 thread_local Poller t_poll;
 thread_local WorkStream t_work;
 
-// graph cache of the CG / FGMRES iteration bodies, valid while every baked-in pointer is unchanged
-struct GraphKey {
-  const void* a[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool operator==(const GraphKey& o) const { return std::memcmp(a, o.a, sizeof(a)) == 0; }
-};
-struct GraphCache {
-  GraphKey key;
-  std::vector<GraphExec> g;
-  void invalidate(size_t n) {
-    for (auto& e : g) e.reset();
-    g.assign(n, GraphExec());
-  }
-};
+// graph caches of the CG / FGMRES iteration bodies live in the multigrid handle that preconditions them (destroyed
+// with it); Jacobi-preconditioned solves (no handle) use these thread-local ones.  Keys: sfem_graph.h.
 thread_local GraphCache t_cg_graph, t_gmres_graph;
 
 cudaStream_t pick_stream(cudaStream_t user, bool* forked) {
@@ -320,19 +309,21 @@ int sfem_krylov_cg(int n, int nnz, const int* rowptr, const int* cols, const dou
     SFEM_LAUNCH_CHECK();
     SFEM_TRY(vec_copy(n, z, p, st));
     const bool use_graph = graphs_enabled();
+    GraphCache& gc = mg ? mg->cg_graph : t_cg_graph;
     if (use_graph) {
       GraphKey key;
       key.a[0] = rowptr; key.a[1] = cols; key.a[2] = vals; key.a[3] = mg; key.a[4] = x; key.a[5] = t_ws.ptr;
-      key.a[6] = (const void*)(uintptr_t)n; key.a[7] = st;
-      if (!(t_cg_graph.key == key) || t_cg_graph.g.empty() || t_cg_graph.g[0].exec == nullptr) {
-        t_cg_graph.invalidate(1);
-        SFEM_TRY(graph_capture(st, t_cg_graph.g[0], iteration));
-        t_cg_graph.key = key;
+      key.a[6] = b; key.a[7] = st;
+      key.n = n; key.nnz = nnz; key.degree = mg ? mg->degree : 0; key.nranks = D.nranks; key.epoch = graph_epoch();
+      if (!(gc.key == key) || gc.g.empty() || gc.g[0].exec == nullptr) {
+        gc.invalidate(1);
+        SFEM_TRY(graph_capture(st, gc.g[0], iteration));
+        gc.key = key;
       }
     }
     bool done = false;
     for (it = 1; it <= maxit && !done; ++it) {
-      if (use_graph) SFEM_TRY(graph_launch(t_cg_graph.g[0], st));
+      if (use_graph) SFEM_TRY(graph_launch(gc.g[0], st));
       else SFEM_TRY(iteration());
       SFEM_TRY(t_poll.post(it & 1, S + 4, st));
       if (it > 1) {
@@ -417,13 +408,15 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
     return SFEM_OK;
   };
   const bool use_graph = graphs_enabled();
+  GraphCache& gc = mg ? mg->gmres_graph : t_gmres_graph;
   if (use_graph) {
     GraphKey key;
-    key.a[0] = rowptr; key.a[1] = cols; key.a[2] = vals; key.a[3] = mg; key.a[4] = t_ws.ptr;
-    key.a[5] = (const void*)(uintptr_t)n; key.a[6] = (const void*)(uintptr_t)m; key.a[7] = st;
-    if (!(t_gmres_graph.key == key) || (int)t_gmres_graph.g.size() != m) {
-      t_gmres_graph.invalidate(m);
-      t_gmres_graph.key = key;
+    key.a[0] = rowptr; key.a[1] = cols; key.a[2] = vals; key.a[3] = mg; key.a[4] = t_ws.ptr; key.a[7] = st;
+    key.n = n; key.m = m; key.nnz = nnz; key.degree = mg ? mg->degree : 0; key.nranks = dist_dev().nranks;
+    key.epoch = graph_epoch();
+    if (!(gc.key == key) || (int)gc.g.size() != m) {
+      gc.invalidate(m);
+      gc.key = key;
     }
   }
   int total = 0;
@@ -443,7 +436,7 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
     int queued = 0, conv_at = -1;
     for (int j = 0; j < m && total + j < maxit; ++j) {
       if (use_graph) {
-        GraphExec& ge = t_gmres_graph.g[j];
+        GraphExec& ge = gc.g[j];
         if (ge.exec == nullptr) SFEM_TRY(graph_capture(st, ge, [&]() { return arnoldi(j); }));
         SFEM_TRY(graph_launch(ge, st));
       } else {

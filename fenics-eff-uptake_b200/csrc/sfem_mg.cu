@@ -181,6 +181,7 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
     set_error("sfem_mg_create: bad arguments");
     return nullptr;
   }
+  graph_epoch_bump();
   sfem_mg* mg = new sfem_mg();
   mg->degree = cheb_degree;
   mg->ratio = eig_ratio;
@@ -251,6 +252,7 @@ int sfem_mg_set_tail(sfem_mg_t mg, sfem_mg_t tail, int n_tail, int P_nnz, const 
   MgLevel& L = mg->levels.back();
   L.P.nrows = L.A.nrows; L.P.ncols = n_tail; L.P.nnz = P_nnz; L.P.rowptr = P_rowptr; L.P.cols = P_cols; L.P.vals = P_vals;
   L.R.nrows = n_tail; L.R.ncols = L.A.nrows; L.R.nnz = R_nnz; L.R.rowptr = R_rowptr; L.R.cols = R_cols; L.R.vals = R_vals;
+  graph_epoch_bump();
   mg->tail = tail;
   mg->n_tail = n_tail;
   cudaFree(mg->tail_b); cudaFree(mg->tail_x);
@@ -280,6 +282,7 @@ int sfem_mg_lambda_max(sfem_mg_t mg, double* h_out) {
 
 void sfem_mg_destroy(sfem_mg_t mg) {
   if (!mg) return;
+  graph_epoch_bump();                       // graphs of OTHER handles may replay this one (Stokes velocity block, dist tail)
   for (MgLevel& L : mg->levels) {
     cudaFree(L.dinv); cudaFree(L.r); cudaFree(L.d0); cudaFree(L.d1); cudaFree(L.x); cudaFree(L.b); cudaFree(L.coef);
   }

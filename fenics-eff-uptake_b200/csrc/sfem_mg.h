@@ -2,6 +2,7 @@
 #pragma once
 #include "sfem_common.cuh"
 #include "sfem_internal.h"
+#include "sfem_graph.h"
 
 #include <vector>
 
@@ -37,6 +38,8 @@ struct sfem_mg {
   int n_tail = 0;
   double* tail_b = nullptr;
   double* tail_x = nullptr;
+  // captured Krylov iteration bodies preconditioned by this handle (owned here: destroyed with the handle)
+  sfem::GraphCache cg_graph, gmres_graph;
 };
 
 namespace sfem {

@@ -362,6 +362,7 @@ int sfem_sell_register(const int* rowptr, const double* csr_vals, int nrows, int
   g_plans[rowptr] = P;
   g_by_vals[csr_vals] = rowptr;
   g_ndirty.fetch_add(1);
+  graph_epoch_bump();                       // captured launch sequences baked in the engine choice for this address
   return SFEM_OK;
 }
 
@@ -372,6 +373,7 @@ void sfem_sell_unregister(const int* rowptr) {
   if (it->second.dirty) g_ndirty.fetch_sub(1);
   g_by_vals.erase(it->second.csr_vals);
   g_plans.erase(it);
+  graph_epoch_bump();
 }
 
 int sfem_sell_mark_dirty(const int* rowptr) {

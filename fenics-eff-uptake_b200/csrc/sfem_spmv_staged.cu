@@ -363,18 +363,21 @@ int sfem_staged_register(const int* rowptr, int nrows, const int* tile_row, int 
   P.cap = ((cap_nnz + 3) & ~3) + 8;          // slack for rounding the span to 16 bytes at both ends
   std::lock_guard<std::mutex> lk(g_plan_mu);
   g_plans[rowptr] = P;
+  graph_epoch_bump();
   return SFEM_OK;
 }
 
 /* matrices with fewer tiles than this use the vector engine (<= 0: default = SM count); returns the old value */
 int sfem_staged_set_min_tiles(int min_tiles) {
   int old = g_min_tiles.exchange(min_tiles < 0 ? 0 : min_tiles);
+  graph_epoch_bump();
   return old == -2 ? 0 : old;
 }
 
 void sfem_staged_unregister(const int* rowptr) {
   std::lock_guard<std::mutex> lk(g_plan_mu);
   g_plans.erase(rowptr);
+  graph_epoch_bump();
 }
 
 }  // extern "C"

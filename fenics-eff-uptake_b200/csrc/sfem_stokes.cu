@@ -234,6 +234,8 @@ struct sfem_stokes {
   WorkStream ws;
   GraphExec iter[2];
   const double* graph_x = nullptr;     // the x pointer baked into the graphs
+  unsigned long long graph_epoch = 0;  // registry epoch of their capture (sfem_graph.h)
+  int graph_nranks = 0;
   int npu = 0, npp = 0;
 };
 
@@ -381,9 +383,12 @@ int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, 
   double eta = gamma1;
   const bool use_graph = graphs_enabled();
   if (gamma1 > 0.0 && maxit > 0) {
-    if (use_graph && (h->iter[0].exec == nullptr || h->graph_x != x)) {
+    if (use_graph && (h->iter[0].exec == nullptr || h->graph_x != x || h->graph_epoch != graph_epoch() ||
+                      h->graph_nranks != dist_dev().nranks)) {
       for (int q = 0; q < 2; ++q) SFEM_TRY(graph_capture(st, h->iter[q], [&]() { return st_iteration(h, q, x, st); }));
       h->graph_x = x;
+      h->graph_epoch = graph_epoch();
+      h->graph_nranks = dist_dev().nranks;
     }
     const double target = rtol * gamma1;
     bool done = false;

@@ -39,6 +39,10 @@ std::vector<ProfRec> g_prof;
 size_t g_prof_max = 0;
 }  // namespace
 
+namespace { std::atomic<unsigned long long> g_graph_epoch{1}; }
+unsigned long long graph_epoch() { return g_graph_epoch.load(std::memory_order_acquire); }
+void graph_epoch_bump() { g_graph_epoch.fetch_add(1, std::memory_order_acq_rel); }
+
 bool profiling_active() { return g_prof_on.load(std::memory_order_relaxed); }
 bool graphs_enabled() {
   static int env = -1;
@@ -309,6 +313,26 @@ int sfem_profile_stop(int cap, int* h_cat, double* h_bytes, float* h_ms) {
   g_prof.clear();
   return n;
 }
+
+namespace sfem {
+__global__ void __launch_bounds__(kThreads) k_vec_select(int n, const unsigned char* __restrict__ flag, const double* a,
+                                                         const double* b, double* out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = flag[i] ? a[i] : (b ? b[i] : 0.0);
+}
+}  // namespace sfem
+
+int sfem_vec_select(int n, const unsigned char* flag, const double* a, const double* b, double* out, void* stream) {
+  if (n < 0 || (n > 0 && (!flag || !a || !out))) { set_error("vec_select: bad arguments"); return SFEM_ERR_ARG; }
+  if (n == 0) return SFEM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  { Prof prof(PC_VEC, 25.0 * n, st);
+  k_vec_select<<<grid_for(n, kThreads * 4), kThreads, 0, st>>>(n, flag, a, b, out); }
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int sfem_vec_copy(int n, const double* x, double* y, void* stream) { return vec_copy(n, x, y, (cudaStream_t)stream); }
 
 int sfem_vec_axpby(int n, double a, const double* x, double b, double* y, void* stream) {
   return vec_axpby(n, a, x, b, y, (cudaStream_t)stream);

@@ -34,9 +34,24 @@ def _plan(mesh_results, domain_type):
     return cache[key]
 
 
+def _mu_key(mu_val):
+    if mu_val is None:
+        return 0.0
+    if np.isscalar(mu_val) or isinstance(mu_val, Constant):
+        return float(mu_val)
+    return ('expr', id(mu_val))
+
+
+def _field_key(f):
+    """Identity + edit counter of a Function (``vector().set_local`` etc. bump the counter, so edited fields are
+    never served stale functionals)."""
+    return None if f is None else (id(f), getattr(f, '_version', 0))
+
+
 def evaluate_functionals(c, u, mesh_results, domain_type, D_val, mu_val):
-    """All facet + cell integrals of one run (cached on ``c``): returns (F[groups,8], M[markers,2])."""
-    key = (id(u), float(D_val), id(mu_val) if not np.isscalar(mu_val) else float(mu_val), domain_type)
+    """All facet + cell integrals of one run (cached on ``c``): returns (F[groups,8], M[markers,2]).  The cache key
+    holds every argument, so the functions below stay pure in (c, u, D, mu) like the reference's."""
+    key = (_field_key(c), _field_key(u), float(D_val), _mu_key(mu_val), domain_type)
     cached = getattr(c, '_functionals', None)
     if cached is not None and cached[0] == key:
         return cached[1], cached[2]
@@ -56,9 +71,32 @@ def evaluate_functionals(c, u, mesh_results, domain_type, D_val, mu_val):
         vals[bottom] = evaluate_expression(mu_val, X[bottom])
         mu_nodal = plan.ctx.up(vals, np.float64)
     F, M = plan.evaluate(cd, ux, uy, D=float(D_val), mu_const=mu_const, mu_nodal=mu_nodal)
-    c._functionals = (key, F, M)
-    c._functionals_any = (F, M)
+    c._functionals = (key, F, M, u)                      # holding `u` keeps its id() from being recycled
     return F, M
+
+
+def _mesh_results_of(c):
+    """Marker containers of the mesh ``c`` lives on (attached by ``hostmesh.build_markers``), for the reference
+    functions whose signature carries only ``measures``."""
+    mesh = c.function_space().mesh()
+    mk = getattr(mesh, '_sfem_markers', None)
+    if mk is None:
+        raise ValueError("the mesh carries no marker sets (build them with hostmesh.build_markers / MeshGenerator)")
+    mr = {'mesh': mesh}
+    mr.update(mk)
+    return mr, ('sulcus' if 'domain_markers' in mk else 'rectangular')
+
+
+def _cached_or_evaluate(c, mu_val=None, need_mu=False):
+    """(F, M) of ``c``: the cached evaluation when it still matches the field (and, if ``need_mu``, the given mu);
+    otherwise a fresh one (u = None, D = 1: the mu c, c and mass integrals do not depend on them)."""
+    cached = getattr(c, '_functionals', None)
+    if cached is not None and cached[0][0] == _field_key(c) and (not need_mu or cached[0][3] == _mu_key(mu_val)):
+        return cached[1], cached[2]
+    mr, domain_type = _mesh_results_of(c)
+    u = cached[3] if cached is not None and cached[0][0] == _field_key(c) else None
+    D = cached[0][2] if u is not None else 1.0
+    return evaluate_functionals(c, u, mr, domain_type, D, mu_val if need_mu else 0.0)
 
 
 def _pf(F, g):
@@ -112,14 +150,15 @@ def compute_flux_metrics(c, u, mesh_results, domain_type, measures, D_val, mu_va
 
 
 def compute_uptake_flux_bottom(c, measures, mu_val):
-    F, _ = c._functionals_any
+    """``assemble(mu c ds(4))`` (reference analysis.py:307-311): pure in (c, mu_val)."""
+    F, _ = _cached_or_evaluate(c, mu_val, need_mu=True)
     return float(F[_G['bottom'], _UPT])
 
 
 def compute_uptake_flux_segments(c, measures, mu_val):
     """Uptake flux mu c over the external bottom segments bottom_left / sulcus / bottom_right and their sum
-    (reference analysis.py:313-333); read from the functionals of the last ``compute_flux_metrics`` on ``c``."""
-    F, _ = c._functionals_any
+    (reference analysis.py:313-333): pure in (c, mu_val)."""
+    F, _ = _cached_or_evaluate(c, mu_val, need_mu=True)
     bl, su, br = (float(F[_G[k], _UPT]) for k in ('bottom_left', 'sulcus', 'bottom_right'))
     return {'bottom_left': bl, 'sulcus': su, 'bottom_right': br, 'total': bl + su + br}
 
@@ -151,14 +190,7 @@ def sample_mu_along_bottom(results, n_points=500, y_at_bottom=0.0, save_csv_path
 # ====================================================================== mass metrics
 def compute_mass_metrics(c, measures, domain_type):
     """Reference analysis.py:677-719."""
-    cached = getattr(c, '_functionals_any', None)
-    if cached is None:
-        mesh = c.function_space().mesh()
-        mr = {'mesh': mesh}
-        mr.update(getattr(mesh, '_sfem_markers', {}))
-        _, M = evaluate_functionals(c, None, mr, domain_type, 1.0, 0.0)
-    else:
-        M = cached[1]
+    _, M = _cached_or_evaluate(c)
     if domain_type == 'sulcus':
         sm, sa = float(M[1, 0]), float(M[1, 1])
         rm, ra = float(M[2, 0]), float(M[2, 1])
@@ -343,7 +375,7 @@ def compute_velocity_metrics(u, mesh_results, params, rng=None):
 # ====================================================================== mu_eff
 def compute_concentration_profiles(results):
     """Line integrals of c along y=0 with the channel-side trace on the mouth (analysis.py:884-946)."""
-    F, _ = results['c']._functionals_any
+    F, _ = _cached_or_evaluate(results['c'])
     e, m = _G['y0_ext'], _G['mouth']
     C_ext, C_m, L_ext, L_m = (float(F[e, _C]), float(F[m, _C]), float(F[e, _LEN]), float(F[m, _LEN]))
     tot_L = L_ext + L_m

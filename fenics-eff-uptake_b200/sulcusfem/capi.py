@@ -63,6 +63,8 @@ SIGNATURES = {
     'sfem_vec_dot': (_i, [_i, _p, _p, C.POINTER(_d), _p]),
     'sfem_vec_set': (_i, [_i, _d, _p, _p]),
     'sfem_vec_pointwise_mul': (_i, [_i, _d, _p, _p, _p, _p]),
+    'sfem_vec_select': (_i, [_i, _p, _p, _p, _p, _p]),
+    'sfem_vec_copy': (_i, [_i, _p, _p, _p]),
     'sfem_dense_inverse_csr': (_i, [_i, _p, _p, _p, _p, _p]),
     'sfem_extract_diag_inv': (_i, [_i, _p, _p, _p, _p, _p]),
     'sfem_postprocess_concentration': (_i, [_i, _p, _i, C.POINTER(_d), _p]),

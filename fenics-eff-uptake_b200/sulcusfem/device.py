@@ -248,7 +248,7 @@ class ScalarLevel:
                 capi.check(fn(self.nf, P(self.fgeo), P(self.fdofs), float(mu_const), P(mu_nodal), int(bool(clamp)),
                               P(F), ctx.stream), 'sfem_facet_robin')
             else:
-                F.zero_()
+                capi.check(lib.sfem_vec_set(int(F.numel()), 0.0, P(F), ctx.stream), 'sfem_vec_set')
         capi.check(lib.sfem_gather_csr(self.A.nnz, P(self.contrib_ptr), P(self.contrib_code), P(self.E), P(self.A.vals),
                                        ctx.stream), 'sfem_gather_csr')
 
@@ -383,7 +383,7 @@ class ScalarProblem:
         if fine:
             f.set_bc_values(bc_values if bc_values is not None else {i: 0.0 for i in f.bc_dofs})
             f.assemble(D, ux, uy, mu_const, mu_nodal, clamp, robin=robin)
-            f.rhs.zero_()
+            capi.check(self.ctx.lib.sfem_vec_set(f.n, 0.0, P(f.rhs), self.ctx.stream), 'sfem_vec_set')
             f.apply_bc(bc_mode)
         self.bc_mode = bc_mode
         vel = self._coarse_velocity(ux, uy) if ux is not None else [(None, None)] * len(self.transfers)
@@ -398,11 +398,10 @@ class ScalarProblem:
 
     def solve(self, method='cg', rtol=1e-13, maxit=400, restart=80, x0=None):
         ctx, f = self.ctx, self.fine
-        torch = _torch()
-        if x0 is None:
-            self.x.copy_(f.bc_val * f.bc_flag.to(torch.float64))
+        if x0 is None:          # initial guess: the Dirichlet values, zero elsewhere
+            capi.check(ctx.lib.sfem_vec_select(f.n, P(f.bc_flag), P(f.bc_val), None, P(self.x), ctx.stream), 'sfem_vec_select')
         else:
-            self.x.copy_(x0)
+            capi.check(ctx.lib.sfem_vec_copy(f.n, P(x0), P(self.x), ctx.stream), 'sfem_vec_copy')
         info = (C.c_double * 4)()
         A = f.A
         if method == 'cg':
@@ -508,7 +507,6 @@ class StokesProblem:
         gil = np.zeros(self.n)
         gil[0:2 * n2:2], gil[1:2 * n2:2] = g[:n2], g[n2:2 * n2]
         self.flag_il = self.ctx.up(fil, np.uint8)
-        self.flag_il_bool = self.flag_il.bool()
         self.g_il.copy_(self.ctx.up(gil, np.float64))
         self._zero_n2 = self.ctx.zeros(n2)
         self._scratch_n2 = self.ctx.zeros(n2)
@@ -611,10 +609,10 @@ class StokesProblem:
             capi.check(lib.sfem_gather_csr(M.nnz, P(cp), P(cc), P(self.EB), P(M.vals), ctx.stream), 'sfem_gather_csr')
         # lifting  b = -[K g_u ; B g_u]  (g_u = Dirichlet values, zero elsewhere), then b = g on the Dirichlet rows
         r = self.rhs_il
-        r.zero_()
+        capi.check(lib.sfem_vec_set(self.n, 0.0, P(r), ctx.stream), 'sfem_vec_set')
         K.spmv(self.g_il[:2 * n2], y=r[:2 * n2], b=r[:2 * n2], mode=1, nb=2)      # r_u = 0 - K g_u (both components)
         self.B.spmv(self.g_il[:2 * n2], y=r[2 * n2:], b=r[2 * n2:], mode=1)        # r_p = 0 - B g_u
-        torch.where(self.flag_il_bool, self.g_il[:2 * n2], r[:2 * n2], out=r[:2 * n2])
+        capi.check(lib.sfem_vec_select(2 * n2, P(self.flag_il), P(self.g_il), P(r), P(r), ctx.stream), 'sfem_vec_select')
         # symmetric elimination of the blocks
         capi.check(lib.sfem_apply_dirichlet(n2, K.nnz, P(K.rowptr), P(K.cols), P(K.vals), P(self._scratch_n2), P(f.bc_flag),
                                             P(self._zero_n2), 1, ctx.stream), 'sfem_apply_dirichlet')
@@ -624,7 +622,7 @@ class StokesProblem:
                                              ctx.stream), 'sfem_csr_zero_flagged')
         # blocked copy of the right-hand side (public layout [ux | uy | p])
         capi.check(lib.sfem_vec_deinterleave2(n2, P(r), P(self.rhs[:n2]), P(self.rhs[n2:2 * n2]), ctx.stream), 'deinterleave')
-        self.rhs[2 * n2:].copy_(r[2 * n2:])
+        capi.check(lib.sfem_vec_copy(nv, P(r[2 * n2:]), P(self.rhs[2 * n2:]), ctx.stream), 'sfem_vec_copy')
         self._assemble_preconditioner()
 
     def solve(self, rtol=1e-12, maxit=2000):
@@ -633,14 +631,14 @@ class StokesProblem:
         if getattr(self, 'bc_mode', None) != 1:
             raise capi.SulcusFemError("StokesProblem.solve needs assemble(bc_mode=1)")
         n2 = self.n2
-        self.x_il.copy_(self.g_il)                                    # initial guess: Dirichlet values, zero elsewhere
+        capi.check(lib.sfem_vec_copy(self.n, P(self.g_il), P(self.x_il), ctx.stream), 'sfem_vec_copy')   # initial guess: Dirichlet values
         info = (C.c_double * 4)()
         rc = lib.sfem_stokes_solve(self.handle, P(self.rhs_il), P(self.x_il), float(rtol), int(maxit), info, ctx.stream)
         capi.check(rc, 'sfem_stokes_solve')
         self.last_info = {'iterations': int(info[0]), 'relres': float(info[1]), 'converged': bool(info[2]),
                           'estimate': float(info[3]), 'method': 'minres'}
         capi.check(lib.sfem_vec_deinterleave2(n2, P(self.x_il), P(self.x[:n2]), P(self.x[n2:2 * n2]), ctx.stream), 'deinterleave')
-        self.x[2 * n2:].copy_(self.x_il[2 * n2:])
+        capi.check(lib.sfem_vec_copy(self.nv, P(self.x_il[2 * n2:]), P(self.x[2 * n2:]), ctx.stream), 'sfem_vec_copy')
         return self.x[:n2], self.x[n2:2 * n2], self.x[2 * n2:]
 
     def __del__(self):

@@ -201,23 +201,29 @@ class _Vector:
     def get_local(self):
         return self._f.values.copy()
 
+    def _edited(self):
+        f = self._f
+        f._dev = None                       # device copy and cached functionals describe the old values
+        f._functionals = None
+        f._version = getattr(f, '_version', 0) + 1
+
     def set_local(self, a):
         self._f.values[:] = np.asarray(a, dtype=np.float64)
-        self._f._dev = None
+        self._edited()
 
     def apply(self, mode):
         return None
 
     def zero(self):
         self._f.values[:] = 0.0
-        self._f._dev = None
+        self._edited()
 
     def size(self):
         return len(self._f.values)
 
     def __setitem__(self, key, value):
         self._f.values[key] = value
-        self._f._dev = None
+        self._edited()
 
     def __getitem__(self, key):
         return self._f.values[key]
@@ -236,6 +242,8 @@ class Function:
         if len(self.values) != V.dim():
             raise ValueError("value array does not match the space dimension")
         self._dev = None
+        self._version = 0
+        self._functionals = None
         self._extrapolate = False
         self._locator = None
 

@@ -210,6 +210,7 @@ def build_markers(mesh: HostMesh, width: float, height: float, xL: float, xR: fl
         out['y0_markers'] = mark_facets(mesh, ['y0_line'], pred)
         cy = mesh.cell_midpoints()[:, 1]
         out['domain_markers'] = MeshMarkers(np.where(cy <= 0.0, 1, 2).astype(np.int32), 2)
+    mesh._sfem_markers = out                 # analysis functions whose reference signature carries only `measures`
     return out
 
 

@@ -121,9 +121,26 @@ def _solve_scalar(mesh_results, C, D, u, mu=None, mu_function=None, clamp=False,
     prob.assemble(float(D), ux, uy, bc_values={1: 1.0, 2: 0.0}, **kw)
     method = 'cg' if ux is None else 'fgmres'
     x = prob.solve(method, rtol=RTOL)
-    if not prob.last_info['converged']:
-        raise RuntimeError(f"Krylov solver did not converge: {prob.last_info}")
+    _accept_scalar(prob.last_info)
     return prob, x
+
+
+# A TRUE relative residual of 10 * RTOL = 1e-12 sits close to the FP64 floor eps * ||A|| ||x|| / ||b|| of large refined
+# (or row-partitioned) systems; the reference's LU never "fails" there.  A recurrence that stagnates below this
+# parity-safe level (concentration error <= ~1200x the residual, profiles/r01_tolerance_study.md) is accepted with a
+# warning; anything above it is an error.
+PARITY_SAFE_RELRES = 5e-12
+
+
+def _accept_scalar(info):
+    if info['converged']:
+        return
+    if np.isfinite(info['relres']) and info['relres'] <= PARITY_SAFE_RELRES:
+        import warnings
+        warnings.warn(f"Krylov recurrence stagnated at true relative residual {info['relres']:.2e} "
+                      f"(target {10 * RTOL:.0e}); accepted, parity-safe: {info}")
+        return
+    raise RuntimeError(f"Krylov solver did not converge: {info}")
 
 
 def _post(prob, x, fix_nonfinite):
@@ -230,8 +247,15 @@ def stokes_solver(mesh_results, W, L_domain, H, mesh_type="sulcus"):
             prob._inflow_H = float(H)
         prob.assemble(bc_mode=1)
         ux, uy, p = prob.solve(rtol=STOKES_RTOL)
-        if not np.isfinite(prob.last_info['relres']) or prob.last_info['relres'] > 1e-9:
-            raise RuntimeError(f"MINRES stalled: {prob.last_info}")
+        info = prob.last_info
+        if not info['converged']:
+            # MINRES stopped on maxit / stagnation above STOKES_RTOL (preconditioned residual).  The u / p errors track
+            # that residual one to one, so only a true residual within 10x of the target is still parity-safe.
+            if not np.isfinite(info['relres']) or info['relres'] > 10.0 * STOKES_RTOL:
+                raise RuntimeError(f"MINRES stalled: {info}")
+            import warnings
+            warnings.warn(f"MINRES stopped before the preconditioned residual reached {STOKES_RTOL:.0e}; true relative "
+                          f"residual {info['relres']:.2e} accepted: {info}")
         n2 = prob.n2
         u = Function(VectorFunctionSpace(mesh, 'P', 2), prob.ctx.down(prob.x[:2 * n2]))
         u._dev = (ux.clone(), uy.clone())

@@ -166,6 +166,10 @@ int sfem_vec_axpby(int n, double a, const double* x, double b, double* y, void* 
 int sfem_vec_dot(int n, const double* x, const double* y, double* h_out, void* stream);    /* syncs stream */
 int sfem_vec_set(int n, double a, double* x, void* stream);                                /* x = a */
 int sfem_vec_pointwise_mul(int n, double a, const double* d, const double* x, double* y, void* stream); /* y = a d.*x */
+/* out[i] = flag[i] ? a[i] : (b ? b[i] : 0): Dirichlet values as initial guess (DirichletBC.apply on a vector,
+ * solvers.py:30-31) and the Dirichlet rows of a lifted right-hand side; out may alias a or b */
+int sfem_vec_select(int n, const unsigned char* flag, const double* a, const double* b, double* out, void* stream);
+int sfem_vec_copy(int n, const double* x, double* y, void* stream);                          /* y = x */
 /* out (n x n row-major) = inverse of a small CSR matrix (coarsest multigrid level, n <= 2048) */
 int sfem_dense_inverse_csr(int n, const int* rowptr, const int* cols, const double* vals, double* out, void* stream);
 int sfem_extract_diag_inv(int n, const int* rowptr, const int* cols, const double* vals, double* dinv, void* stream);

@@ -403,6 +403,36 @@ def test_functionals_match_oracle(ctx, small):
     close(Cc[1, 1], refm['sulcus_area']); close(Cc[2, 1], refm['rectangle_area'])
 
 
+def test_analysis_functions_are_pure_in_their_arguments(ctx, small):
+    """compute_uptake_flux_* take (c, measures, mu_val) like analysis.py:307-333: the result must not depend on which
+    evaluation ran last on ``c``, and editing ``c`` through ``vector()`` must not serve stale functionals."""
+    from oracle import cpu_oracle as co
+    from sulcusfem import analysis
+    from sulcusfem.fem import Function, FunctionSpace
+    mesh, mk, om = small
+    X = om.p2_dof_coords()
+    cv = 1.0 - X[:, 0] / 10 + 0.1 * np.sin(5 * X[:, 0]) * np.cos(3 * X[:, 1])
+    omk = {k: v.values for k, v in mk.items()}
+    mr = {'mesh': mesh}
+    mr.update(mk)
+    c = Function(FunctionSpace(mesh, 'CG', 2), cv.copy())
+    ref = co.flux_metrics(om, omk, 'sulcus', 1.0, cv, mu=0.7)
+    # no prior evaluation at all
+    assert abs(analysis.compute_uptake_flux_bottom(c, {}, 0.7) - ref['uptake_flux']) < 1e-11
+    # an evaluation with mu = 0 in between (physical fluxes) must not leak into the uptake integrals
+    analysis.compute_physical_flux_boundary(c, None, mr, {}, 4, 1.0)
+    assert abs(analysis.compute_uptake_flux_bottom(c, {}, 0.7) - ref['uptake_flux']) < 1e-11
+    seg = analysis.compute_uptake_flux_segments(c, {}, 0.7)
+    for k in ('bottom_left', 'sulcus', 'bottom_right'):
+        assert abs(seg[k] - ref['sulcus_specific']['uptake_flux'][k]) < 1e-11
+    assert abs(analysis.compute_uptake_flux_bottom(c, {}, 1.4) - 2 * ref['uptake_flux']) < 1e-11
+    m0 = analysis.compute_mass_metrics(c, {}, 'sulcus')['total_mass']
+    # edit the field: everything must follow
+    c.vector().set_local(2.0 * cv)
+    assert abs(analysis.compute_uptake_flux_bottom(c, {}, 0.7) - 2 * ref['uptake_flux']) < 1e-11
+    assert abs(analysis.compute_mass_metrics(c, {}, 'sulcus')['total_mass'] - 2 * m0) < 1e-11
+
+
 def test_mailbox_halo_exchange_and_vector_allreduce_emulated(ctx):
     """Two 'ranks' inside one process on one GPU: the send halves of all ranks run first, then the
     wait + unpack halves (the production kernels do both in one launch, one rank per GPU)."""
