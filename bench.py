@@ -294,8 +294,121 @@ def same_mesh_leg(ctx, h, flush_l2, reps=5):
 
 
 def run_dd_strong(args, case, rank, world, dist, flush_l2):
-    """Filled in below (config 5)."""
-    return None
+    """BASELINE config 5 on the driver's clock: ONE case (the bench step: Stokes + adv-diff + functionals, mu = 1)
+    row-partitioned over all ranks -- peer-memory halo exchange + in-kernel all-reduces (csrc/sfem_dist.cu), NCCL only
+    for the all-gather of the fields between the replicated stages -- against the same step on one GPU.
+    Returns one record per refinement level: strong-scaling efficiency t_1 / (N t_N) and the relative L2 distance of
+    the distributed fields from the single-GPU ones."""
+    import torch
+    from sulcusfem.dist import DistScalarProblem, DistStokesProblem, DistWorld, num_distributed_levels, plan_partitions
+    ctx = case.ctx
+    out = []
+    refines = [args.refine] + [int(r) for r in str(args.dd_refine).split(',') if r.strip() != '' and int(r) != args.refine]
+    for refine in refines:
+        cs = case if refine == args.refine else Case(ctx, args.h, refine, MU)
+        mu_saved, cs.mu = cs.mu, MU                       # every rank: the SAME case
+        st, sc, plan, D = cs.stokes, cs.scalar, cs.plan, cs.D
+        rb = args.dd_replicate_below
+
+        def timed(fn, reps):
+            ts = []
+            for _ in range(reps):
+                flush_l2()
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t = torch.tensor([float(np.median(ts))], dtype=torch.float64, device=ctx.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        # single-GPU time of the same case (every rank runs it; no communicator is active yet)
+        reps = max(3, min(args.steps, 5))
+        for _ in range(2):
+            cs.step()
+        t1 = timed(cs.step, reps)
+        info1 = {k: dict(v) for k, v in cs.info.items()}
+        ref = [t.clone() for t in (st.x[:st.n2], st.x[st.n2:2 * st.n2], sc.x)]
+        t0 = time.perf_counter()
+        nd_v = num_distributed_levels(st.vel, rb)
+        nd_c = num_distributed_levels(sc, rb)
+        vec_cap = max(2 * st.vel.levels[nd_v].n, sc.levels[nd_c].n)
+        wd = DistWorld(ctx, rank, world, vec_cap)
+        ds = DistStokesProblem(st, wd, replicate_below=rb)
+        dc = DistScalarProblem(sc, rank, world, world=wd, nb=1, plan=plan_partitions(sc, world, rb))
+        wd.commit()
+        ds.finalize()
+        dc.finalize()
+        torch.cuda.synchronize()
+        t_plan = time.perf_counter() - t0
+        marks = {}
+
+        def dd_step(ev=None):
+            def mark(name):
+                if ev is not None:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    ev.append((name, e))
+            mark('start')
+            st.assemble(bc_mode=1)
+            ds.refresh()
+            mark('stokes_assemble+extract')
+            ds.solve(rtol=STOKES_RTOL)
+            mark('stokes_minres')
+            ux, uy, p = ds.gather()
+            mark('allgather_u')
+            sc.assemble(D, ux, uy, mu_const=MU, bc_values={1: 1.0, 2: 0.0})
+            dc.refresh()
+            mark('advdiff_assemble+extract')
+            dc.solve('fgmres', rtol=RTOL)
+            mark('advdiff_fgmres')
+            c = dc.gather()
+            F, M = plan.evaluate(c, ux, uy, D=D, mu_const=MU)
+            mark('allgather_c+functionals')
+            return ux, uy, p, c, F
+
+        for _ in range(2):
+            dd_step()
+        tN = timed(dd_step, reps)
+        ev = []
+        flush_l2(); dist.barrier(); torch.cuda.synchronize()
+        ux, uy, p, c, F = dd_step(ev)
+        torch.cuda.synchronize()
+        phases = {ev[i][0]: ev[i - 1][1].elapsed_time(ev[i][1]) for i in range(1, len(ev))}
+
+        def rel(a, b):
+            return float(((a - b).norm() / b.norm()).item())
+        lu = ds.vel.parts[0]
+        rec = {"refine": refine, "dofs": int(cs.ndof), "n_gpus": world, "ms_1gpu": t1, "ms_ngpu": tN,
+               "efficiency": t1 / (world * tN), "speedup": t1 / tN, "dofs_per_s": cs.ndof / (tN / 1e3),
+               "rel_l2_vs_single": {"ux": rel(ux, ref[0]), "uy_abs_over_ux": float(((uy - ref[1]).norm() / ref[0].norm()).item()),
+                                    "c": rel(c, ref[2])},
+               "iterations": {"single": {k: v['iterations'] for k, v in info1.items()},
+                              "distributed": {"stokes": ds.last_info['iterations'], "advdiff": dc.last_info['iterations']}},
+               "phases_ms_last_step": phases,
+               "solve_only": {"ms_ngpu": phases['stokes_minres'] + phases['advdiff_fgmres']},
+               "distributed_levels": {"velocity": ds.vel.nd, "concentration": dc.nd, "replicate_below": rb},
+               "exchanges_per_vcycle": {"velocity": 6 * ds.vel.nd - 2, "concentration": 6 * dc.nd - 2,
+                                        "note": "per row-partitioned level: Chebyshev step, residual, restriction, prolongation, "
+                                                "residual + Chebyshev step of the post-smoother (the last level restricts / prolongs "
+                                                "through one vector all-reduce instead)"},
+               "halo_bytes": {"velocity_level0_per_exchange": 16 * int(len(lu.ghost)), "owned_velocity_dofs": int(lu.n_own),
+                              "concentration_level0_per_exchange": 8 * int(len(dc.parts[0].ghost))},
+               "plan_s": t_plan, "setup_s": cs.setup.get('total_s'),
+               "assembly": "replicated (every rank assembles the global operators, then extracts its rows)"}
+        rec["parity_ok"] = bool(rec["rel_l2_vs_single"]["ux"] <= 1e-10 and rec["rel_l2_vs_single"]["c"] <= 1e-10
+                                and rec["rel_l2_vs_single"]["uy_abs_over_ux"] <= 1e-10)
+        out.append(rec)
+        ds.close()
+        dc.close()
+        wd.close()
+        cs.mu = mu_saved
+        if cs is not case:
+            del cs
+        dist.barrier()
+    return out
 
 
 def run_gpu(args, rank, world):
@@ -482,6 +595,7 @@ def main():
     ap.add_argument('--same-h', type=float, default=0.02)   # same-mesh leg / cpu_baseline: the reference's default mesh size (385 k dofs)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-dd', action='store_true')         # N > 1: skip the domain-decomposed (config 5) leg
+    ap.add_argument('--dd-replicate-below', type=int, default=200000)   # multigrid levels below this many unknowns stay replicated
     ap.add_argument('--dd-refine', default=os.environ.get('SFEM_BENCH_DD_REFINE', ''))   # extra refinements for the dd leg, e.g. "3"
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

@@ -19,7 +19,7 @@
 namespace sfem {
 
 constexpr int kMaxRanks = 16;
-constexpr int kAllreduceMaxK = 8;
+constexpr int kAllreduceMaxK = 16;   // >= kMaxRanks: the Gershgorin all-gather of sfem_mg.cu publishes one slot per rank
 
 // device-visible description of the communicator (passed by value to kernels)
 struct DistDev {

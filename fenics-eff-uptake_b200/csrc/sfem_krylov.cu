@@ -98,10 +98,11 @@ __global__ void k_store_sum(const double* __restrict__ partial, int np, double* 
 
 // ================================================================== FGMRES
 // Hess layout (device): H[(m+1) x m] column-major (col j at H + j*(m+1)), cs[m], sn[m], g[m+1], misc[4]
-__global__ void __launch_bounds__(kThreads) k_multidot(int n, const double* __restrict__ V, int nvec,
+// (ld = stride between the basis vectors: n on one GPU, n_loc = owned + ghosts when row-partitioned)
+__global__ void __launch_bounds__(kThreads) k_multidot(int n, size_t ld, const double* __restrict__ V, int nvec,
                                                        const double* __restrict__ w, double* __restrict__ partial, int gx) {
   __shared__ double sh[33];
-  const double* v = V + (size_t)blockIdx.y * n;
+  const double* v = V + (size_t)blockIdx.y * ld;
   double acc = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc = fma(v[i], w[i], acc);
   const double t = block_sum(acc, sh);
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kThreads) k_multidot(int n, const double* __re
 }
 
 // one block per vector: hcol[i] (+)= sum partial[i][:]; hstep[i] = this pass's coefficient
+// (accumulate < 0: only hstep is written -- the multi-GPU path folds the GLOBAL sum into hcol in k_gs_allreduce)
 __global__ void k_gs_coeff(const double* __restrict__ partial, int gx, double* __restrict__ hcol,
                            double* __restrict__ hstep, int accumulate) {
   __shared__ double sh[33];
@@ -116,11 +118,32 @@ __global__ void k_gs_coeff(const double* __restrict__ partial, int gx, double* _
   const double t = block_sum_array(partial + (size_t)i * gx, gx, sh);
   if (threadIdx.x == 0) {
     hstep[i] = t;
-    hcol[i] = accumulate ? hcol[i] + t : t;
+    if (accumulate >= 0) hcol[i] = accumulate ? hcol[i] + t : t;
   }
 }
 
-__global__ void __launch_bounds__(kThreads) k_gs_update(int n, const double* __restrict__ V, int nvec,
+// multi-GPU: the nvec coefficients of one Gram-Schmidt pass are sums over the ranks; all-reduced in chunks of
+// kAllreduceMaxK by one thread (hstep = this pass's local sums -> global), then folded into the Hessenberg column
+__global__ void k_gs_allreduce(int nvec, double* __restrict__ hstep, double* __restrict__ hcol, int accumulate, DistDev D) {
+  __shared__ double old[kAllreduceMaxK];
+  for (int k0 = 0; k0 < nvec; k0 += kAllreduceMaxK) {
+    const int K = min(kAllreduceMaxK, nvec - k0);
+    if (threadIdx.x < K) old[threadIdx.x] = hstep[k0 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double v[kAllreduceMaxK];
+      for (int k = 0; k < K; ++k) v[k] = old[k];
+      dist_allreduce_scalars(D, v, K);            // summed in rank order: bit-identical on every rank
+      for (int k = 0; k < K; ++k) {
+        hstep[k0 + k] = v[k];
+        hcol[k0 + k] = accumulate ? hcol[k0 + k] + v[k] : v[k];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_gs_update(int n, size_t ld, const double* __restrict__ V, int nvec,
                                                         const double* __restrict__ hstep, double* __restrict__ w,
                                                         double* __restrict__ partial) {
   __shared__ double sh[33];
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) k_gs_update(int n, const double* __r
   double acc = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double wi = w[i];
-    for (int k = 0; k < nvec; ++k) wi = fma(-hs[k], V[(size_t)k * n + i], wi);
+    for (int k = 0; k < nvec; ++k) wi = fma(-hs[k], V[(size_t)k * ld + i], wi);
     w[i] = wi;
     acc = fma(wi, wi, acc);
   }
@@ -142,10 +165,11 @@ __global__ void __launch_bounds__(kThreads) k_gs_update(int n, const double* __r
 // misc[0] = 1/h_{j+1,j}, misc[1] = |g_{j+1}| (residual estimate)
 __global__ void k_gmres_givens(const double* __restrict__ p_ww, int np, int j, int m, double* __restrict__ H,
                                double* __restrict__ cs, double* __restrict__ sn, double* __restrict__ g,
-                               double* __restrict__ misc) {
+                               double* __restrict__ misc, DistDev D) {
   __shared__ double sh[33];
-  const double ww = block_sum_array(p_ww, np, sh);
+  double ww = block_sum_array(p_ww, np, sh);
   if (threadIdx.x == 0) {
+    dist_allreduce_scalars(D, &ww, 1);
     double* h = H + (size_t)j * (m + 1);
     const double hn = sqrt(ww);
     h[j + 1] = hn;
@@ -173,10 +197,12 @@ __global__ void k_scale_dev(int n, const double* __restrict__ scal, const double
 }
 
 // beta = sqrt(sum); g[0] = beta; misc[0] = 1/beta; misc[1] = beta
-__global__ void k_gmres_start(const double* __restrict__ partial, int np, double* __restrict__ g, double* __restrict__ misc) {
+__global__ void k_gmres_start(const double* __restrict__ partial, int np, double* __restrict__ g, double* __restrict__ misc,
+                              DistDev D) {
   __shared__ double sh[33];
-  const double t = block_sum_array(partial, np, sh);
+  double t = block_sum_array(partial, np, sh);
   if (threadIdx.x == 0) {
+    dist_allreduce_scalars(D, &t, 1);
     const double beta = sqrt(t);
     g[0] = beta;
     misc[0] = (beta > 0.0) ? 1.0 / beta : 0.0;
@@ -184,14 +210,14 @@ __global__ void k_gmres_start(const double* __restrict__ partial, int np, double
   }
 }
 
-__global__ void k_lincomb_add(int n, const double* __restrict__ Z, int nvec, const double* __restrict__ y,
+__global__ void k_lincomb_add(int n, size_t ld, const double* __restrict__ Z, int nvec, const double* __restrict__ y,
                               double* __restrict__ x) {
   extern __shared__ double ys[];
   for (int k = threadIdx.x; k < nvec; k += blockDim.x) ys[k] = y[k];
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double xi = x[i];
-    for (int k = 0; k < nvec; ++k) xi = fma(ys[k], Z[(size_t)k * n + i], xi);
+    for (int k = 0; k < nvec; ++k) xi = fma(ys[k], Z[(size_t)k * ld + i], xi);
     x[i] = xi;
   }
 }
@@ -350,10 +376,15 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
   SFEM_TRY(sell_ensure_all(user));          // dirty sliced-ELL mirrors are re-packed before any graph replay
   if (n <= 0 || restart < 1) { set_error("fgmres: bad arguments"); return SFEM_ERR_ARG; }
   if (mg && (!mg->ready || mg->nb != 1)) { set_error("fgmres: multigrid not set up (or nb != 1)"); return SFEM_ERR_ARG; }
-  if (dist_dev().nranks > 1) { set_error("fgmres: the row-partitioned (multi-GPU) path serves CG only in this version"); return SFEM_ERR_ARG; }
   Csr A; A.nrows = A.ncols = n; A.nnz = nnz; A.rowptr = rowptr; A.cols = cols; A.vals = vals;
+  // row-partitioned operator (multi-GPU): n = owned rows; every vector an SpMV reads (x, the z_j) carries the ghosts
+  // behind the owned entries, so all basis vectors use the stride n_loc and the reductions run over the owned part
+  const Halo* halo = find_halo(rowptr);
+  if (halo) A.ncols = halo->dev.n_loc;
+  const DistDev D = dist_dev();
+  if (D.nranks > 1 && !halo) { set_error("fgmres: a communicator is active but the matrix is not row-partitioned"); return SFEM_ERR_ARG; }
   const int m = restart;
-  const size_t nn = (size_t)n;
+  const size_t nn = (size_t)(halo ? halo->dev.n_loc : n);
   const int gx = grid_for(n, kThreads * 4, 2);
   const size_t small = (size_t)(m + 1) * m + 4 * (size_t)(m + 2) + 16;
   SFEM_TRY(t_ws.ensure((2 * (size_t)m + 3) * nn + (size_t)(m + 1) * gx + 2 * kMaxPartials + small + 64));
@@ -391,16 +422,20 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
     for (int pass = 0; pass < 2; ++pass) {
       dim3 grid(gx, nvec);
       { Prof prof(PC_VEC, 8.0 * n * (nvec + 1), st);
-      k_multidot<<<grid, kThreads, 0, st>>>(n, V, nvec, w, partial, gx); }
+      k_multidot<<<grid, kThreads, 0, st>>>(n, nn, V, nvec, w, partial, gx); }
       SFEM_LAUNCH_CHECK();
-      k_gs_coeff<<<nvec, kThreads, 0, st>>>(partial, gx, hcol, hstep, pass);
+      k_gs_coeff<<<nvec, kThreads, 0, st>>>(partial, gx, hcol, hstep, D.nranks > 1 ? -1 : pass);
       SFEM_LAUNCH_CHECK();
+      if (D.nranks > 1) {
+        k_gs_allreduce<<<1, 32, 0, st>>>(nvec, hstep, hcol, pass, D);
+        SFEM_LAUNCH_CHECK();
+      }
       nww = grid_for(n, kThreads * 4, 4);
       { Prof prof(PC_VEC, 8.0 * n * (nvec + 2), st);
-      k_gs_update<<<nww, kThreads, nvec * sizeof(double), st>>>(n, V, nvec, hstep, w, part1); }
+      k_gs_update<<<nww, kThreads, nvec * sizeof(double), st>>>(n, nn, V, nvec, hstep, w, part1); }
       SFEM_LAUNCH_CHECK();
     }
-    k_gmres_givens<<<1, kThreads, 0, st>>>(part1, nww, j, m, H, cs, sn, g, misc);
+    k_gmres_givens<<<1, kThreads, 0, st>>>(part1, nww, j, m, H, cs, sn, g, misc, D);
     SFEM_LAUNCH_CHECK();
     { Prof prof(PC_VEC, 16.0 * n, st);
     k_scale_dev<<<grid_for(n, kThreads * 4), kThreads, 0, st>>>(n, misc, w, V + (size_t)(j + 1) * nn); }
@@ -427,7 +462,7 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
     SFEM_TRY(spmv(A, x, b, w, 1, st));
     int np = 0;
     SFEM_TRY(vec_dot_partial(n, w, w, part1, &np, st));
-    k_gmres_start<<<1, kThreads, 0, st>>>(part1, np, g, misc);
+    k_gmres_start<<<1, kThreads, 0, st>>>(part1, np, g, misc, D);
     SFEM_LAUNCH_CHECK();
     SFEM_TRY(read_double(misc + 1, &est, st));
     if (est <= target || total >= maxit) break;
@@ -468,7 +503,7 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
         hy[i] = s / hH[(size_t)i * (m + 1) + i];
       }
       SFEM_CUDA(cudaMemcpyAsync(hstep, hy.data(), k * sizeof(double), cudaMemcpyHostToDevice, st));
-      k_lincomb_add<<<grid_for(n, kThreads * 4), kThreads, k * sizeof(double), st>>>(n, Z, k, hstep, x);
+      k_lincomb_add<<<grid_for(n, kThreads * 4), kThreads, k * sizeof(double), st>>>(n, nn, Z, k, hstep, x);
       SFEM_LAUNCH_CHECK();
       SFEM_CUDA(cudaStreamSynchronize(st));              // hy is reused by the next cycle
     }

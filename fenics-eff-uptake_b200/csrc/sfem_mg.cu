@@ -78,10 +78,11 @@ __global__ void k_cheb_coef(const double* __restrict__ partial, int np, double f
     if (D.nranks > 1) {
       // row-partitioned operator: the bound must be the same on every rank (a rank-dependent polynomial
       // would not be a symmetric preconditioner).  All-gather through the scalar all-reduce, then max.
+      static_assert(kAllreduceMaxK >= kMaxRanks, "one all-reduce slot per rank");
       double v[kAllreduceMaxK];
       for (int q = 0; q < kAllreduceMaxK; ++q) v[q] = (q == D.rank) ? lmax : 0.0;
-      dist_allreduce_scalars(D, v, D.nranks < kAllreduceMaxK ? D.nranks : kAllreduceMaxK);
-      for (int q = 0; q < D.nranks && q < kAllreduceMaxK; ++q) lmax = fmax(lmax, v[q]);
+      dist_allreduce_scalars(D, v, D.nranks);
+      for (int q = 0; q < D.nranks; ++q) lmax = fmax(lmax, v[q]);
     }
     if (!(lmax > 0.0)) lmax = 2.0;
   }

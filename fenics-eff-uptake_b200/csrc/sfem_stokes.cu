@@ -32,10 +32,11 @@ namespace {
 
 // S: 0 gamma_prev, 1 gamma, 3 delta, 4 eta, 5 c_prev, 6 c, 7 s_prev, 8 s, 9 a1, 10 a2, 11 a3,
 //    12 xcoef, 13 gamma1, 14 delta/gamma, 15 gamma/gamma_prev, 16 1/gamma (of the current z)
-__global__ void k_sm_init(const double* __restrict__ partial, int np, double* __restrict__ S) {
+__global__ void k_sm_init(const double* __restrict__ partial, int np, double* __restrict__ S, DistDev D) {
   __shared__ double sh[33];
-  const double t = block_sum_array(partial, np, sh);
+  double t = block_sum_array(partial, np, sh);
   if (threadIdx.x == 0) {
+    dist_allreduce_scalars(D, &t, 1);
     const double gamma = sqrt(fabs(t));
     S[0] = 1.0; S[1] = gamma; S[2] = 0.0; S[3] = 0.0; S[4] = gamma;
     S[5] = 1.0; S[6] = 1.0; S[7] = 0.0; S[8] = 0.0; S[13] = gamma;
@@ -44,14 +45,16 @@ __global__ void k_sm_init(const double* __restrict__ partial, int np, double* __
 }
 
 __global__ void k_sm_delta(const double* __restrict__ pu, int npu, const double* __restrict__ pp, int npp,
-                           double* __restrict__ S) {
+                           double* __restrict__ S, DistDev D) {
   __shared__ double sh[33];
   const double du = block_sum_array(pu, npu, sh);
   const double dp = block_sum_array(pp, npp, sh);
   if (threadIdx.x == 0) {
+    double dsum = du + dp;
+    dist_allreduce_scalars(D, &dsum, 1);
     const double gamma = S[1];
     const double invg = (gamma > 0.0) ? 1.0 / gamma : 0.0;
-    const double delta = (du + dp) * invg * invg;
+    const double delta = dsum * invg * invg;
     S[3] = delta;
     S[14] = delta * invg;
     S[15] = gamma / S[0];
@@ -86,10 +89,11 @@ __global__ void __launch_bounds__(kThreads) k_sm_vnext(int n, const double* __re
   }
 }
 
-__global__ void k_sm_rot(const double* __restrict__ partial, int np, double* __restrict__ S) {
+__global__ void k_sm_rot(const double* __restrict__ partial, int np, double* __restrict__ S, DistDev D) {
   __shared__ double sh[33];
-  const double t = block_sum_array(partial, np, sh);
+  double t = block_sum_array(partial, np, sh);
   if (threadIdx.x == 0) {
+    dist_allreduce_scalars(D, &t, 1);
     const double gamma = S[1], delta = S[3], eta = S[4];
     const double c_prev = S[5], c = S[6], s_prev = S[7], s = S[8];
     const double gamma_next = sqrt(fabs(t));
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) k_zt_partial(const int* __restrict__
 
 // stage 2 (one block): t = sum of partials per row; coef = C t
 __global__ void __launch_bounds__(kThreads) k_zt_coef(int nz, int nchunks, const double* __restrict__ partial,
-                                                      const double* __restrict__ Cc, double* __restrict__ coef) {
+                                                      const double* __restrict__ Cc, double* __restrict__ coef, DistDev D) {
   extern __shared__ double t[];
   for (int k = threadIdx.x; k < nz; k += blockDim.x) {
     double s = 0.0;
@@ -191,6 +195,11 @@ __global__ void __launch_bounds__(kThreads) k_zt_coef(int nz, int nchunks, const
     t[k] = s;
   }
   __syncthreads();
+  if (D.nranks > 1) {                       // row-partitioned pressure: Z^T r is a sum over the ranks' owned dofs
+    if (threadIdx.x == 0)
+      for (int k0 = 0; k0 < nz; k0 += kAllreduceMaxK) dist_allreduce_scalars(D, t + k0, min(kAllreduceMaxK, nz - k0));
+    __syncthreads();
+  }
   for (int k = threadIdx.x; k < nz; k += blockDim.x) {
     double s = 0.0;
     for (int j = 0; j < nz; ++j) s = fma(Cc[(size_t)k * nz + j], t[j], s);
@@ -217,7 +226,14 @@ constexpr int kZtChunks = 16;
 using namespace sfem;
 
 struct sfem_stokes {
-  int n2 = 0, nv = 0, n = 0;
+  int n2 = 0, nv = 0, n = 0;           // owned velocity dofs (per component), owned pressure dofs, n = 2 n2 + nv
+  // Row-partitioned (multi-GPU) layout of every Stokes vector: [u owned, interleaved | p owned | pad | u ghosts | p ghosts].
+  // The owned part is contiguous (all vector kernels and dot products run over it and never see a ghost); K's local
+  // column numbering has a hole of ceil(nv / 2) pairs between owned and ghost velocity dofs, B^T's ghost pressure
+  // columns sit behind the velocity ghosts (the partition planner, sulcusfem/dist.py, numbers them so).  Single GPU:
+  // n_alloc = n, nothing changes.
+  size_t n_alloc = 0;
+  size_t nv_alloc = 0;                 // length of the pressure work vectors (owned + hole + ghosts)
   Csr K, B, BT, Mp;
   sfem_mg* mg = nullptr;
   int nz = 0;
@@ -257,7 +273,7 @@ int st_precond(sfem_stokes* h, const double* r, double* out, cudaStream_t st) {
     dim3 grid(kZtChunks, h->nz);
     k_zt_partial<<<grid, kThreads, 0, st>>>(h->zt_rowptr, h->zt_cols, h->zt_vals, r + nu, kZtChunks, h->zt_part);
     SFEM_LAUNCH_CHECK();
-    k_zt_coef<<<1, kThreads, h->nz * sizeof(double), st>>>(h->nz, kZtChunks, h->zt_part, h->Cc, h->zcoef);
+    k_zt_coef<<<1, kThreads, h->nz * sizeof(double), st>>>(h->nz, kZtChunks, h->zt_part, h->Cc, h->zcoef, dist_dev());
     SFEM_LAUNCH_CHECK();
     { Prof prof(PC_VEC, 28.0 * h->nv, st);
     k_z_apply<<<grid_for(h->nv, kThreads * 2), kThreads, 0, st>>>(h->nv, h->zidx, h->zw, h->zcoef, out + nu); }
@@ -274,7 +290,7 @@ int st_iteration(sfem_stokes* h, int q, double* x, cudaStream_t st) {
   double* vc = h->v[q];     double* vp = h->v[q ^ 1];
   double* wc = h->w[q];     double* wp = h->w[q ^ 1];
   SFEM_TRY(st_apply(h, zc, h->Az, st));
-  k_sm_delta<<<1, kThreads, 0, st>>>(h->part_u, h->npu, h->part_p, h->npp, h->S);
+  k_sm_delta<<<1, kThreads, 0, st>>>(h->part_u, h->npu, h->part_p, h->npp, h->S, dist_dev());
   SFEM_LAUNCH_CHECK();
   { Prof prof(PC_VEC, 32.0 * n, st);
   if (aligned16(h->Az, vc, vp)) k_sm_vnext<true><<<gv, kThreads, 0, st>>>(n, h->S, h->Az, vc, vp);
@@ -283,7 +299,7 @@ int st_iteration(sfem_stokes* h, int q, double* x, cudaStream_t st) {
   SFEM_TRY(st_precond(h, vp, zn, st));                       // vp now holds v_{j+1}
   int np = 0;
   SFEM_TRY(vec_dot_partial(n, zn, vp, h->part, &np, st));
-  k_sm_rot<<<1, kThreads, 0, st>>>(h->part, np, h->S);
+  k_sm_rot<<<1, kThreads, 0, st>>>(h->part, np, h->S, dist_dev());
   SFEM_LAUNCH_CHECK();
   { Prof prof(PC_VEC, 48.0 * n, st);
   if (aligned16(zc, wc, wp, x)) k_sm_wx<true><<<gv, kThreads, 0, st>>>(n, h->S, zc, wc, wp, x);
@@ -304,7 +320,25 @@ sfem_stokes_t sfem_stokes_create(int n2, int nv,
                                  sfem_mg_t mg,
                                  int nz, const int* zt_rowptr, const int* zt_cols, const double* zt_vals,
                                  const int* zidx, const double* zw, const double* Cc) {
-  if (n2 <= 0 || nv <= 0 || !mg || mg->nb != 2 || mg->levels[0].A.nrows != n2 || nz < 0 || nz > 1024) {
+  return sfem_stokes_create_part(n2, nv, K_nnz, K_rowptr, K_cols, K_vals, B_nnz, B_rowptr, B_cols, B_vals, BT_rowptr, BT_cols,
+                                 BT_vals, Mp_nnz, Mp_rowptr, Mp_cols, Mp_vals, mg, nz, zt_rowptr, zt_cols, zt_vals, zidx, zw, Cc,
+                                 B_nnz, 2LL * n2 + nv, nv);
+}
+
+/* Row-partitioned variant (one rank of a multi-GPU solve): n2 / nv = OWNED velocity / pressure dofs, all matrices hold
+ * the owned rows with columns in the local numbering described at `struct sfem_stokes`; n_alloc = length of every
+ * Stokes vector (b, x and the work vectors: owned part + hole + ghosts), nv_alloc = length of a pressure work vector. */
+sfem_stokes_t sfem_stokes_create_part(int n2, int nv,
+                                      int K_nnz, const int* K_rowptr, const int* K_cols, const double* K_vals,
+                                      int B_nnz, const int* B_rowptr, const int* B_cols, const double* B_vals,
+                                      const int* BT_rowptr, const int* BT_cols, const double* BT_vals,
+                                      int Mp_nnz, const int* Mp_rowptr, const int* Mp_cols, const double* Mp_vals,
+                                      sfem_mg_t mg,
+                                      int nz, const int* zt_rowptr, const int* zt_cols, const double* zt_vals,
+                                      const int* zidx, const double* zw, const double* Cc,
+                                      int BT_nnz, long long n_alloc, long long nv_alloc) {
+  if (n2 <= 0 || nv <= 0 || !mg || mg->nb != 2 || mg->levels[0].A.nrows != n2 || nz < 0 || nz > 1024 ||
+      n_alloc < 2LL * n2 + nv || nv_alloc < nv) {
     set_error("sfem_stokes_create: bad arguments (the multigrid handle must be built with nb = 2 on the velocity block)");
     return nullptr;
   }
@@ -312,13 +346,16 @@ sfem_stokes_t sfem_stokes_create(int n2, int nv,
   h->n2 = n2; h->nv = nv; h->n = 2 * n2 + nv;
   h->K.nrows = h->K.ncols = n2; h->K.nnz = K_nnz; h->K.rowptr = K_rowptr; h->K.cols = K_cols; h->K.vals = K_vals;
   h->B.nrows = nv; h->B.ncols = 2 * n2; h->B.nnz = B_nnz; h->B.rowptr = B_rowptr; h->B.cols = B_cols; h->B.vals = B_vals;
-  h->BT.nrows = 2 * n2; h->BT.ncols = nv; h->BT.nnz = B_nnz; h->BT.rowptr = BT_rowptr; h->BT.cols = BT_cols; h->BT.vals = BT_vals;
+  h->BT.nrows = 2 * n2; h->BT.ncols = nv; h->BT.nnz = BT_nnz; h->BT.rowptr = BT_rowptr; h->BT.cols = BT_cols; h->BT.vals = BT_vals;
   h->Mp.nrows = h->Mp.ncols = nv; h->Mp.nnz = Mp_nnz; h->Mp.rowptr = Mp_rowptr; h->Mp.cols = Mp_cols; h->Mp.vals = Mp_vals;
   h->mg = mg;
   h->nz = nz; h->zt_rowptr = zt_rowptr; h->zt_cols = zt_cols; h->zt_vals = zt_vals; h->zidx = zidx; h->zw = zw; h->Cc = Cc;
-  const size_t nn = ((size_t)h->n + 1) & ~(size_t)1;     // even stride: velocity parts are read as double2
-  const size_t total = 7 * nn + 4 * (size_t)nv + 3 * (size_t)kMaxPartials + (size_t)(nz + 1) * (kZtChunks + 1) + kChebCoefLen + 64;
-  if (cudaMalloc(&h->buf, total * sizeof(double)) != cudaSuccess || cudaMallocHost(&h->h_pin, 8 * sizeof(double)) != cudaSuccess ||
+  const size_t nn = ((size_t)n_alloc + 1) & ~(size_t)1;  // even stride: velocity parts are read as double2
+  const size_t nvp = (size_t)nv_alloc;
+  h->n_alloc = nn; h->nv_alloc = nvp;
+  const size_t total = 7 * nn + 4 * nvp + 3 * (size_t)kMaxPartials + (size_t)(nz + 1) * (kZtChunks + 1) + kChebCoefLen + 64;
+  if (cudaMalloc(&h->buf, total * sizeof(double)) != cudaSuccess || cudaMemset(h->buf, 0, total * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost(&h->h_pin, 8 * sizeof(double)) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming) != cudaSuccess || h->ws.init() != SFEM_OK) {
     set_error("sfem_stokes_create: allocation failed");
@@ -328,7 +365,7 @@ sfem_stokes_t sfem_stokes_create(int n2, int nv,
   double* p = h->buf;
   h->v[0] = p; p += nn; h->v[1] = p; p += nn; h->z[0] = p; p += nn; h->z[1] = p; p += nn;
   h->w[0] = p; p += nn; h->w[1] = p; p += nn; h->Az = p; p += nn;
-  h->mp_dinv = p; p += nv; h->mp_r = p; p += nv; h->mp_d0 = p; p += nv; h->mp_d1 = p; p += nv;
+  h->mp_dinv = p; p += nvp; h->mp_r = p; p += nvp; h->mp_d0 = p; p += nvp; h->mp_d1 = p; p += nvp;
   h->part_u = p; p += kMaxPartials; h->part_p = p; p += kMaxPartials; h->part = p; p += kMaxPartials;
   h->zt_part = p; p += (size_t)(nz + 1) * kZtChunks; h->zcoef = p; p += nz + 1; h->mp_coef = p; p += kChebCoefLen; h->S = p;
   return h;
@@ -347,7 +384,10 @@ void sfem_stokes_destroy(sfem_stokes_t h) {
 
 int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, int maxit, double* h_info, void* stream) {
   if (!h || !h->mg->ready) { set_error("stokes solve: handle / multigrid not set up"); return SFEM_ERR_ARG; }
-  if (dist_dev().nranks > 1) { set_error("stokes solve: the row-partitioned (multi-GPU) path serves CG only in this version"); return SFEM_ERR_ARG; }
+  if (dist_dev().nranks > 1 && (find_halo(h->K.rowptr) == nullptr || h->n_alloc == (((size_t)h->n + 1) & ~(size_t)1))) {
+    set_error("stokes solve: a communicator is active but this handle is not row-partitioned (sfem_stokes_create_part + halos)");
+    return SFEM_ERR_ARG;
+  }
   if ((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15u) {
     set_error("stokes solve: b and x must be 16-byte aligned (interleaved velocity is read as double2)");
     return SFEM_ERR_ARG;
@@ -357,7 +397,7 @@ int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, 
   SFEM_TRY(h->ws.fork(user));
   cudaStream_t st = h->ws.s;
   const int n = h->n;
-  const size_t nn = (size_t)n;
+  const size_t nn = h->n_alloc;              // whole vectors (ghost areas included) are cleared
   const int gv = grid_for(n, kThreads * 4, 4);
   SFEM_TRY(extract_diag_inv(h->Mp, h->mp_dinv, st));
   SFEM_TRY(cheb_setup(nullptr, nullptr, 2.0, 4.0, 4, h->part, h->mp_coef, st));
@@ -374,7 +414,7 @@ int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, 
   SFEM_TRY(st_precond(h, h->v[0], h->z[0], st));
   int np = 0;
   SFEM_TRY(vec_dot_partial(n, h->z[0], h->v[0], h->part, &np, st));
-  k_sm_init<<<1, kThreads, 0, st>>>(h->part, np, h->S);
+  k_sm_init<<<1, kThreads, 0, st>>>(h->part, np, h->S, dist_dev());
   SFEM_LAUNCH_CHECK();
   double gamma1 = 0.0;
   SFEM_CUDA(cudaMemcpyAsync(&gamma1, h->S + 13, sizeof(double), cudaMemcpyDeviceToHost, st));

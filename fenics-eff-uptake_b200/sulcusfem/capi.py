@@ -99,6 +99,8 @@ SIGNATURES = {
     'sfem_dist_allreduce_scalars': (_i, [_p, _p, _i, _p]),
     'sfem_facet_functionals': (_i, [_i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _d, _d, _p, _p, _p]),
     'sfem_cell_functionals': (_i, [_i, _p, _p, _p, _i, _p, _p, _p]),
+    'sfem_stokes_create_part': (_p, [_i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p,
+                                     _i, _p, _p, _p, _p, _p, _p, _i, C.c_longlong, C.c_longlong]),
     'sfem_eval_points': (_i, [_i, _i, _p, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i, _p, _i, C.POINTER(_p), _d, _p, _p, _p]),
 }
 

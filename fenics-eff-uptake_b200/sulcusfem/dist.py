@@ -5,11 +5,14 @@ row-partitioned in x-slabs over the ranks; halo exchange and the Krylov all-redu
 store straight into the peers' memory over NVLink (``csrc/sfem_dist.cu``) -- ``torch.distributed`` is
 used once, to all-gather the 64-byte CUDA-IPC handles of the mailboxes.
 
-Scope of this version: the symmetric (pure-diffusion / Robin) solve, i.e. multigrid-preconditioned CG.
-Assembly is replicated (every rank assembles the global matrices with the single-GPU kernels -- <1 % of
-the solve time -- and extracts its rows with ``sfem_csr_extract``); the solve itself is distributed.
-Levels with fewer than ``replicate_below`` unknowns are kept on every rank and solved redundantly after a
-vector all-reduce of the restricted residual.
+Scope: all three solves of the path -- multigrid-preconditioned CG (pure diffusion / Robin), FGMRES
+(advection-diffusion, ``solvers.py:16-57``) and the Taylor-Hood MINRES (``solvers.py:237-306``) with its
+2-right-hand-side velocity multigrid, pressure-mass Chebyshev sweep and lubrication coarse correction.
+Assembly is replicated (every rank assembles the global matrices with the single-GPU kernels and extracts
+its rows with ``sfem_csr_extract``); the solves are distributed; fields are all-gathered (NCCL, the one
+real exchange of full vectors) where the next replicated stage needs them.  Levels with fewer than
+``replicate_below`` unknowns are kept on every rank and solved redundantly after a vector all-reduce of
+the restricted residual.  One mailbox (:class:`DistWorld`) serves every problem of the process.
 """
 from __future__ import annotations
 
@@ -97,18 +100,57 @@ class _LocalOp:
                    'sfem_csr_extract')
 
 
+class DistWorld:
+    """The communicator of this process: ONE mailbox shared by every row-partitioned problem.  Partitions are
+    planned first (host only; every rank computes the channel layout of all ranks), then :meth:`commit` allocates
+    the mailbox, exchanges the IPC handles and activates the communicator."""
+
+    def __init__(self, ctx: Context, rank: int, nranks: int, vec_cap: int, group=None, emulate=False):
+        self.ctx, self.rank, self.nranks, self.group, self.emulate = ctx, int(rank), int(nranks), group, emulate
+        self.vec_cap = int(vec_cap)
+        header = int(ctx.lib.sfem_dist_header_words(self.nranks, self.vec_cap))
+        self.base = [header] * self.nranks
+        self.dist: Optional[DistContext] = None
+
+    def plan(self, owner, ghosts, nb_max=1, gap=0) -> pt.LevelPartition:
+        if self.dist is not None:
+            raise capi.SulcusFemError("DistWorld.plan after commit")
+        lp = pt.partition_level(owner, self.nranks, self.rank, ghosts, self.base, nb_max=nb_max, ghost_gap=gap)
+        self.base = list(lp.all_mailbox_ends)
+        return lp
+
+    def commit(self):
+        if self.dist is None:
+            self.dist = DistContext(self.ctx, self.rank, self.nranks, int(max(self.base)) + 8, self.vec_cap,
+                                    group=self.group, emulate=self.emulate)
+        return self.dist
+
+    def error(self) -> bool:
+        return self.dist is not None and self.dist.error()
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.close()
+            self.dist = None
+
+
 def level_coordinates(prob: ScalarProblem, l: int) -> np.ndarray:
     lev = prob.levels[l]
     return dm.p2_dof_coordinates(lev.mesh) if lev.degree == 2 else lev.mesh.coords
 
 
-def plan_partitions(prob: ScalarProblem, nranks: int, replicate_below: int = 20000):
-    """Owner arrays + ghost sets of the row-partitioned levels (identical on every rank)."""
+def num_distributed_levels(prob: ScalarProblem, replicate_below: int) -> int:
     nl = len(prob.levels)
     nd = 0
     while nd < nl - 1 and prob.levels[nd].n >= replicate_below:
         nd += 1
-    nd = max(nd, 1)                                         # at least the system level is distributed
+    return max(nd, 1)                                       # at least the system level is distributed
+
+
+def plan_partitions(prob: ScalarProblem, nranks: int, replicate_below: int = 20000, extra_ops0=None):
+    """Owner arrays + ghost sets of the row-partitioned levels (identical on every rank).  ``extra_ops0(owner0)``:
+    further operators whose columns live on the system level (the Stokes divergence block)."""
+    nd = num_distributed_levels(prob, replicate_below)
     owners = []
     for l in range(nd):
         X = level_coordinates(prob, l)
@@ -123,6 +165,8 @@ def plan_partitions(prob: ScalarProblem, nranks: int, replicate_below: int = 200
         if l > 0:                                           # prolongation l -> l-1: rows on l-1, columns on l
             T = prob.hierarchy.transfers[l - 1]
             ops.append((T.rowptr, T.cols, owners[l - 1]))
+        if l == 0 and extra_ops0 is not None:
+            ops.extend(extra_ops0(owners[0]))
         ghosts.append(pt.ghost_sets(owners[l], nranks, ops))
     return nd, owners, ghosts
 
@@ -138,22 +182,84 @@ def mailbox_layout(prob: ScalarProblem, nranks: int, nd: int, owners, ghosts, he
     return parts, int(max(base)) + 8
 
 
+def _gather_map(ctx, idx):
+    return ctx.up(np.ascontiguousarray(idx, dtype=np.int32), np.int32)
+
+
+def _gather(ctx, n, slot, src, dst):
+    """dst[i] = src[slot[i]] (device)."""
+    capi.check(ctx.lib.sfem_csr_extract(int(n), P(slot), P(src), P(dst), ctx.stream), 'sfem_csr_extract')
+
+
+class AllGather:
+    """All-gather of the ranks' owned entries into full (replicated) vectors: one NCCL all-gather of equally padded
+    segments, then gathers by precomputed position maps.  ``owned_lists[q]``: global ids in the order rank q stores
+    its owned entries; ``fields``: {name: (offset of the field in a rank's segment as a function of q, global ids per
+    rank)} -- built by the problems below."""
+
+    def __init__(self, ctx, nranks, seg_len, group=None):
+        torch = _torch()
+        self.ctx, self.nranks, self.group = ctx, nranks, group
+        self.seg = int(max(seg_len))
+        self.send = torch.zeros(self.seg, dtype=torch.float64, device=ctx.device)
+        self.recv = torch.zeros(self.seg * nranks, dtype=torch.float64, device=ctx.device)
+        self.maps = {}
+
+    def add_field(self, name, n_global, pos_of_global):
+        """pos_of_global[g] = index into the concatenated receive buffer of global entry g."""
+        assert len(pos_of_global) == n_global and pos_of_global.min() >= 0
+        self.maps[name] = (int(n_global), _gather_map(self.ctx, pos_of_global),
+                           self.ctx.zeros(n_global))
+
+    def run(self):
+        if self.nranks > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        else:
+            capi.check(self.ctx.lib.sfem_vec_copy(self.seg, P(self.send), P(self.recv), self.ctx.stream), 'sfem_vec_copy')
+        out = {}
+        for name, (n, pos, dst) in self.maps.items():
+            _gather(self.ctx, n, pos, self.recv, dst)
+            out[name] = dst
+        return out
+
+
 class DistScalarProblem:
-    """Row-partitioned view of a :class:`ScalarProblem` (which every rank holds and assembles in full)."""
+    """Row-partitioned view of a :class:`ScalarProblem` (which every rank holds and assembles in full).
+
+    ``nb = 2``: the velocity block of the Taylor-Hood solver (two interleaved right-hand sides per V-cycle).
+    ``world``: shared communicator (planning only; call :meth:`finalize` after ``world.commit()``); without one the
+    problem owns a private communicator and is ready after construction."""
 
     def __init__(self, prob: ScalarProblem, rank: int, nranks: int, group=None, replicate_below: int = 20000,
-                 emulate=False):
+                 emulate=False, world: Optional[DistWorld] = None, nb: int = 1, plan=None, level0_gap: int = 0):
         self.prob, self.ctx = prob, prob.ctx
         ctx, lib = self.ctx, self.ctx.lib
-        self.rank, self.nranks = rank, nranks
-        nd, owners, ghosts = plan_partitions(prob, nranks, replicate_below)
-        self.nd = nd
-        n_tail = prob.levels[nd].n
-        header = int(lib.sfem_dist_header_words(nranks, n_tail))
-        parts_all, words = mailbox_layout(prob, nranks, nd, owners, ghosts, header)
-        self.parts_all = parts_all
-        self.parts = [row[rank] for row in parts_all]
-        self.dist = DistContext(ctx, rank, nranks, words, n_tail, group=group, emulate=emulate)
+        self.rank, self.nranks, self.nb, self.group = rank, nranks, int(nb), group
+        nd, owners, ghosts = plan if plan is not None else plan_partitions(prob, nranks, replicate_below)
+        self.nd, self.owners = nd, owners
+        self.n_tail = prob.levels[nd].n
+        self._own_world = world is None
+        self.world = world if world is not None else DistWorld(ctx, rank, nranks, self.n_tail * self.nb, group=group,
+                                                               emulate=emulate)
+        if self.world.vec_cap < self.n_tail * self.nb:
+            raise capi.SulcusFemError("DistWorld.vec_cap is smaller than the replicated coarse level of this problem")
+        self.parts = [self.world.plan(owners[l], ghosts[l], nb_max=self.nb, gap=(level0_gap if l == 0 else 0))
+                      for l in range(nd)]
+        self.mg = None
+        self.halos = []
+        if self._own_world:
+            self.world.commit()
+            self.finalize()
+
+    @property
+    def dist(self):
+        return self.world.dist
+
+    def finalize(self):
+        """Device side (after the communicator exists): halos, local operators, multigrid handles."""
+        prob, ctx, lib, nd, nb = self.prob, self.ctx, self.ctx.lib, self.nd, self.nb
+        n_tail = self.n_tail
         self.halos = [DeviceHalo(ctx, lp) for lp in self.parts]
         H = prob.hierarchy
         self.A: List[_LocalOp] = []
@@ -176,12 +282,12 @@ class DistScalarProblem:
                 # owned columns (its partial results are summed over the ranks)
                 ident = np.arange(n_tail, dtype=np.int64)
                 Pl = _LocalOp(ctx, dT.P, T.rowptr, T.cols, lp.owned, ident, n_tail)
-                own_only = np.where(lp.g2l < lp.n_own, lp.g2l, -1)
+                own_only = np.where((lp.g2l >= 0) & (lp.g2l < lp.n_own), lp.g2l, -1)
                 Rl = _LocalOp(ctx, dT.R, T.t_rowptr, T.t_cols, ident, own_only, lp.n_own, drop_missing=True)
             self.Pm.append(Pl)
             self.Rm.append(Rl)
         # multigrid handles: replicated tail (global levels nd..) and the row-partitioned head
-        self.tail = Multigrid(ctx, prob.levels[nd:], prob.transfers[nd:], prob.mg_cheb_degree, prob.mg_eig_ratio, 1)
+        self.tail = Multigrid(ctx, prob.levels[nd:], prob.transfers[nd:], prob.mg_cheb_degree, prob.mg_eig_ratio, nb)
         nlv = nd
         IntArr, PtrArr = C.c_int * nlv, C.c_void_p * nlv
 
@@ -196,7 +302,7 @@ class DistScalarProblem:
                  rv=parr([r_.csr.vals for r_ in self.Rm[:-1]]))
         self._keep = k
         self.mg = lib.sfem_mg_create(nlv, k['n'], k['annz'], k['arp'], k['ac'], k['av'], k['pnnz'], k['prp'], k['pc'], k['pv'],
-                                     k['rrp'], k['rc'], k['rv'], None, prob.mg_cheb_degree, float(prob.mg_eig_ratio), 1)
+                                     k['rrp'], k['rc'], k['rv'], None, prob.mg_cheb_degree, float(prob.mg_eig_ratio), nb)
         if not self.mg:
             raise capi.SulcusFemError("sfem_mg_create (distributed) failed: " + lib.sfem_last_error().decode())
         Pl, Rl = self.Pm[-1].csr, self.Rm[-1].csr
@@ -204,36 +310,66 @@ class DistScalarProblem:
                                         Rl.nnz, P(Rl.rowptr), P(Rl.cols), P(Rl.vals)), 'sfem_mg_set_tail')
         lp0 = self.parts[0]
         self.owned = ctx.up(lp0.owned, np.int64)
-        self.x = ctx.zeros(lp0.n_loc)
-        self.rhs = ctx.zeros(lp0.n_own)
+        self.owned32 = _gather_map(ctx, lp0.owned)
+        self.x = ctx.zeros(lp0.n_loc * nb)
+        self.rhs = ctx.zeros(lp0.n_own * nb)
         self.last_info = None
+        self._ag = None
 
-    def refresh(self):
+    def refresh_operators(self):
         """Pull this rank's rows out of the freshly assembled global operators and set up the smoothers."""
         for ops in (self.A, self.Pm, self.Rm):
             for o in ops:
                 o.refresh()
         self.tail.setup()
         capi.check(self.ctx.lib.sfem_mg_setup(self.mg, self.ctx.stream), 'sfem_mg_setup')
-        f = self.prob.fine
-        self.rhs.copy_(f.rhs[self.owned])
 
-    def solve(self, rtol=1e-13, maxit=400):
+    def refresh(self):
+        self.refresh_operators()
+        f = self.prob.fine
+        _gather(self.ctx, self.parts[0].n_own, self.owned32, f.rhs, self.rhs)
+
+    def solve(self, method='cg', rtol=1e-13, maxit=400, restart=80):
         ctx, f = self.ctx, self.prob.fine
-        torch = _torch()
-        x0 = f.bc_val * f.bc_flag.to(torch.float64)
-        self.x.zero_()
-        self.x[:self.parts[0].n_own].copy_(x0[self.owned])
+        lib = ctx.lib
+        n_own = self.parts[0].n_own
+        if not hasattr(self, '_x0g'):
+            self._x0g = ctx.zeros(f.n)
+        capi.check(lib.sfem_vec_select(f.n, P(f.bc_flag), P(f.bc_val), None, P(self._x0g), ctx.stream), 'sfem_vec_select')
+        capi.check(lib.sfem_vec_set(self.parts[0].n_loc, 0.0, P(self.x), ctx.stream), 'sfem_vec_set')
+        _gather(ctx, n_own, self.owned32, self._x0g, self.x)
         info = (C.c_double * 4)()
         A = self.A[0].csr
-        rc = ctx.lib.sfem_krylov_cg(self.parts[0].n_own, A.nnz, P(A.rowptr), P(A.cols), P(A.vals), self.mg, P(self.rhs),
+        if method == 'cg':
+            rc = lib.sfem_krylov_cg(n_own, A.nnz, P(A.rowptr), P(A.cols), P(A.vals), self.mg, P(self.rhs),
                                     P(self.x), float(rtol), int(maxit), info, ctx.stream)
-        capi.check(rc, 'sfem_krylov_cg (distributed)')
-        if self.dist.error():
+        elif method == 'fgmres':
+            rc = lib.sfem_krylov_fgmres(n_own, A.nnz, P(A.rowptr), P(A.cols), P(A.vals), self.mg, P(self.rhs),
+                                        P(self.x), float(rtol), int(restart), int(maxit), info, ctx.stream)
+        else:
+            raise ValueError(f"unknown method {method!r}")
+        capi.check(rc, f'sfem_krylov_{method} (distributed)')
+        if self.world.error():
             raise capi.SulcusFemError("multi-GPU exchange timed out (a peer did not answer)")
         self.last_info = {'iterations': int(info[0]), 'relres': float(info[1]), 'converged': bool(info[2]),
-                          'estimate': float(info[3]), 'method': 'cg', 'ranks': self.nranks}
-        return self.x[:self.parts[0].n_own]
+                          'estimate': float(info[3]), 'method': method, 'ranks': self.nranks}
+        return self.x[:n_own]
+
+    def gather(self):
+        """The full (replicated) solution vector on every rank."""
+        if self._ag is None:
+            n = self.prob.fine.n
+            counts = [int((self.owners[0] == q).sum()) for q in range(self.nranks)]
+            ag = AllGather(self.ctx, self.nranks, counts, group=self.group)
+            pos = np.empty(n, dtype=np.int64)
+            for q in range(self.nranks):
+                g = np.flatnonzero(self.owners[0] == q)
+                pos[g] = q * ag.seg + np.arange(len(g))
+            ag.add_field('x', n, pos)
+            self._ag = ag
+        n_own = self.parts[0].n_own
+        capi.check(self.ctx.lib.sfem_vec_copy(n_own, P(self.x), P(self._ag.send), self.ctx.stream), 'sfem_vec_copy')
+        return self._ag.run()['x']
 
     def close(self):
         if getattr(self, 'mg', None):
@@ -243,4 +379,146 @@ class DistScalarProblem:
             if h.handle:
                 self.ctx.lib.sfem_halo_destroy(h.handle)
                 h.handle = None
-        self.dist.close()
+        if self._own_world:
+            self.world.close()
+
+
+class DistStokesProblem:
+    """Row-partitioned Taylor-Hood solve (reference ``solvers.py:237-306`` over several GPUs).
+
+    Every rank holds the full :class:`StokesProblem` and assembles the global block views K, B, B^T, Mp (replicated
+    assembly); this class extracts the rank's rows, numbers the local unknowns so that the owned part of a Stokes
+    vector is contiguous (``csrc/sfem_stokes.cu``: [u owned, interleaved | p owned | pad | u ghosts | p ghosts]) and runs
+    MINRES with the same preconditioner as on one GPU: row-partitioned 2-right-hand-side velocity multigrid,
+    pressure-mass Chebyshev sweep, lubrication coarse correction (its 11 coefficients all-reduced in-kernel)."""
+
+    def __init__(self, stokes, world: DistWorld, replicate_below: int = 200000):
+        from .device import StokesProblem  # noqa: F401  (type only)
+        self.stokes, self.ctx, self.world = stokes, stokes.ctx, world
+        ctx, rank, nranks = self.ctx, world.rank, world.nranks
+        self.rank, self.nranks = rank, nranks
+        mesh = stokes.mesh
+        n2, nv = stokes.n2, stokes.nv
+        pb, pbt, _, mp = dm.stokes_block_plans(mesh)
+        self._pat = (pb, pbt, mp)
+
+        def extra0(owner0):
+            # the divergence block reads velocity pairs j = col // 2 from the rows of the pressure owner
+            return [(pb.rowptr, pb.cols.astype(np.int64) // 2, owner0[:nv])]
+        plan = plan_partitions(stokes.vel, nranks, replicate_below, extra_ops0=extra0)
+        owner0 = plan[1][0]
+        self.owner_u, self.owner_p = owner0, owner0[:nv].copy()
+        nv_own = int((self.owner_p == rank).sum())
+        self.hole = pt.stokes_gaps(nv_own, 0)[0]               # pairs between owned and ghost velocity dofs
+        self.vel = DistScalarProblem(stokes.vel, rank, nranks, group=world.group, world=world, nb=2, plan=plan,
+                                     level0_gap=self.hole)
+        lu = self.vel.parts[0]
+        n2_own, n2_gh = lu.n_own, len(lu.ghost)
+        # pressure partition: ghosts read by B^T (rows = velocity owner) and by the mass matrix
+        row_owner_bt = np.repeat(owner0, 2)                    # interleaved velocity rows 2 j + c
+        ghosts_p = pt.ghost_sets(self.owner_p, nranks, [(pbt.rowptr, pbt.cols, row_owner_bt), (mp.rowptr, mp.cols, self.owner_p)])
+        self.gap_p = pt.stokes_gaps(nv_own, n2_gh)[1]          # pad + velocity ghosts sit between owned and ghost pressure
+        self.lp = world.plan(self.owner_p, ghosts_p, nb_max=1, gap=self.gap_p)
+        assert self.lp.n_own == nv_own
+        self.n2_own, self.nv_own = n2_own, nv_own
+        self.n_own = 2 * n2_own + nv_own
+        self.n_alloc = 2 * lu.n_loc + len(self.lp.ghost)       # 2 (n2_own + hole + n2_gh) + nv_gh
+        self.nv_alloc = self.lp.n_loc
+        self.handle = None
+
+    def finalize(self):
+        ctx, lib, st = self.ctx, self.ctx.lib, self.stokes
+        self.vel.finalize()
+        pb, pbt, mp = self._pat
+        lu, lp = self.vel.parts[0], self.lp
+        n2, nv = st.n2, st.nv
+        self.halo_p = DeviceHalo(ctx, lp)
+        # B: owned pressure rows; columns = interleaved velocity scalars in K's local numbering (2 g2l[j] + c)
+        col_b = np.full(2 * n2, -1, dtype=np.int64)
+        present = lu.g2l >= 0
+        col_b[0::2] = np.where(present, 2 * lu.g2l, -1)
+        col_b[1::2] = np.where(present, 2 * lu.g2l + 1, -1)
+        self.B = _LocalOp(ctx, st.B, pb.rowptr, pb.cols, lp.owned, col_b, 2 * lu.n_loc)
+        # B^T: owned velocity rows (interleaved), columns = local pressure ids (relative to the start of the p part)
+        rows_bt = np.stack([2 * lu.owned, 2 * lu.owned + 1], axis=1).ravel()
+        self.BT = _LocalOp(ctx, st.BT, pbt.rowptr, pbt.cols, rows_bt, lp.g2l, lp.n_loc)
+        self.halo_p.attach(self.BT.csr)
+        self.Mp = _LocalOp(ctx, st.Mp, mp.rowptr, mp.cols, lp.owned, lp.g2l, lp.n_loc)
+        self.halo_p.attach(self.Mp.csr)
+        # lubrication correction restricted to the owned pressure dofs
+        nz, zt = 0, [None] * 6
+        q = st.schur
+        if q is not None:
+            if q.nz > 1024:
+                raise capi.SulcusFemError("Schur correction too large")
+            own_only = np.where((lp.g2l >= 0) & (lp.g2l < lp.n_own), lp.g2l, -1)
+            rp, lc, slot = pt.localize_csr(q.zt_rowptr, q.zt_cols, np.arange(q.nz), own_only, drop_missing=True)
+            self._z = (ctx.up(rp, np.int32), ctx.up(np.concatenate([lc, [0]]), np.int32),
+                       ctx.up(np.concatenate([np.asarray(q.zt_vals)[slot], [0.0]]), np.float64),
+                       ctx.up(np.asarray(q.zidx)[lp.owned], np.int32), ctx.up(np.asarray(q.zw)[lp.owned], np.float64),
+                       ctx.up(q.C.ravel(), np.float64))
+            nz, zt = q.nz, [P(t) for t in self._z]
+        K = self.vel.A[0].csr
+        B, BT, Mp = self.B.csr, self.BT.csr, self.Mp.csr
+        self.handle = lib.sfem_stokes_create_part(self.n2_own, self.nv_own, K.nnz, P(K.rowptr), P(K.cols), P(K.vals),
+                                                  B.nnz, P(B.rowptr), P(B.cols), P(B.vals),
+                                                  P(BT.rowptr), P(BT.cols), P(BT.vals),
+                                                  Mp.nnz, P(Mp.rowptr), P(Mp.cols), P(Mp.vals), self.vel.mg, nz, *zt,
+                                                  BT.nnz, self.n_alloc, self.nv_alloc)
+        if not self.handle:
+            raise capi.SulcusFemError("sfem_stokes_create_part failed: " + lib.sfem_last_error().decode())
+        # gather maps: solver layout of the global problem ([u interleaved | p]) -> owned part of the local vectors
+        src = np.concatenate([rows_bt, 2 * n2 + lp.owned])
+        self.own_map = _gather_map(ctx, src)
+        self.b = ctx.zeros(self.n_alloc + 2)
+        self.x = ctx.zeros(self.n_alloc + 2)
+        self.last_info = None
+        # all-gather of the solution into blocked global fields ux | uy | p
+        counts = [2 * int((self.owner_u == r).sum()) + int((self.owner_p == r).sum()) for r in range(self.nranks)]
+        ag = AllGather(ctx, self.nranks, counts, group=self.world.group)
+        pos_ux, pos_uy, pos_p = np.empty(n2, np.int64), np.empty(n2, np.int64), np.empty(nv, np.int64)
+        for r in range(self.nranks):
+            gu = np.flatnonzero(self.owner_u == r)
+            gp = np.flatnonzero(self.owner_p == r)
+            pos_ux[gu] = r * ag.seg + 2 * np.arange(len(gu))
+            pos_uy[gu] = r * ag.seg + 2 * np.arange(len(gu)) + 1
+            pos_p[gp] = r * ag.seg + 2 * len(gu) + np.arange(len(gp))
+        ag.add_field('ux', n2, pos_ux)
+        ag.add_field('uy', n2, pos_uy)
+        ag.add_field('p', nv, pos_p)
+        self._ag = ag
+
+    def refresh(self):
+        """After ``StokesProblem.assemble(bc_mode=1)``: this rank's rows of every operator + the right-hand side."""
+        self.vel.refresh_operators()
+        for o in (self.B, self.BT, self.Mp):
+            o.refresh()
+        _gather(self.ctx, self.n_own, self.own_map, self.stokes.rhs_il, self.b)
+
+    def solve(self, rtol=1e-12, maxit=2000):
+        ctx, lib = self.ctx, self.ctx.lib
+        capi.check(lib.sfem_vec_set(self.n_alloc, 0.0, P(self.x), ctx.stream), 'sfem_vec_set')
+        _gather(ctx, self.n_own, self.own_map, self.stokes.g_il, self.x)       # initial guess: the Dirichlet values
+        info = (C.c_double * 4)()
+        capi.check(lib.sfem_stokes_solve(self.handle, P(self.b), P(self.x), float(rtol), int(maxit), info, ctx.stream),
+                   'sfem_stokes_solve (distributed)')
+        if self.world.error():
+            raise capi.SulcusFemError("multi-GPU exchange timed out (a peer did not answer)")
+        self.last_info = {'iterations': int(info[0]), 'relres': float(info[1]), 'converged': bool(info[2]),
+                          'estimate': float(info[3]), 'method': 'minres', 'ranks': self.nranks}
+        return self.x[:self.n_own]
+
+    def gather(self):
+        """(ux, uy, p): the full (replicated, blocked) fields on every rank."""
+        capi.check(self.ctx.lib.sfem_vec_copy(self.n_own, P(self.x), P(self._ag.send), self.ctx.stream), 'sfem_vec_copy')
+        out = self._ag.run()
+        return out['ux'], out['uy'], out['p']
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.sfem_stokes_destroy(self.handle)
+            self.handle = None
+        if getattr(self, 'halo_p', None) is not None and self.halo_p.handle:
+            self.ctx.lib.sfem_halo_destroy(self.halo_p.handle)
+            self.halo_p.handle = None
+        self.vel.close()

@@ -101,10 +101,13 @@ def _mesh_h(mesh: HostMesh) -> float:
 
 def coarser_synthetic(mesh: HostMesh, h: float) -> Optional[HostMesh]:
     g = mesh.geometry
-    if g.get('mesher') == 'delaunay':
+    if str(g.get('mesher', '')).startswith('delaunay'):
         from .unstructured import mesh_domain
         try:
-            return mesh_domain(g['L'], g['H'], g.get('w', 0.5), g.get('d', 1.0), h, g['domain_type'])
+            # a graded fine mesh (reference refinement_factor > 1) is coarsened with the same grading: every level
+            # doubles the spacing everywhere, near the sulcus too
+            return mesh_domain(g['L'], g['H'], g.get('w', 0.5), g.get('d', 1.0), h, g['domain_type'],
+                               refinement_factor=g.get('refinement_factor', 1))
         except RuntimeError:
             pass
     if g.get('domain_type') == 'sulcus':
@@ -130,7 +133,7 @@ def build_hierarchy(mesh: HostMesh, coarsest_vertices: int = 400, max_levels: in
         transfers.append(midpoint_transfer(m.parent))
         m = m.parent
         meshes.append(m)
-    h = _mesh_h(m)
+    h = float(m.geometry['h']) if m.geometry.get('mesher') == 'delaunay-graded' else _mesh_h(m)
     H = m.geometry.get('H', None)
     while (m.num_vertices > coarsest_vertices and len(meshes) < max_levels
            and m.geometry.get('domain_type') in ('sulcus', 'rectangular')):

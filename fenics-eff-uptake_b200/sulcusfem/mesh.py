@@ -6,8 +6,10 @@ The reference writes a ``.geo`` file, shells out to Gmsh, converts with meshio a
 'domain_markers'], 'mesh_info'}`` with the marker semantics of ``mesh.py:196-256,425-453`` -- from
 the in-process meshers of :mod:`sulcusfem.unstructured` / :mod:`sulcusfem.hostmesh`, or from a mesh
 file the reference pipeline already wrote (``mesh_file=`` dolfin-XML or Gmsh msh2).
-``refinement_factor`` > 1 is honoured as uniform refinement levels of the whole mesh
-(``uniform_refinements``), the knob BASELINE config 5 (mesh convergence) turns.
+``refinement_factor`` > 1 grades the Delaunay mesh towards the sulcus with the reference's Distance / Threshold size
+field (``lc_fine = mesh_size / refinement_factor`` within w/10 of the sulcus nodes, ``mesh_size`` beyond w/2;
+``mesh.py:266,330-337`` -> ``unstructured.threshold_size_field``); ``uniform_refinements`` (not a reference argument)
+adds uniform red refinements of the whole mesh, the knob BASELINE config 5 (mesh convergence) turns.
 """
 from __future__ import annotations
 
@@ -78,7 +80,8 @@ class MeshGenerator:
         if self.mesher == 'delaunay':
             from .unstructured import mesh_domain
             try:
-                mesh = mesh_domain(self.width, self.height, self.sulcus_width, self.sulcus_depth, h, self.domain_type)
+                mesh = mesh_domain(self.width, self.height, self.sulcus_width, self.sulcus_depth, h, self.domain_type,
+                                   refinement_factor=self.refinement_factor)
             except RuntimeError as e:                      # tiny cavities: fall back to the structured mesher
                 logging.warning(f"unstructured mesher failed ({e}); using the structured mesher")
         if mesh is None:

@@ -78,6 +78,7 @@ class LevelPartition:
     cap: List[int] = field(default_factory=list)
     mailbox_end: int = 0              # first free word of this rank's mailbox after this level's channels
     all_mailbox_ends: List[int] = field(default_factory=list)
+    ghost_gap: int = 0                # unused local ids between the owned and the ghost DOFs
 
     @property
     def n_own(self) -> int:
@@ -85,7 +86,7 @@ class LevelPartition:
 
     @property
     def n_loc(self) -> int:
-        return int(len(self.owned) + len(self.ghost))
+        return int(len(self.owned) + self.ghost_gap + len(self.ghost))
 
 
 def _even(v: int) -> int:
@@ -93,12 +94,14 @@ def _even(v: int) -> int:
 
 
 def partition_level(owner: np.ndarray, nranks: int, rank: int, ghosts: List[np.ndarray],
-                    mailbox_base: Sequence[int], nb_max: int = 2) -> LevelPartition:
+                    mailbox_base: Sequence[int], nb_max: int = 2, ghost_gap: int = 0) -> LevelPartition:
     """Partition data of ``rank`` for one level.
 
     ``ghosts``: output of :func:`ghost_sets`.  ``mailbox_base[q]``: first free word of rank q's mailbox
     before this level; the returned ``mailbox_end`` values of all ranks are obtained by calling this
     function for every q (or :func:`mailbox_ends`).  Channels hold ``nb_max`` values per DOF.
+    ``ghost_gap``: unused local ids between the owned and the ghost DOFs of THIS rank (the Taylor-Hood solver keeps
+    the owned pressure entries of a Stokes vector in that hole, so that the owned part of the vector is contiguous).
     """
     owner = np.asarray(owner)
     n = len(owner)
@@ -131,8 +134,9 @@ def partition_level(owner: np.ndarray, nranks: int, rank: int, ghosts: List[np.n
     gh_owner = gh_owner[order]
     g2l = np.full(n, -1, dtype=np.int64)
     g2l[mine] = np.arange(len(mine))
-    g2l[gh] = len(mine) + np.arange(len(gh))
-    lp = LevelPartition(rank, nranks, n, mine, gh, g2l)
+    gap = int(ghost_gap)
+    g2l[gh] = len(mine) + gap + np.arange(len(gh))
+    lp = LevelPartition(rank, nranks, n, mine, gh, g2l, ghost_gap=gap)
     for q in range(nranks):
         if not nbr[rank, q]:
             continue
@@ -142,7 +146,7 @@ def partition_level(owner: np.ndarray, nranks: int, rank: int, ghosts: List[np.n
         want = np.sort(gq[owner[gq] == rank]) if len(gq) else np.zeros(0, dtype=np.int64)
         lp.send_idx.append(g2l[want].astype(np.int32))
         sel = np.flatnonzero(gh_owner == q)
-        lp.recv_off.append(int(len(mine) + (sel[0] if len(sel) else 0)))
+        lp.recv_off.append(int(len(mine) + gap + (sel[0] if len(sel) else 0)))
         lp.recv_cnt.append(int(len(sel)))
         d_off, f_off, cap = chan[(q, rank)]              # I write into q's channel for sender = me
         lp.peer_data_off.append(d_off); lp.peer_flag_off.append(f_off)
@@ -180,6 +184,16 @@ def localize_csr(rowptr: np.ndarray, cols: np.ndarray, rows: np.ndarray, col_g2l
         raise ValueError("localize_csr: a column is neither owned nor ghost on this rank")
     rp_loc = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     return rp_loc, lc.astype(np.int32), slot.astype(np.int64)
+
+
+def stokes_gaps(nv_own: int, n2_ghost: int) -> Tuple[int, int]:
+    """Local numbering of a row-partitioned Taylor-Hood vector
+    ``[u owned, interleaved | p owned | pad | u ghosts, interleaved | p ghosts]`` (csrc/sfem_stokes.cu):
+    returns ``(hole, gap_p)`` -- ``hole`` = velocity PAIRS between the owned and the ghost velocity dofs in K's column
+    numbering (the owned pressure entries live there), ``gap_p`` = entries between the owned and the ghost pressure
+    dofs in B^T's column numbering (pad + the velocity ghosts)."""
+    hole = (int(nv_own) + 1) // 2
+    return hole, (2 * hole - int(nv_own)) + 2 * int(n2_ghost)
 
 
 def emulate_exchange(parts: List[LevelPartition], xs: List[np.ndarray], nb: int = 1) -> None:

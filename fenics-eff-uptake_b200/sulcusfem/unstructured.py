@@ -122,8 +122,162 @@ def _smooth(points, cells, fixed_mask):
     return new
 
 
-def mesh_domain(L=10.0, H=1.0, w=0.5, d=1.0, h=0.02, domain_type='sulcus', smooth_passes=2) -> HostMesh:
-    """Unstructured isotropic mesh of the sulcus or rectangular domain."""
+# ------------------------------------------------------------------------------------ graded meshes
+def threshold_size_field(pts, nodes, lc, lc_fine, dist_min, dist_max):
+    """Gmsh ``Field[1] = Distance`` (to the node list) + ``Field[2] = Threshold`` exactly as the reference's ``.geo``
+    file sets them (``mesh.py:330-337``): ``LcMin`` within ``DistMin`` of the nearest sulcus node, ``LcMax`` beyond
+    ``DistMax``, linear in between."""
+    dist, _ = cKDTree(np.asarray(nodes)).query(np.asarray(pts))
+    t = np.clip((dist - dist_min) / max(dist_max - dist_min, 1e-300), 0.0, 1.0)
+    return lc_fine + t * (lc - lc_fine)
+
+
+def reference_sulcus_nodes(L, w, d, n_segments=20):
+    """The 21 floor samples the reference lists in ``Field[1].NodesList`` (``mesh.py:139-155``), for BOTH domain types
+    (on the rectangle they lie below the floor: the "imaginary sulcus")."""
+    x_rel = np.arange(n_segments + 1) / n_segments
+    x = (L / 2 - w / 2) + x_rel * w
+    y = -d * np.sin(np.pi * x_rel)
+    y[0] = y[-1] = 0.0
+    return np.stack([x, y], axis=1)
+
+
+def _dyadic_level(size, h_f, lmax):
+    """Largest lattice level whose spacing h_f 2^l does not exceed the requested size."""
+    return np.clip(np.floor(np.log2(np.maximum(size, h_f) / h_f + 1e-9)).astype(np.int64), 0, lmax)
+
+
+def _sample_polyline_graded(dense, size_fn):
+    """Points along the dense polyline ``dense`` ([M, 2], end points included) spaced by ``size_fn``: the metric length
+    int ds / size is split into an integer number of equal parts.  Returns the samples WITHOUT the end point."""
+    seg = np.hypot(*np.diff(dense, axis=0).T)
+    mid = 0.5 * (dense[1:] + dense[:-1])
+    m = np.concatenate([[0.0], np.cumsum(seg / size_fn(mid))])
+    n = max(1, int(round(m[-1])))
+    tgt = np.linspace(0.0, m[-1], n + 1)[:-1]
+    arc = np.concatenate([[0.0], np.cumsum(seg)])
+    s = np.interp(tgt, m, arc)
+    out = np.stack([np.interp(s, arc, dense[:, 0]), np.interp(s, arc, dense[:, 1])], axis=1)
+    out[0] = dense[0]
+    return out
+
+
+def _mesh_domain_graded(L, H, w, d, h, domain_type, refinement_factor, smooth_passes):
+    """Locally graded mesh: the reference's ``refinement_factor`` (``lc_fine = lc / refinement_factor`` within w/10 of
+    the sulcus nodes, ``lc`` beyond w/2, ``mesh.py:266,330-337``).  Interior points come from ONE hexagonal lattice of
+    spacing lc_fine and its nested dyadic sub-lattices (spacing lc_fine 2^l): a lattice point of level l is kept where
+    the size field asks for a spacing >= lc_fine 2^l' with l' <= l, so the spacing follows the Threshold field in
+    octaves and is never coarser than it."""
+    xL, xR = L / 2 - w / 2, L / 2 + w / 2
+    rf = float(refinement_factor)
+    h_f = h / rf
+    lmax = int(math.floor(math.log2(rf) + 1e-9))
+    nodes = reference_sulcus_nodes(L, w, d)
+    h_cav = min(h, w / 3.0)
+
+    def size(p):
+        s = threshold_size_field(p, nodes, h, h_f, w / 10.0, w / 2.0)
+        if domain_type == 'sulcus' and h_cav < h:          # narrow cavities: at least three cells across (as ungraded)
+            near = (p[:, 1] < 1.5 * h) & (p[:, 0] > xL - 2 * h) & (p[:, 0] < xR + 2 * h)
+            s = np.where(near, np.minimum(s, h_cav), s)
+        return s
+
+    def qsize(p):
+        return h_f * 2.0 ** _dyadic_level(size(p), h_f, lmax)
+
+    def line(p, q):
+        n = max(2, int(math.ceil(np.linalg.norm(np.subtract(q, p)) / (0.05 * h_f))))
+        t = np.linspace(0.0, 1.0, n + 1)
+        out = np.outer(1 - t, p) + np.outer(t, q)
+        for k in (0, 1):
+            if p[k] == q[k]:
+                out[:, k] = p[k]
+        return out
+
+    def sample(p, q):
+        out = _sample_polyline_graded(line(p, q), qsize)
+        for k in (0, 1):                                   # axis-aligned walls: exact coordinate
+            if p[k] == q[k]:
+                out[:, k] = p[k]
+        return out
+    if domain_type == 'sulcus':
+        sx = np.linspace(0.0, 1.0, 8001)
+        fx = xL + sx * w
+        fy = sulcus_floor(fx, xL, w, d)
+        fy[0] = fy[-1] = 0.0
+        floor = _sample_polyline_graded(np.stack([fx, fy], axis=1), qsize)
+        floor[:, 1] = sulcus_floor(floor[:, 0], xL, w, d)
+        floor[0] = (xL, 0.0)
+        bpts = np.concatenate([sample((0.0, 0.0), (xL, 0.0)), floor, sample((xR, 0.0), (L, 0.0)),
+                               sample((L, 0.0), (L, H)), sample((L, H), (0.0, H)), sample((0.0, H), (0.0, 0.0))], axis=0)
+        mouth_inner = sample((xL, 0.0), (xR, 0.0))[1:]
+    else:
+        bpts = np.concatenate([sample((0.0, 0.0), (L, 0.0)), sample((L, 0.0), (L, H)), sample((L, H), (0.0, H)),
+                               sample((0.0, H), (0.0, 0.0))], axis=0)
+        mouth_inner = np.zeros((0, 2))
+    nb = len(bpts)
+    bsegs = np.stack([np.arange(nb), (np.arange(nb) + 1) % nb], axis=1)
+    isegs = np.zeros((0, 2), dtype=np.int64)
+    if len(mouth_inner):
+        iL = int(np.argmin(np.hypot(bpts[:, 0] - xL, bpts[:, 1])))
+        iR = int(np.argmin(np.hypot(bpts[:, 0] - xR, bpts[:, 1])))
+        ids = np.concatenate([[iL], nb + np.arange(len(mouth_inner)), [iR]])
+        isegs = np.stack([ids[:-1], ids[1:]], axis=1)
+    fixed = np.concatenate([bpts, mouth_inner], axis=0)
+    # nested hexagonal lattices: fine integer coordinates (X in units of h_f / 2, Y in units of dy)
+    y0 = -d if domain_type == 'sulcus' else 0.0
+    dy = h_f * math.sqrt(3.0) / 2.0
+    ny = int(math.ceil((H - y0) / dy)) + 2
+    nx = int(math.ceil(L / h_f)) + 3
+    # keep only the rows / columns a level can use before materialising the finest lattice everywhere: build per level
+    pts, lvl = [], []
+    for l in range(lmax, -1, -1):
+        step = 1 << l
+        jj = np.arange(0, ny, step)
+        ii = np.arange(0, 2 * nx, step)
+        Y, X = np.meshgrid(jj, ii, indexing='ij')
+        on = (((X >> l) - (Y >> l)) % 2 == 0)
+        if l < lmax:                                       # points of the coarser lattices were emitted already
+            up = step << 1
+            on &= ~((X % up == 0) & (Y % up == 0) & ((((X >> (l + 1)) - (Y >> (l + 1))) % 2) == 0))
+        P = np.stack([X[on] * (0.5 * h_f) - 0.25 * h_f, y0 + Y[on] * dy + 0.37 * dy], axis=1)
+        P = P[(P[:, 0] > 0) & (P[:, 0] < L) & (P[:, 1] < H)]
+        if l < lmax:                                       # a finer point is only needed where the field asks for it
+            P = P[_dyadic_level(size(P), h_f, lmax) <= l]
+        pts.append(P)
+        lvl.append(np.full(len(P), l))
+    lat = np.concatenate(pts, axis=0)
+    poly = bpts
+    lat = lat[_inside_polygon(poly, lat)]
+    dist, _ = cKDTree(fixed).query(lat)
+    lat = lat[dist >= 0.8 * qsize(lat)]
+    points = np.concatenate([fixed, lat], axis=0)
+    fixed_mask = np.zeros(len(points), dtype=bool)
+    fixed_mask[:len(fixed)] = True
+    h_min = min(h_f, h_cav)
+    cells = _triangulate(points, poly, h_min)
+    if not _validate(cells, len(points), bsegs, isegs):
+        raise RuntimeError("graded mesher: boundary/mouth recovery failed")
+    for _ in range(smooth_passes):
+        trial = _smooth(points, cells, fixed_mask)
+        tcells = _triangulate(trial, poly, h_min)
+        if _validate(tcells, len(trial), bsegs, isegs):
+            points, cells = trial, tcells
+        else:
+            break
+    geo = {'domain_type': domain_type, 'L': float(L), 'H': float(H), 'h': float(h), 'mesher': 'delaunay-graded',
+           'refinement_factor': rf, 'lc_fine': h_f}
+    if domain_type == 'sulcus':
+        geo.update({'w': float(w), 'd': float(d), 'xL': float(xL), 'xR': float(xR)})
+    return HostMesh(points, cells, geo).check()
+
+
+def mesh_domain(L=10.0, H=1.0, w=0.5, d=1.0, h=0.02, domain_type='sulcus', smooth_passes=2,
+                refinement_factor=1) -> HostMesh:
+    """Unstructured isotropic mesh of the sulcus or rectangular domain; ``refinement_factor`` > 1 grades it towards
+    the sulcus like the reference's Distance / Threshold size field."""
+    if float(refinement_factor) > 1.0:
+        return _mesh_domain_graded(L, H, w, d, h, domain_type, refinement_factor, smooth_passes)
     xL, xR = L / 2 - w / 2, L / 2 + w / 2
     if domain_type == 'sulcus':
         h_cav = min(h, w / 3.0)

@@ -234,6 +234,19 @@ sfem_stokes_t sfem_stokes_create(int n2, int nv,
                                  sfem_mg_t mg,
                                  int nz, const int* zt_rowptr, const int* zt_cols, const double* zt_vals,
                                  const int* zidx, const double* zw, const double* Cc);
+/* Row-partitioned variant for one rank of a multi-GPU solve (BASELINE config 5): n2 / nv = OWNED velocity / pressure
+ * dofs; all matrices hold the owned rows, columns in the rank-local numbering [owned | hole | ghosts] planned by
+ * sulcusfem/dist.py; n_alloc = length of b, x and every work vector, nv_alloc = length of a pressure work vector.
+ * Halo patterns are attached to K, B^T and Mp with sfem_halo_attach; the Krylov scalars are all-reduced in-kernel. */
+sfem_stokes_t sfem_stokes_create_part(int n2, int nv,
+                                      int K_nnz, const int* K_rowptr, const int* K_cols, const double* K_vals,
+                                      int B_nnz, const int* B_rowptr, const int* B_cols, const double* B_vals,
+                                      const int* BT_rowptr, const int* BT_cols, const double* BT_vals,
+                                      int Mp_nnz, const int* Mp_rowptr, const int* Mp_cols, const double* Mp_vals,
+                                      sfem_mg_t mg,
+                                      int nz, const int* zt_rowptr, const int* zt_cols, const double* zt_vals,
+                                      const int* zidx, const double* zw, const double* Cc,
+                                      int BT_nnz, long long n_alloc, long long nv_alloc);
 int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, int maxit, double* h_info, void* stream);
 void sfem_stokes_destroy(sfem_stokes_t h);
 

@@ -249,18 +249,20 @@ def test_stokes_assembly_and_dirichlet(ctx, small):
 
 
 def test_dense_inverse(ctx):
+    """Blocked (32 x 32) multi-CTA Gauss-Jordan: sizes below / at / across block boundaries, called back to back on one
+    stream (the workspace is shared) and with a growing workspace."""
     import torch
     import scipy.sparse as sp
     from sulcusfem import capi
     from sulcusfem.device import DeviceCsr, P
-    n = 150
-    A = (sp.random(n, n, 0.05, random_state=3) + sp.eye(n) * 3).tocsr()
-    A.sort_indices()
-    dA = DeviceCsr(ctx, n, n, A.indptr, A.indices, A.data)
-    out = ctx.zeros(n * n)
-    capi.check(ctx.lib.sfem_dense_inverse_csr(n, P(dA.rowptr), P(dA.cols), P(dA.vals), P(out), ctx.stream))
-    inv = out.cpu().numpy().reshape(n, n)
-    assert np.abs(inv @ A.toarray() - np.eye(n)).max() < 1e-11
+    for n in (1, 5, 32, 33, 150, 64, 449, 1000):
+        A = (sp.random(n, n, min(1.0, 8.0 / n), random_state=3 + n) + sp.eye(n) * 3).tocsr()
+        A.sort_indices()
+        dA = DeviceCsr(ctx, n, n, A.indptr, A.indices, A.data, staged=False, sell=False)
+        out = ctx.zeros(n * n)
+        capi.check(ctx.lib.sfem_dense_inverse_csr(n, P(dA.rowptr), P(dA.cols), P(dA.vals), P(out), ctx.stream))
+        inv = out.cpu().numpy().reshape(n, n)
+        assert np.abs(inv @ A.toarray() - np.eye(n)).max() < 1e-11, n
 
 
 def test_diffusion_solve_matches_lu(ctx, small, engine):

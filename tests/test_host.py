@@ -571,3 +571,45 @@ def test_simulation_save_results_json(tmp_path):
     assert out['mesh_info']['num_cells'] == mesh.num_cells and out['mass_metrics']['total_mass'] == 1.5
     assert out['mass_metrics']['profiles_full']['x'] == [0.0, 1.0, 2.0] and out['mu_eff_comparison'] is None
     assert out['params']['mode'] == 'no-adv' if 'mode' in out['params'] else True
+
+
+@pytest.mark.parametrize('domain', ['sulcus', 'rectangular'])
+def test_refinement_factor_grades_the_mesh_like_the_threshold_field(domain):
+    """reference mesh.py:266,330-337: lc_fine = lc / refinement_factor within w/10 of the sulcus nodes, lc beyond w/2,
+    linear in between (Gmsh Distance + Threshold fields).  The graded mesher must follow that field (in octaves,
+    never coarser), leave the far field at lc and keep the marker / boundary contracts of the ungraded mesher."""
+    from sulcusfem import hostmesh as hm
+    from sulcusfem.mesh import MeshGenerator
+    from sulcusfem.unstructured import reference_sulcus_nodes, threshold_size_field
+    L, H, w, d, lc, rf = 10.0, 1.0, 0.5, 1.0, 0.05, 4
+    out = MeshGenerator(L, H, d, w, lc, rf, domain).generate_mesh()
+    base = MeshGenerator(L, H, d, w, lc, 1, domain).generate_mesh()
+    mesh = out['mesh']
+    assert mesh.geometry['mesher'] == 'delaunay-graded' and mesh.num_cells > 1.2 * base['mesh'].num_cells
+    assert mesh.num_cells < 0.5 * rf * rf * base['mesh'].num_cells          # local, not uniform, refinement
+    p = mesh.coords[mesh.cells]
+    e = np.stack([np.hypot(*(p[:, i] - p[:, (i + 1) % 3]).T) for i in range(3)], axis=1).mean(axis=1)
+    nodes = reference_sulcus_nodes(L, w, d)
+    s = threshold_size_field(p.mean(axis=1), nodes, lc, lc / rf, w / 10, w / 2)
+    assert (e / s).max() < 1.5 and (e / s).min() > 0.35                     # follows the field within an octave
+    from scipy.spatial import cKDTree
+    dist, _ = cKDTree(nodes).query(p.mean(axis=1))
+    assert abs(np.median(e[dist < w / 10]) / (lc / rf) - 1.0) < 0.15        # LcMin near the sulcus nodes
+    assert abs(np.median(e[dist > w]) / lc - 1.0) < 0.15                    # LcMax in the far field
+    area = np.abs(mesh.signed_areas())
+    q = 4 * np.sqrt(3) * area / (np.stack([np.hypot(*(p[:, i] - p[:, (i + 1) % 3]).T) for i in range(3)], axis=1) ** 2).sum(axis=1)
+    assert q.min() > 0.4 and q.mean() > 0.95
+    expect = 10.0 + (2 * w * d / np.pi if domain == 'sulcus' else 0.0)
+    assert abs(area.sum() - expect) < 5e-3
+    # markers: same ids on the same boundary pieces
+    bm = out['bc_markers'].values
+    assert set(np.unique(bm[mesh.edge_on_boundary])) == {1, 2, 3, 4}
+    if domain == 'sulcus':
+        assert set(np.unique(out['domain_markers'].values)) == {1, 2}
+        y0 = out['y0_markers'].values
+        assert (y0 == 10).sum() > 0
+    # the multigrid hierarchy coarsens a graded mesh with the same grading
+    from sulcusfem.hierarchy import build_hierarchy
+    hier = build_hierarchy(mesh)
+    assert len(hier.meshes) >= 3 and hier.meshes[1].geometry.get('mesher') == 'delaunay-graded'
+    assert hier.meshes[-1].num_vertices < 0.1 * mesh.num_vertices

@@ -160,3 +160,74 @@ def test_case_sharding_round_robin():
     got = [shard_cases(cases, r, 8) for r in range(8)]
     assert sorted(sum(got, [])) == cases
     assert max(map(len, got)) - min(map(len, got)) <= 1
+
+
+@pytest.mark.parametrize('nranks', [2, 3])
+def test_stokes_vector_layout_with_contiguous_owned_part(nranks):
+    """Row-partitioned Taylor-Hood apply in the layout of csrc/sfem_stokes.cu / sulcusfem/dist.py::DistStokesProblem:
+    [u owned (interleaved) | p owned | pad | u ghosts | p ghosts].  numpy model: local K (2 right-hand sides), B, B^T
+    with the planner's column numbering + the halo exchanges must reproduce the global saddle-point apply."""
+    import scipy.sparse as sp
+    from sulcusfem import hostmesh as hm, dofmap as dm, partition as pt
+    mesh = hm.rectangle_mesh(10.0, 1.0, 24, 5)
+    n2, nv = dm.p2_num_dofs(mesh), mesh.num_vertices
+    cd = dm.p2_cell_dofs(mesh)
+    patk = dm.build_pattern(n2, n2, [(cd, cd)])
+    pb, pbt, _, _ = dm.stokes_block_plans(mesh)
+    rng = np.random.default_rng(3)
+    K = sp.csr_matrix((rng.random(patk.nnz), patk.cols, patk.rowptr), shape=(n2, n2))
+    B = sp.csr_matrix((rng.random(pb.nnz), pb.cols[:pb.nnz], pb.rowptr), shape=(nv, 2 * n2))
+    BT = sp.csr_matrix((rng.random(pbt.nnz), pbt.cols[:pbt.nnz], pbt.rowptr), shape=(2 * n2, nv))
+    X = dm.p2_dof_coordinates(mesh)
+    owner_u = pt.slab_owner(X[:, 0], nranks, X[:, 1])
+    owner_p = owner_u[:nv]
+    gh_u = pt.ghost_sets(owner_u, nranks, [(patk.rowptr, patk.cols, owner_u),
+                                           (pb.rowptr, pb.cols.astype(np.int64) // 2, owner_p)])
+    gh_p = pt.ghost_sets(owner_p, nranks, [(pbt.rowptr, pbt.cols, np.repeat(owner_u, 2))])
+    base = [5] * nranks
+    lus, lps = [], []
+    for r in range(nranks):
+        nv_own = int((owner_p == r).sum())
+        hole, _ = pt.stokes_gaps(nv_own, 0)
+        lus.append(pt.partition_level(owner_u, nranks, r, gh_u, base, nb_max=2, ghost_gap=hole))
+    base = lus[0].all_mailbox_ends
+    for r in range(nranks):
+        nv_own = int((owner_p == r).sum())
+        _, gap_p = pt.stokes_gaps(nv_own, len(lus[r].ghost))
+        lps.append(pt.partition_level(owner_p, nranks, r, gh_p, base, nb_max=1, ghost_gap=gap_p))
+    # global vectors (solver layout: interleaved velocity | pressure) and the global apply
+    zu, zp = rng.random((n2, 2)), rng.random(nv)
+    yu = K @ zu + (BT @ zp).reshape(n2, 2)
+    yp = B @ zu.ravel()
+    # local vectors
+    zs = []
+    for lu, lp in zip(lus, lps):
+        n_alloc = 2 * lu.n_loc + len(lp.ghost)
+        z = np.full(n_alloc, np.nan)
+        z[:2 * lu.n_own] = zu[lu.owned].ravel()
+        z[2 * lu.n_own:2 * lu.n_own + lp.n_own] = zp[lp.owned]
+        assert 2 * lu.n_own + lp.n_own <= 2 * (lu.n_own + lu.ghost_gap)          # owned pressure fits in the hole
+        assert 2 * lu.n_own + lp.n_loc == n_alloc                                # pressure ghosts end the vector
+        zs.append(z)
+    pt.emulate_exchange(lus, [z[:2 * lu.n_loc] for z, lu in zip(zs, lus)], nb=2)
+    pt.emulate_exchange(lps, [z[2 * lu.n_own:] for z, lu in zip(zs, lus)], nb=1)
+    for r, (lu, lp, z) in enumerate(zip(lus, lps, zs)):
+        rp, lc, slot = pt.localize_csr(patk.rowptr, patk.cols, lu.owned, lu.g2l)
+        Kl = sp.csr_matrix((K.data[slot], lc, rp), shape=(lu.n_own, lu.n_loc))
+        col_b = np.full(2 * n2, -1, dtype=np.int64)
+        ok = lu.g2l >= 0
+        col_b[0::2] = np.where(ok, 2 * lu.g2l, -1)
+        col_b[1::2] = np.where(ok, 2 * lu.g2l + 1, -1)
+        rp, lc, slot = pt.localize_csr(pb.rowptr, pb.cols, lp.owned, col_b)
+        Bl = sp.csr_matrix((B.data[slot], lc, rp), shape=(lp.n_own, 2 * lu.n_loc))
+        rows_bt = np.stack([2 * lu.owned, 2 * lu.owned + 1], axis=1).ravel()
+        rp, lc, slot = pt.localize_csr(pbt.rowptr, pbt.cols, rows_bt, lp.g2l)
+        BTl = sp.csr_matrix((BT.data[slot], lc, rp), shape=(2 * lu.n_own, lp.n_loc))
+        zu_l = np.nan_to_num(z[:2 * lu.n_loc], nan=0.0).reshape(lu.n_loc, 2)     # the hole holds pressure / pad: K never reads it
+        assert not np.isnan(z[:2 * lu.n_loc].reshape(lu.n_loc, 2)[np.unique(Kl.indices)]).any()
+        zp_l = z[2 * lu.n_own:]
+        assert not np.isnan(zp_l[np.unique(BTl.indices)]).any()
+        got_u = Kl @ zu_l + (BTl @ np.nan_to_num(zp_l, nan=0.0)).reshape(lu.n_own, 2)
+        got_p = Bl @ np.nan_to_num(z[:2 * lu.n_loc], nan=0.0)
+        assert np.allclose(got_u, yu[lu.owned], rtol=1e-13, atol=1e-13)
+        assert np.allclose(got_p, yp[lp.owned], rtol=1e-13, atol=1e-13)
