@@ -37,6 +37,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 
 namespace sfem {
@@ -174,6 +175,7 @@ struct SellPlan {
   double* svals = nullptr;           // device [padded]
   const double* csr_vals = nullptr;  // the CSR value array this mirror follows
   bool dirty = true;
+  std::thread::id dirty_by;          // thread whose entry wrote the CSR values last (it owns the stream they were written on)
 };
 std::mutex g_mu;
 std::unordered_map<const int*, SellPlan> g_plans;              // by rowptr address
@@ -320,13 +322,19 @@ void sell_mark_dirty(const double* csr_vals) {
   auto pit = g_plans.find(it->second);
   if (pit == g_plans.end()) return;
   if (!pit->second.dirty) { pit->second.dirty = true; g_ndirty.fetch_add(1); }
+  pit->second.dirty_by = std::this_thread::get_id();
 }
 
 int sell_ensure_all(cudaStream_t st) {
   if (g_ndirty.load(std::memory_order_relaxed) <= 0) return SFEM_OK;
+  // Only mirrors the engine would serve (>= min_rows; smaller ones stay dirty and cost nothing) and only those whose
+  // values were written by THIS thread: with several solver threads (sweep.run_concurrent, one stream each) another
+  // thread's matrix may be half-assembled on a stream this one is not ordered with.
+  const int mr = min_rows();
+  const std::thread::id me = std::this_thread::get_id();
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& kv : g_plans)
-    if (kv.second.dirty) SFEM_TRY(pack_locked(kv.second, st));
+    if (kv.second.dirty && kv.second.nrows >= mr && kv.second.dirty_by == me) SFEM_TRY(pack_locked(kv.second, st));
   return SFEM_OK;
 }
 
@@ -353,6 +361,7 @@ int sfem_sell_register(const int* rowptr, const double* csr_vals, int nrows, int
   P.parts = parts; P.nparts = nparts;
   P.slice_ptr = slice_ptr; P.perm = perm; P.scols = scols; P.src = src; P.svals = svals; P.csr_vals = csr_vals;
   P.dirty = true;
+  P.dirty_by = std::this_thread::get_id();
   std::lock_guard<std::mutex> lk(g_mu);
   auto old = g_plans.find(rowptr);
   if (old != g_plans.end()) {

@@ -27,7 +27,8 @@ def _plan(mesh_results, domain_type):
     if cache is None:
         cache = {}
         setattr(mesh, '_sfem_cache', cache)
-    key = ('functionals', domain_type)
+    from .solvers import _slot_key
+    key = _slot_key(('functionals', domain_type))
     if key not in cache:
         from .device import FunctionalPlan
         cache[key] = FunctionalPlan(mesh, mesh_results, domain_type)

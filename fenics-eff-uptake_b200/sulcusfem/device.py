@@ -36,6 +36,8 @@ class Context:
             raise capi.SulcusFemError("no CUDA device: sulcusfem has no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         torch.cuda.set_device(self.device)
+        if dm.DEVICE_SORT is None:
+            dm.DEVICE_SORT = self.device         # large CSR patterns / gather maps are sorted on the device from now on
 
     @classmethod
     def get(cls):

@@ -93,6 +93,50 @@ class CsrPattern:
         return int(self.cols.shape[0])
 
 
+# Set by ``device.Context`` (never in the host-only worker processes of ``simulation.prefetch_meshes``): the CUDA device
+# on which large patterns are sorted.  The key sort is >= 85 % of the host set-up time of a refined mesh (numpy's stable
+# int64 sort: ~10 s for the 34 M element entries of the bench mesh); on the device it takes milliseconds.  Both paths are
+# the same stable sort of the same keys, hence bit-identical outputs (tests/test_gpu_core.py).
+DEVICE_SORT = None
+DEVICE_SORT_MIN = 1 << 20
+
+
+def _build_pattern_device(nrows, ncols, families, device) -> CsrPattern:
+    import torch
+    key_parts, bases = [], []
+    base = 0
+    for rows, cols in families:
+        n, a = np.asarray(rows).shape
+        b = np.asarray(cols).shape[1]
+        bases.append(base)
+        if n:
+            r = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int64)).to(device)
+            c = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int64)).to(device)
+            key_parts.append((r[:, :, None] * int(ncols) + c[:, None, :]).reshape(-1))
+        base += n * a * b
+    if base >= 2 ** 31:
+        raise ValueError("element buffer exceeds int32 addressing")
+    keys = torch.cat(key_parts) if len(key_parts) > 1 else key_parts[0]
+    del key_parts
+    # element-buffer codes are base_f + u a_f b_f + i b_f + j = the running index of the concatenated key list, so the
+    # sorted codes are the sort permutation itself
+    skeys, order = torch.sort(keys, stable=True)
+    del keys
+    new = torch.ones(skeys.numel(), dtype=torch.bool, device=device)
+    new[1:] = skeys[1:] != skeys[:-1]
+    starts = torch.nonzero(new).reshape(-1)
+    ukeys = skeys[starts]
+    del skeys, new
+    contrib_ptr = torch.cat([starts, torch.tensor([order.numel()], device=device, dtype=starts.dtype)]).to(torch.int32)
+    contrib_code = order.to(torch.int32)
+    r = torch.div(ukeys, int(ncols), rounding_mode='floor')
+    c = (ukeys - r * int(ncols)).to(torch.int32)
+    rowptr = torch.zeros(nrows + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(torch.bincount(r, minlength=nrows), 0)
+    return CsrPattern(nrows, ncols, rowptr.to(torch.int32).cpu().numpy(), c.cpu().numpy(), contrib_ptr.cpu().numpy(),
+                      contrib_code.cpu().numpy(), bases, base)
+
+
 def build_pattern(nrows: int, ncols: int,
                   families: Sequence[Tuple[np.ndarray, np.ndarray]]) -> CsrPattern:
     """CSR pattern + gather map for a list of element families.
@@ -102,6 +146,10 @@ def build_pattern(nrows: int, ncols: int,
     ``family_base[f] + u*a_f*b_f + i*b_f + j`` (one row-major element matrix per unit), so the
     gather kernel finds the entries of one matrix row of one cell inside one short span.
     """
+    if DEVICE_SORT is not None:
+        total = sum(int(np.asarray(r).shape[0]) * int(np.asarray(r).shape[1]) * int(np.asarray(c).shape[1]) for r, c in families)
+        if total >= DEVICE_SORT_MIN:
+            return _build_pattern_device(nrows, ncols, families, DEVICE_SORT)
     key_parts, code_parts, bases = [], [], []
     base = 0
     for rows, cols in families:
@@ -131,9 +179,8 @@ def build_pattern(nrows: int, ncols: int,
     r = ukeys // ncols
     c = (ukeys % ncols).astype(np.int32)
     rowptr = np.zeros(nrows + 1, dtype=np.int64)
-    np.add.at(rowptr, r + 1, 1)
-    rowptr = np.cumsum(rowptr).astype(np.int32)
-    return CsrPattern(nrows, ncols, rowptr, c, contrib_ptr, contrib_code, bases, base)
+    rowptr[1:] = np.cumsum(np.bincount(r, minlength=nrows))
+    return CsrPattern(nrows, ncols, rowptr.astype(np.int32), c, contrib_ptr, contrib_code, bases, base)
 
 
 def memo_pattern(mesh: HostMesh, key, nrows: int, ncols: int, families) -> CsrPattern:

@@ -125,7 +125,7 @@ class Hierarchy:
     transfers: List[Transfer]       # transfers[0]: P1(mesh0)->P2(mesh0); transfers[l]: P1(mesh_l)->P1(mesh_{l-1})
 
 
-def build_hierarchy(mesh: HostMesh, coarsest_vertices: int = 400, max_levels: int = 12) -> Hierarchy:
+def build_hierarchy(mesh: HostMesh, coarsest_vertices: int = 700, max_levels: int = 12) -> Hierarchy:
     meshes = [mesh]
     transfers = [midpoint_transfer(mesh)]
     m = mesh

@@ -40,6 +40,14 @@ def _cache(mesh):
     return c
 
 
+def _slot_key(key):
+    """Cache key of a device object: unchanged on the main thread, tagged with the worker's slot inside
+    ``sweep.run_concurrent`` (concurrent cases own separate device buffers, graphs and streams)."""
+    from .sweep import current_slot
+    slot = current_slot()
+    return key if slot == 0 else (key, 'slot', slot)
+
+
 def _markers_array(m):
     return np.asarray(m.array() if hasattr(m, 'array') else m)
 
@@ -56,7 +64,7 @@ def scalar_problem(mesh, bc_markers, robin_id=4):
     """Cached device problem (patterns, gather maps, multigrid hierarchy) of one mesh."""
     from .device import ScalarProblem
     c = _cache(mesh)
-    key = ('scalar', int(robin_id))
+    key = _slot_key(('scalar', int(robin_id)))
     if key not in c:
         c[key] = ScalarProblem(mesh, _markers_array(bc_markers), dirichlet_ids=(1, 2), robin_id=robin_id,
                                hierarchy=_hierarchy(mesh))
@@ -66,9 +74,10 @@ def scalar_problem(mesh, bc_markers, robin_id=4):
 def stokes_problem(mesh, bc_markers):
     from .device import StokesProblem
     c = _cache(mesh)
-    if 'stokes' not in c:
-        c['stokes'] = StokesProblem(mesh, _markers_array(bc_markers), hierarchy=_hierarchy(mesh))
-    return c['stokes']
+    key = _slot_key('stokes')
+    if key not in c:
+        c[key] = StokesProblem(mesh, _markers_array(bc_markers), hierarchy=_hierarchy(mesh))
+    return c[key]
 
 
 def _check_space(C, kind):

@@ -6,6 +6,8 @@ files with the reference's exact column names -- without the plotting / menu lay
     adv_diff_analysis.py:177-300       run_advdiff_step_...  run_advdiff_step_validation  advdiff_validation_step_pe_x_mu.csv
     no_advection_analysis_A.py:1257-1347  run_mu_sweep       run_mu_sweep             mu_parameter_sweep_results.csv
     no_advection_analysis_A.py:1349-1452  run_aspect_ratio_analysis  run_aspect_ratio_analysis  aspect_ratio_analysis_results.csv
+    no_advection_analysis_A.py:1463-1581  run_geometry_analysis  run_geometry_analysis    geometry_analysis_results.csv
+    no_advection_analysis_A.py:1583-1682  run_mu_eff_analysis    run_mu_eff_analysis      mu_eff_analysis_results.csv
     no_uptake_analysis.py:50-313,921-975  run_geometry_study  run_geometry_study      geometry_comparison_results.csv
 
 The reference runs every case serially; the cases are independent, so each driver deals them round-robin to the
@@ -22,6 +24,7 @@ import contextlib
 import io
 import json
 import os
+import threading
 import time
 from typing import Dict, Iterable, List, Optional, Sequence
 
@@ -45,10 +48,20 @@ def _world(rank, world):
 
 
 def _run(quiet, **kw):
-    if not quiet:
-        return run_simulation(**kw)
+    from .sweep import current_slot
+    if not quiet or current_slot() != 0 or threading.current_thread() is not threading.main_thread():
+        return run_simulation(**kw)             # worker threads: stdout is redirected once, around the whole pool
     with contextlib.redirect_stdout(io.StringIO()):
         return run_simulation(**kw)
+
+
+def _sharded(cases, one, rank, world, streams, quiet):
+    """``sweep.run_sharded`` with the study's stdout handling: with several streams the (process-global) redirect is
+    set once around the worker pool instead of once per case."""
+    if streams > 1 and quiet:
+        with contextlib.redirect_stdout(io.StringIO()):
+            return run_sharded(cases, one, rank, world, streams=streams)
+    return run_sharded(cases, one, rank, world, streams=streams)
 
 
 def _prefetch(jobs, rank=0, world=1, enable=True):
@@ -140,7 +153,7 @@ def phase_b_row(gkey, gcfg, mu, conc_s, conc_r, flux_s, flux_r):
 
 
 def run_no_adv_mu_sweep(output_dir=None, mu_factors: Iterable[float] = None, geometries: Optional[Dict] = None,
-                        mesh_size_dim=0.02, rank=None, world=None, quiet=True, prefetch=True):
+                        mesh_size_dim=0.02, rank=None, world=None, quiet=True, prefetch=True, streams=1):
     """Reference ``run_no_adv_mu_sweep`` (23 geometries x 3 mu x {sulcus, rectangle} = 138 solves by default).
     Returns the DataFrame with the reference's columns; rank 0 writes ``no_adv_mu_sweep_results.csv``."""
     rank, world = _world(rank, world)
@@ -151,7 +164,7 @@ def run_no_adv_mu_sweep(output_dir=None, mu_factors: Iterable[float] = None, geo
     _prefetch([[(_params_no_adv(mu, cfg['sulci_w_dim'], cfg['sulci_h_dim'], mesh_size_dim), 'sulcus'),
                 (_params_no_adv(mu, cfg['sulci_w_dim'], cfg['sulci_h_dim'], mesh_size_dim), 'rectangular')]
                for mu, _, cfg in cases], rank, world, prefetch)
-    done = run_sharded(cases, lambda c: phase_b_case(c, mesh_size_dim, quiet), rank, world)
+    done = _sharded(cases, lambda c: phase_b_case(c, mesh_size_dim, quiet), rank, world, streams, quiet)
     df = _frame([row for _, row in done], ['mu_factor', 'geometry'])
     p0 = Parameters(mode='no-adv')
     p0.validate()
@@ -321,7 +334,7 @@ def _slim(result, **extra):
 
 
 def run_mu_sweep(output_dir=None, regimes: Optional[Dict[str, List[float]]] = None, w_dim=0.25, h_dim=0.25,
-                 mesh_size_dim=0.02, rank=None, world=None, quiet=True):
+                 mesh_size_dim=0.02, rank=None, world=None, quiet=True, streams=1):
     """Reference ``run_mu_sweep``: 20 mu values in three uptake regimes on the 0.25 x 0.25 mm sulcus; the mesh,
     patterns and multigrid hierarchy are built once and reused by every mu.  Rank 0 writes
     ``mu_parameter_sweep_results.csv``."""
@@ -342,7 +355,7 @@ def run_mu_sweep(output_dir=None, regimes: Optional[Dict[str, List[float]]] = No
                    domain_type='sulcus', params=p)
         return extract_mu_sweep_data(_slim(res, regime=reg, mu_factor=factor, mu_dim_used=p.mu_dim, mu_used=p.mu,
                                            baseline_mu_dim=base), name)
-    done = run_sharded(cases, one, rank, world)
+    done = _sharded(cases, one, rank, world, streams, quiet)
     df = _frame([row for _, row in done])
     _save(df, output_dir, "mu_parameter_sweep_results.csv", None, rank)
     return df
@@ -392,6 +405,116 @@ def run_aspect_ratio_analysis(output_dir=None, cases=None, mesh_size_dim=0.02, r
     done = run_sharded(cases, one, rank, world)
     df = _frame([row for _, row in done])
     _save(df, output_dir, "aspect_ratio_analysis_results.csv", None, rank)
+    return df
+
+
+# ====================================================================== Phase A: geometry analysis and mu_eff spatial analysis
+def extract_geometry_analysis_data(result, config_name, geometry_name, mu_value, mu_factor, config_results=None):
+    """no_advection_analysis_A.py:165-231 (same columns, same order)."""
+    row = {'Config': config_name, 'Geometry_Name': geometry_name, 'Mu_Value': mu_value, 'Mu_Factor': mu_factor}
+    if config_results and 'geometry_config' in config_results:
+        g = config_results['geometry_config']
+        w, h = g.get('sulci_w_dim'), g.get('sulci_h_dim')
+        row['Sulcus_Width_mm'], row['Sulcus_Depth_mm'] = w, h
+        if w and h and w > 0:
+            row['Aspect_Ratio'] = h / w
+        row['Aspect_Ratio_Category'] = g.get('aspect_ratio_category', 'unknown')
+    row.update(_mu_eff_columns(result))
+    return row
+
+
+def extract_mu_eff_analysis_data(result, config_name, mu_value, mu_factor):
+    """no_advection_analysis_A.py:233-296 (same columns, same order; mu(x) sampled at 100 points of the floor)."""
+    from .analysis import sample_mu_along_bottom
+    row = {'Config': config_name, 'Mu_Value': mu_value, 'Mu_Factor': mu_factor}
+    params = result.get('params')
+    if params is not None:
+        row.update({'Sulcus_Width_mm': getattr(params, 'sulci_w_dim', 0.5), 'Sulcus_Depth_mm': getattr(params, 'sulci_h_dim', 1.0),
+                    'Domain_Length_mm': getattr(params, 'L_dim', 10.0),
+                    'L_ref': getattr(params, 'L_ref', getattr(params, 'H_dim', 1.0)),
+                    'L_nondim': getattr(params, 'L', 10.0), 'H_nondim': getattr(params, 'H', 1.0),
+                    'Sulcus_W_nondim': getattr(params, 'sulci_w', 0.5), 'Sulcus_H_nondim': getattr(params, 'sulci_h', 1.0),
+                    'Mu_base_nondim': getattr(params, 'mu', mu_value)})
+    else:
+        row.update({'Sulcus_Width_mm': 0.5, 'Sulcus_Depth_mm': 1.0, 'Domain_Length_mm': 10.0, 'L_ref': 1.0, 'L_nondim': 10.0,
+                    'H_nondim': 1.0, 'Sulcus_W_nondim': 0.5, 'Sulcus_H_nondim': 1.0, 'Mu_base_nondim': mu_value})
+    if 'mu_eff_comparison' in result:
+        d = result['mu_eff_comparison']
+        r = d.get('ratios', {})
+        row.update({'Mu_Eff_Simulation': d.get('mu_eff_sim'), 'Mu_Eff_Analytical': d.get('mu_eff_arc'),
+                    'Mu_Eff_Enhanced': d.get('mu_eff_enh'), 'Mu_Eff_Opening': d.get('mu_eff_open'),
+                    'Ratio_Sim': r.get('sim'), 'Ratio_Analytical': r.get('arc'), 'Ratio_Enhanced': r.get('enh'),
+                    'Ratio_Opening': r.get('open')})
+    try:
+        ms = sample_mu_along_bottom(result, n_points=100)
+        row.update({'Mu_Mean_Bottom': ms['mu_mean'], 'Mu_Min_Bottom': ms['mu_min'], 'Mu_Max_Bottom': ms['mu_max'],
+                    'Mu_X_Array': str(np.asarray(ms['x']).tolist()), 'Mu_Values_Array': str(np.asarray(ms['mu']).tolist())})
+    except Exception as e:
+        print(f"Warning: Could not sample mu for {config_name}: {e}")
+        row.update({'Mu_Mean_Bottom': None, 'Mu_Min_Bottom': None, 'Mu_Max_Bottom': None, 'Mu_X_Array': None,
+                    'Mu_Values_Array': None})
+    return row
+
+
+def run_geometry_analysis(output_dir=None, mu_factors=(0.1, 1.0, 10), geometries: Optional[Dict] = None, mesh_size_dim=0.02,
+                          rank=None, world=None, quiet=True, prefetch=True, streams=1):
+    """Reference ``run_geometry_analysis`` (no_advection_analysis_A.py:1463-1581): every geometry of
+    ``create_geometry_variations`` x mu factors (23 x 3 = 69 sulcus solves by default); the device problems of a
+    geometry are reused by its mu values.  Rank 0 writes ``geometry_analysis_results.csv``."""
+    rank, world = _world(rank, world)
+    base_params = Parameters(mode='no-adv', mesh_size_dim=mesh_size_dim)
+    base_params.sulci_w_dim = base_params.sulci_h_dim = 0.25                 # :1474-1477
+    base_params.validate()
+    base_params.nondim()
+    base = float(getattr(Parameters, 'MU_DIM_NO_ADV', base_params.mu_dim))
+    geos = geometries if geometries is not None else create_geometry_variations(base_params)
+    mu_factors = list(mu_factors)
+    # geometry-major case order (:1506-1507): consecutive cases of a rank share the cached geometry
+    cases = [(g, cfg, f) for g, cfg in geos.items() for f in mu_factors]
+
+    def params_of(cfg, f):
+        p = Parameters(mode='no-adv', mesh_size_dim=mesh_size_dim)
+        p.sulci_w_dim, p.sulci_h_dim = cfg['sulci_w_dim'], cfg['sulci_h_dim']
+        p.mu_dim = base * f
+        p.validate()
+        p.nondim()
+        return p
+    _prefetch([[(params_of(cfg, f), 'sulcus')] for _, cfg, f in cases], rank, world, prefetch)
+
+    def one(case):
+        g, cfg, f = case
+        name = f"{g}_mu_{f}"
+        res = _run(quiet, mode='no-adv', study_type="Phase A/Geometry Comparison Simulations", config_name=name,
+                   domain_type='sulcus', params=params_of(cfg, f))
+        return extract_geometry_analysis_data(_slim(res), name, g, base * f, f, {'geometry_config': cfg})
+    done = _sharded(cases, one, rank, world, streams, quiet)
+    df = _frame([row for _, row in done])
+    _save(df, output_dir, "geometry_analysis_results.csv", None, rank)
+    return df
+
+
+def run_mu_eff_analysis(output_dir=None, mu_factors=(0.1, 1.0, 10.0), w_dim=0.5, h_dim=1.0, mesh_size_dim=0.02, rank=None,
+                        world=None, quiet=True):
+    """Reference ``run_mu_eff_analysis`` (no_advection_analysis_A.py:1583-1682): the 0.5 x 1.0 mm sulcus at three mu
+    values, with mu(x) sampled along the floor.  Rank 0 writes ``mu_eff_analysis_results.csv`` (the reference's
+    checked-in copy of this file holds the BASELINE config-1 numbers)."""
+    rank, world = _world(rank, world)
+    base = float(getattr(Parameters, 'MU_DIM_NO_ADV', 0.0003))
+
+    def one(factor):
+        p = Parameters(mode='no-adv', mesh_size_dim=mesh_size_dim)
+        p.sulci_w_dim, p.sulci_h_dim = w_dim, h_dim
+        p.mu_dim = base * factor
+        p.validate()
+        p.nondim()
+        name = f"mu_eff_analysis_mu_{factor}x"
+        res = _run(quiet, mode='no-adv', study_type="Phase A/Mu_Eff Spatial Analysis Simulations", config_name=name,
+                   domain_type='sulcus', params=p)
+        keep = _slim(res, params=res.get('params', p), mesh_results={'mesh': res['mesh_results']['mesh']})
+        return extract_mu_eff_analysis_data(keep, name, p.mu_dim, factor)
+    done = run_sharded([float(f) for f in mu_factors], one, rank, world)
+    df = _frame([row for _, row in done])
+    _save(df, output_dir, "mu_eff_analysis_results.csv", None, rank)
     return df
 
 

@@ -13,7 +13,9 @@ FILES = {
     'mu_parameter_sweep_results.csv': 'No Advection - Phase A/Mu Parameter Sweep Analysis/mu_parameter_sweep_results.csv',
     'aspect_ratio_analysis_results.csv': 'No Advection - Phase A/Aspect Ratio Study Analysis/aspect_ratio_analysis_results.csv',
     'geometry_comparison_results.csv': 'No Uptake Simulations/Geometry Comparison Analysis/geometry_comparison_results.csv',
+    'mu_eff_analysis_results.csv': 'No Advection - Phase A/Mu_Eff Spatial Analysis Analysis/mu_eff_analysis_results.csv',
 }
+csv.field_size_limit(10 ** 9)
 out = {}
 for name, rel in FILES.items():
     with open(os.path.join(REF, rel), newline='') as f:

@@ -248,6 +248,29 @@ def test_stokes_assembly_and_dirichlet(ctx, small):
     assert np.abs(sp_.rhs.cpu().numpy() - bref).max() < 1e-15
 
 
+def test_device_sorted_patterns_are_bit_identical_to_the_host_path(ctx):
+    """dofmap.build_pattern sorts large key lists on the device (set-up wall of refined meshes); same stable sort of the
+    same keys -> every array of the pattern / gather map must equal the numpy path bit for bit."""
+    from sulcusfem import dofmap as dm, hostmesh as hm
+    mesh = hm.refine_n(hm.rectangle_mesh(10.0, 1.0, 60, 12), 1)
+    cd = dm.p2_cell_dofs(mesh)
+    n = dm.p2_num_dofs(mesh)
+    c1 = dm.p1_cell_dofs(mesh)
+    il = np.concatenate([2 * cd.astype(np.int64), 2 * cd.astype(np.int64) + 1], axis=1)
+    for nrows, ncols, fam in ((n, n, [(cd, cd), (cd[:70, :3], cd[:70, :3])]), (mesh.num_vertices, 2 * n, [(c1, il)]),
+                              (2 * n, mesh.num_vertices, [(il, c1)])):
+        saved, dm.DEVICE_SORT = dm.DEVICE_SORT, None
+        try:
+            a = dm.build_pattern(nrows, ncols, fam)
+        finally:
+            dm.DEVICE_SORT = saved
+        b = dm._build_pattern_device(nrows, ncols, fam, ctx.device)
+        for k in ('rowptr', 'cols', 'contrib_ptr', 'contrib_code'):
+            x, y = getattr(a, k), getattr(b, k)
+            assert x.dtype == y.dtype and np.array_equal(x, y), k
+        assert a.family_base == b.family_base and a.buffer_len == b.buffer_len
+
+
 def test_dense_inverse(ctx):
     """Blocked (32 x 32) multi-CTA Gauss-Jordan: sizes below / at / across block boundaries, called back to back on one
     stream (the workspace is shared) and with a growing workspace."""

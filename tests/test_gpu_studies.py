@@ -149,3 +149,52 @@ def test_concentration_profiles_against_reference_samples(tmp_path):
     # of the largest cavity (8.8e-5: it runs through the two re-entrant mouth corners)
     assert max(worst.values()) < 5e-4
     assert max(v for k, v in worst.items() if k[2] != 'mouth_level') < 2e-5
+
+
+def test_mu_eff_analysis_against_reference_csv(tmp_path):
+    """run_mu_eff_analysis (no_advection_analysis_A.py:1583-1682) at the reference's resolution: the rows of the
+    reference's checked-in mu_eff_analysis_results.csv (BASELINE config 1: 0.5 x 1.0 mm sulcus, mu x {0.1, 1, 10};
+    dolfin on a Gmsh mesh that cannot be regenerated) -- closed forms bit-exact, simulated values to mesh tolerance."""
+    from sulcusfem import studies
+    g = GOLD['mu_eff_analysis_results.csv']
+    df = studies.run_mu_eff_analysis(str(tmp_path), mesh_size_dim=0.02)
+    assert list(df.columns) == g['columns'] and len(df) == 3
+    assert os.path.exists(tmp_path / 'mu_eff_analysis_results.csv')
+    for (_, row), ref in zip(df.iterrows(), g['rows']):
+        assert row['Config'] == ref['Config']
+        assert row['Mu_Eff_Analytical'] == float(ref['Mu_Eff_Analytical'])            # scipy quad closed form: bit-exact
+        assert abs(row['Mu_Eff_Enhanced'] - float(ref['Mu_Eff_Enhanced'])) <= 2e-16 * abs(float(ref['Mu_Eff_Enhanced'])) + 1e-18
+        assert abs(row['Mu_Eff_Simulation'] / float(ref['Mu_Eff_Simulation']) - 1.0) < 2e-2     # mesh-dependent (corner singularities; 1.1 % at mu = 10)
+        assert abs(row['Mu_Eff_Opening'] / float(ref['Mu_Eff_Opening']) - 1.0) < 5e-2
+        assert abs(row['Ratio_Sim'] - row['Mu_Eff_Simulation'] / row['Mu_base_nondim']) < 1e-14
+        assert row['Mu_X_Array'] == ref['Mu_X_Array']
+
+
+def test_geometry_analysis_rows(tmp_path):
+    """run_geometry_analysis (no_advection_analysis_A.py:1463-1581): geometry x mu cases, device problems of a geometry
+    reused across its mu values; one row against the oracle on the mesh the driver used."""
+    from oracle import cpu_oracle as co
+    from sulcusfem import studies, simulation
+    from sulcusfem.parameters import Parameters, create_geometry_variations
+    geos = create_geometry_variations(Parameters(mode='no-adv'))
+    pick = {k: geos[k] for k in list(geos)[:2]}
+    df = studies.run_geometry_analysis(str(tmp_path), mu_factors=[0.1, 10], geometries=pick, mesh_size_dim=H)
+    assert len(df) == 4 and os.path.exists(tmp_path / 'geometry_analysis_results.csv')
+    assert list(df.columns)[:8] == ['Config', 'Geometry_Name', 'Mu_Value', 'Mu_Factor', 'Sulcus_Width_mm', 'Sulcus_Depth_mm',
+                                    'Aspect_Ratio', 'Aspect_Ratio_Category']
+    assert list(df['Config']) == [f"{g}_mu_{f}" for g in pick for f in (0.1, 10)]
+    row = df.iloc[1]
+    p = Parameters(mode='no-adv', mesh_size_dim=H)
+    p.sulci_w_dim, p.sulci_h_dim = row['Sulcus_Width_mm'], row['Sulcus_Depth_mm']
+    p.mu_dim = row['Mu_Value']
+    p.validate()
+    p.nondim()
+    mr = simulation._simulation_generate_mesh(p, 'sulcus')
+    om = co.Mesh(mr['mesh'].coords, mr['mesh'].cells)
+    mk = {k: mr[k].values for k in ('bc_markers', 'bottom_segment_markers', 'y0_markers', 'domain_markers')}
+    c, _, _ = co.solve_concentration(om, mk['bc_markers'], p.D, mu=p.mu)
+    fl = co.flux_metrics(om, mk, 'sulcus', p.D, c, mu=p.mu)
+    me = co.mu_eff_metrics(fl, p.L, p.sulci_h, p.sulci_w, p.mu)
+    assert abs(row['Mu_Eff_Simulation'] - me['mu_eff_sim']) <= 1e-8 * abs(me['mu_eff_sim'])
+    assert abs(row['Mu_Eff_Opening'] - me['mu_eff_open']) <= 1e-8 * abs(me['mu_eff_open'])
+    assert abs(row['Total_Mass'] - co.mass_metrics(om, c, 'sulcus', mk['domain_markers'])['total_mass']) < 1e-10

