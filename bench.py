@@ -35,7 +35,7 @@ import numpy as np  # noqa: E402
 W_SULCUS, D_SULCUS, L_CH, H_CH = 0.5, 1.0, 10.0, 1.0
 PE, MU = 40.0, 1.0
 RTOL, STOKES_RTOL = 1e-13, 1e-12          # = sulcusfem.solvers.RTOL / STOKES_RTOL (the API path's defaults; checked in main)
-CAT_NAMES = ['spmv', 'spmv_dot', 'cheb_step', 'resid_d0', 'elem', 'gather', 'vec', 'other', 'spmv_staged']
+CAT_NAMES = ['spmv', 'spmv_dot', 'cheb_step', 'resid_d0', 'elem', 'gather', 'vec', 'other', 'spmv_staged', 'halo']
 
 
 def build_mesh(h, refine):
@@ -331,6 +331,11 @@ def run_dd_strong(args, case, rank, world, dist, flush_l2):
         t1 = timed(cs.step, reps)
         info1 = {k: dict(v) for k, v in cs.info.items()}
         ref = [t.clone() for t in (st.x[:st.n2], st.x[st.n2:2 * st.n2], sc.x)]
+
+        def asm_only():                                   # assembly share of the single-GPU step (for the solve-only ratio)
+            st.assemble(bc_mode=1)
+            sc.assemble(D, ref[0], ref[1], mu_const=MU, bc_values={1: 1.0, 2: 0.0})
+        t1_asm = timed(asm_only, 3)
         t0 = time.perf_counter()
         nd_v = num_distributed_levels(st.vel, rb)
         nd_c = num_distributed_levels(sc, rb)
@@ -352,16 +357,14 @@ def run_dd_strong(args, case, rank, world, dist, flush_l2):
                     e.record()
                     ev.append((name, e))
             mark('start')
-            st.assemble(bc_mode=1)
-            ds.refresh()
-            mark('stokes_assemble+extract')
+            ds.assemble_local()
+            mark('stokes_assemble_local')
             ds.solve(rtol=STOKES_RTOL)
             mark('stokes_minres')
             ux, uy, p = ds.gather()
             mark('allgather_u')
-            sc.assemble(D, ux, uy, mu_const=MU, bc_values={1: 1.0, 2: 0.0})
-            dc.refresh()
-            mark('advdiff_assemble+extract')
+            dc.assemble_local(D, ux, uy, mu_const=MU, bc_values={1: 1.0, 2: 0.0})
+            mark('advdiff_assemble_local')
             dc.solve('fgmres', rtol=RTOL)
             mark('advdiff_fgmres')
             c = dc.gather()
@@ -369,6 +372,20 @@ def run_dd_strong(args, case, rank, world, dist, flush_l2):
             mark('allgather_c+functionals')
             return ux, uy, p, c, F
 
+        # the distributed assembly must produce exactly the rows of the replicated (global) assembly
+        st.assemble(bc_mode=1)
+        ds.refresh()
+        keep = [t.clone() for t in (ds.vel.A[0].csr.vals, ds.B.csr.vals, ds.BT.csr.vals, ds.Mp.csr.vals, ds.b[:ds.n_own])]
+        ds.assemble_local()
+        now = (ds.vel.A[0].csr.vals, ds.B.csr.vals, ds.BT.csr.vals, ds.Mp.csr.vals, ds.b[:ds.n_own])
+        # operators: bit for bit (same element arithmetic, same gather order); right-hand side: the lifting SpMV sums a
+        # row in the order of the engine's chunking, which differs between the global and the local mirror -> rounding level
+        local_equals = bool(all(torch.equal(a, b) for a, b in zip(keep[:4], now[:4]))
+                            and float((keep[4] - now[4]).norm() / keep[4].norm()) < 1e-13)
+        eq = torch.tensor([1.0 if local_equals else 0.0], dtype=torch.float64, device=ctx.device)
+        dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+        local_equals = bool(eq.item() > 0.5)
+        del keep
         for _ in range(2):
             dd_step()
         tN = timed(dd_step, reps)
@@ -377,6 +394,23 @@ def run_dd_strong(args, case, rank, world, dist, flush_l2):
         ux, uy, p, c, F = dd_step(ev)
         torch.cuda.synchronize()
         phases = {ev[i][0]: ev[i - 1][1].elapsed_time(ev[i][1]) for i in range(1, len(ev))}
+
+        # one un-graphed dd step with a CUDA event pair around every launch (all ranks run it; rank 0 reports): where
+        # the distributed step spends its kernel time, and what one peer-memory exchange costs
+        import ctypes as C
+        cap = 400000
+        lib = ctx.lib
+        dist.barrier()
+        lib.sfem_profile_start(cap)
+        dd_step()
+        cats, byts, mss = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)()
+        nrec = lib.sfem_profile_stop(cap, cats, byts, mss)
+        cats, mss = np.array(cats[:nrec]), np.array(mss[:nrec], dtype=np.float64)
+        prof = {name: {"launches": int((cats == k).sum()), "ms": float(mss[cats == k].sum())}
+                for k, name in enumerate(CAT_NAMES) if (cats == k).any()}
+        if 'halo' in prof and prof['halo']['launches']:
+            prof['halo']['note'] = "peer-memory halo exchanges and vector all-reduces (send + wait + unpack): un-graphed"
+            prof['halo']['avg_us'] = 1e3 * prof['halo']['ms'] / prof['halo']['launches']
 
         def rel(a, b):
             return float(((a - b).norm() / b.norm()).item())
@@ -387,8 +421,9 @@ def run_dd_strong(args, case, rank, world, dist, flush_l2):
                                     "c": rel(c, ref[2])},
                "iterations": {"single": {k: v['iterations'] for k, v in info1.items()},
                               "distributed": {"stokes": ds.last_info['iterations'], "advdiff": dc.last_info['iterations']}},
-               "phases_ms_last_step": phases,
-               "solve_only": {"ms_ngpu": phases['stokes_minres'] + phases['advdiff_fgmres']},
+               "phases_ms_last_step": phases, "profiled_step_by_category": prof,
+               "solve_only": {"ms_ngpu": phases['stokes_minres'] + phases['advdiff_fgmres'],
+                              "ms_1gpu_estimate": t1 - (t1_asm if t1_asm is not None else 0.0)},
                "distributed_levels": {"velocity": ds.vel.nd, "concentration": dc.nd, "replicate_below": rb},
                "exchanges_per_vcycle": {"velocity": 6 * ds.vel.nd - 2, "concentration": 6 * dc.nd - 2,
                                         "note": "per row-partitioned level: Chebyshev step, residual, restriction, prolongation, "
@@ -397,8 +432,10 @@ def run_dd_strong(args, case, rank, world, dist, flush_l2):
                "halo_bytes": {"velocity_level0_per_exchange": 16 * int(len(lu.ghost)), "owned_velocity_dofs": int(lu.n_own),
                               "concentration_level0_per_exchange": 8 * int(len(dc.parts[0].ghost))},
                "plan_s": t_plan, "setup_s": cs.setup.get('total_s'),
-               "assembly": "replicated (every rank assembles the global operators, then extracts its rows)"}
-        rec["parity_ok"] = bool(rec["rel_l2_vs_single"]["ux"] <= 1e-10 and rec["rel_l2_vs_single"]["c"] <= 1e-10
+               "assembly": "distributed: every rank assembles the rows it owns from the cells that touch them (system level "
+                           "and row-partitioned multigrid levels); only the coarse levels below replicate_below are assembled "
+                           "on every rank", "local_assembly_equals_replicated": local_equals}
+        rec["parity_ok"] = bool(local_equals and rec["rel_l2_vs_single"]["ux"] <= 1e-10 and rec["rel_l2_vs_single"]["c"] <= 1e-10
                                 and rec["rel_l2_vs_single"]["uy_abs_over_ux"] <= 1e-10)
         out.append(rec)
         ds.close()

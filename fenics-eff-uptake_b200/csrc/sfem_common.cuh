@@ -19,7 +19,7 @@ extern std::atomic<long long> g_launches;
 // bytes, milliseconds) per launch.  Disabled -> a single relaxed load per launch.
 enum ProfCat {
   PC_SPMV = 0, PC_SPMV_DOT = 1, PC_CHEB = 2, PC_RESID_D0 = 3, PC_ELEM = 4, PC_GATHER = 5, PC_VEC = 6,
-  PC_OTHER = 7, PC_SPMV_STAGED = 8
+  PC_OTHER = 7, PC_SPMV_STAGED = 8, PC_HALO = 9
 };
 struct Prof {
   Prof(int cat, double bytes, cudaStream_t st);

@@ -139,7 +139,7 @@ int halo_exchange(const Halo* h, double* x, int nb, cudaStream_t st, int phase) 
   if (h == nullptr || h->dev.nneigh == 0) return SFEM_OK;
   Dist* d = g_dist;
   if (!d) { set_error("halo exchange without an active communicator"); return SFEM_ERR_ARG; }
-  Prof prof(PC_OTHER, 16.0 * nb * h->max_cnt * h->dev.nneigh, st);
+  Prof prof(PC_HALO, 16.0 * nb * h->max_cnt * h->dev.nneigh, st);
   if (nb == 2) k_halo_exchange<2><<<h->dev.nneigh, 256, 0, st>>>(d->dev, h->dev, x, phase);
   else k_halo_exchange<1><<<h->dev.nneigh, 256, 0, st>>>(d->dev, h->dev, x, phase);
   SFEM_LAUNCH_CHECK();
@@ -151,6 +151,7 @@ int dist_allreduce_vec(Dist* d, double* x, int n, cudaStream_t st, int phase) {
   if (n > d->dev.vec_cap) { set_error("vector all-reduce larger than the mailbox capacity"); return SFEM_ERR_ARG; }
   unsigned int* ticket = reinterpret_cast<unsigned int*>(d->dev.seq + 8);
   const int grid = grid_for(n, 256 * 2, 1);
+  Prof prof(PC_HALO, 16.0 * n * d->dev.nranks, st);
   if (phase != 2) {
     k_allreduce_vec_send<<<grid, 256, 0, st>>>(d->dev, x, n, ticket);
     SFEM_LAUNCH_CHECK();

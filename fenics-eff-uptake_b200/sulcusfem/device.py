@@ -125,19 +125,19 @@ class DeviceCsr:
         self.sell = None
         if sell and self.nrows >= self.SELL_MIN_ROWS and self.nnz > 0:
             from . import sell as sl
-            plan = sl.build_plan(rp[:self.nrows + 1], cc[:self.nnz], self.SELL_SIGMA)
+            plan = sl.build_plan_device(self.rowptr[:self.nrows + 1], self.cols[:self.nnz], self.SELL_SIGMA)
             nparts = int(ctx.lib.sfem_sell_parts())
-            if plan.padded <= self.SELL_MAX_FILL * self.nnz:
+            if plan['padded'] <= self.SELL_MAX_FILL * self.nnz:
+                parts = sl.partition_slices(plan['slice_ptr'].cpu().numpy(), plan['padded'], plan['nslices'], nparts)
                 self.sell = dict(
-                    fill=plan.padded / self.nnz, nslices=plan.nslices, padded=plan.padded,
-                    slice_ptr=ctx.up(plan.slice_ptr, np.int32), perm=ctx.up(plan.perm, np.int32),
-                    scols=ctx.up(plan.scols, np.int32), src=ctx.up(plan.src, np.int32),
-                    parts=ctx.up(sl.partition(plan, nparts), np.int32), nparts=nparts,
-                    svals=torch.zeros(max(plan.padded, 1), dtype=torch.float64, device=ctx.device))
+                    fill=plan['padded'] / self.nnz, nslices=plan['nslices'], padded=plan['padded'],
+                    slice_ptr=plan['slice_ptr'], perm=plan['perm'], scols=plan['scols'], src=plan['src'],
+                    parts=ctx.up(parts, np.int32), nparts=nparts,
+                    svals=torch.zeros(max(plan['padded'], 1), dtype=torch.float64, device=ctx.device))
                 k = self.sell
-                capi.check(ctx.lib.sfem_sell_register(P(self.rowptr), P(self.vals_buf), self.nrows, plan.nslices,
+                capi.check(ctx.lib.sfem_sell_register(P(self.rowptr), P(self.vals_buf), self.nrows, plan['nslices'],
                                                       P(k['slice_ptr']), P(k['perm']), P(k['scols']), P(k['src']),
-                                                      P(k['svals']), plan.padded, P(k['parts']), nparts), 'sfem_sell_register')
+                                                      P(k['svals']), plan['padded'], P(k['parts']), nparts), 'sfem_sell_register')
 
     def mark_dirty(self):
         """Tell the library that the CSR values were written outside of it (torch ops on ``vals``)."""
@@ -509,6 +509,7 @@ class StokesProblem:
         gil = np.zeros(self.n)
         gil[0:2 * n2:2], gil[1:2 * n2:2] = g[:n2], g[n2:2 * n2]
         self.flag_il = self.ctx.up(fil, np.uint8)
+        self.g_il_host = gil                     # Dirichlet values in solver layout (read by the row-partitioned assembly)
         self.g_il.copy_(self.ctx.up(gil, np.float64))
         self._zero_n2 = self.ctx.zeros(n2)
         self._scratch_n2 = self.ctx.zeros(n2)

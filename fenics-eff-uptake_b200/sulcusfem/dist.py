@@ -91,6 +91,7 @@ class _LocalOp:
     def __init__(self, ctx, global_csr: DeviceCsr, g_rowptr, g_cols, rows, col_g2l, ncols_loc, drop_missing=False):
         rp, lc, slot = pt.localize_csr(g_rowptr, g_cols, rows, col_g2l, drop_missing=drop_missing)
         self.csr = DeviceCsr(ctx, len(rows), ncols_loc, rp, lc)
+        self.slot_host = slot
         self.slot = ctx.up(slot, np.int32)
         self.src = global_csr
         self.ctx = ctx
@@ -224,6 +225,109 @@ class AllGather:
         return out
 
 
+def _flatten_contribs(contrib_ptr, contrib_code, slot):
+    """Contribution lists of the CSR slots ``slot``: (lengths per slot, element-buffer codes, concatenated)."""
+    cp = np.asarray(contrib_ptr, dtype=np.int64)
+    slot = np.asarray(slot, dtype=np.int64)
+    lens = cp[slot + 1] - cp[slot]
+    tot = int(lens.sum())
+    idx = np.repeat(cp[slot], lens) + (np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(lens) - lens, lens))
+    return lens, np.asarray(contrib_code)[idx].astype(np.int64)
+
+
+def plan_local_gather(ops, nce, cell_family_end=None):
+    """Gather maps of the owned rows of one or more operators that read ONE element buffer, re-addressed to a buffer
+    that holds only the cells those rows touch.  ``ops``: list of ``(lens, codes)`` from :func:`_flatten_contribs`;
+    ``nce`` doubles per cell; codes >= ``cell_family_end`` belong to a further family (Robin facets) that is kept whole
+    behind the cells.  Returns ``(cells, [(contrib_ptr, contrib_code), ...])``.  The order of the contributions of a
+    slot is untouched, so the local assembly sums exactly what the global one sums (bit-identical values)."""
+    allc = []
+    for _, codes in ops:
+        c = codes if cell_family_end is None else codes[codes < cell_family_end]
+        allc.append(np.unique(c // nce))
+    cells = np.unique(np.concatenate(allc)) if allc else np.zeros(0, dtype=np.int64)
+    out = []
+    for lens, codes in ops:
+        new = np.empty_like(codes)
+        is_cell = np.ones(len(codes), dtype=bool) if cell_family_end is None else codes < cell_family_end
+        cc = codes[is_cell]
+        new[is_cell] = np.searchsorted(cells, cc // nce) * nce + cc % nce
+        if cell_family_end is not None:
+            new[~is_cell] = len(cells) * nce + (codes[~is_cell] - cell_family_end)
+        ptr = np.concatenate([[0], np.cumsum(lens)])
+        if len(new) and (new.max() >= 2 ** 31 or ptr[-1] >= 2 ** 31):
+            raise ValueError("local element buffer exceeds int32 addressing")
+        out.append((ptr.astype(np.int32), new.astype(np.int32)))
+    return cells, out
+
+
+class _LocalAssembly:
+    """Assembly of the OWNED rows of one scalar level straight into the rank's local operator: the element kernel runs
+    over the cells that touch an owned row only (1/N of the mesh + one cell layer), the gather map is the global one
+    restricted to the owned rows and re-addressed -- no rank assembles the global matrix (strong scaling of the
+    assembly phase of BASELINE config 5)."""
+
+    def __init__(self, ctx, lev, lp, op: _LocalOp):
+        from .device import cell_geometry
+        self.ctx, self.lev, self.lp, self.op = ctx, lev, lp, op
+        pat = lev.pattern
+        self.nce = lev.ndof_cell ** 2
+        fb = int(lev.facet_base)
+        lens, codes = _flatten_contribs(pat.contrib_ptr, pat.contrib_code, op.slot_host)
+        cells, maps = plan_local_gather([(lens, codes)], self.nce, fb if lev.nf else None)
+        self.cells = cells
+        self.nc = len(cells)
+        self.contrib_ptr = ctx.up(maps[0][0], np.int32)
+        self.contrib_code = ctx.up(np.concatenate([maps[0][1], [0]]), np.int32)
+        self.geo = ctx.up(np.ascontiguousarray(cell_geometry(lev.mesh)[:, cells]), np.float64)
+        cd = dm.p2_cell_dofs(lev.mesh) if lev.degree == 2 else dm.p1_cell_dofs(lev.mesh)
+        self.celldofs = ctx.up(np.ascontiguousarray(cd[cells].T), np.int32)      # GLOBAL dof ids: velocity / mu are read from global vectors
+        self.facet_len = int(pat.buffer_len - fb) if lev.nf else 0
+        self.E = ctx.zeros(max(self.nc * self.nce + self.facet_len, 1))
+        # Dirichlet data in the local column numbering (owned | hole | ghosts)
+        l2g = np.full(lp.n_loc, -1, dtype=np.int64)
+        present = np.flatnonzero(lp.g2l >= 0)
+        l2g[lp.g2l[present]] = present
+        self.l2g = l2g
+        flag = np.where(l2g >= 0, lev.bc_flag_host[np.maximum(l2g, 0)], 0).astype(np.uint8)
+        self.flag = ctx.up(flag, np.uint8)
+        self.val_map = _gather_map(ctx, np.maximum(l2g, 0))
+        self.val = ctx.zeros(lp.n_loc)
+        self.rhs = ctx.zeros(max(lp.n_own, 1))
+
+    def assemble(self, D, ux=None, uy=None, mu_const=0.0, mu_nodal=None, clamp=False, upwind=False, robin=True):
+        ctx, lib, lev, A = self.ctx, self.ctx.lib, self.lev, self.op.csr
+        if self.nc:
+            if lev.degree == 2:
+                capi.check(lib.sfem_elem_p2_advdiff(self.nc, P(self.geo), P(self.celldofs), float(D), P(ux), P(uy), P(self.E),
+                                                    ctx.stream), 'sfem_elem_p2_advdiff (local)')
+            else:
+                capi.check(lib.sfem_elem_p1_advdiff(self.nc, P(self.geo), P(self.celldofs), float(D), P(ux), P(uy),
+                                                    int(bool(upwind)), P(self.E), ctx.stream), 'sfem_elem_p1_advdiff (local)')
+        if lev.nf:
+            F = self.E[self.nc * self.nce:]
+            if robin:
+                fn = lib.sfem_facet_p2_robin if lev.degree == 2 else lib.sfem_facet_p1_robin
+                capi.check(fn(lev.nf, P(lev.fgeo), P(lev.fdofs), float(mu_const), P(mu_nodal), int(bool(clamp)), P(F),
+                              ctx.stream), 'sfem_facet_robin (local)')
+            else:
+                capi.check(lib.sfem_vec_set(self.facet_len, 0.0, P(F), ctx.stream), 'sfem_vec_set')
+        capi.check(lib.sfem_gather_csr(A.nnz, P(self.contrib_ptr), P(self.contrib_code), P(self.E), P(A.vals), ctx.stream),
+                   'sfem_gather_csr (local)')
+
+    def apply_bc(self, rhs=None, with_values=True):
+        """Symmetric elimination of the owned rows (ghost columns included); ``with_values``: the level's Dirichlet
+        values (system level), else zeros (multigrid levels, Stokes velocity block)."""
+        ctx, lib, A = self.ctx, self.ctx.lib, self.op.csr
+        if with_values:
+            _gather(ctx, self.lp.n_loc, self.val_map, self.lev.bc_val, self.val)
+        else:
+            capi.check(lib.sfem_vec_set(self.lp.n_loc, 0.0, P(self.val), ctx.stream), 'sfem_vec_set')
+        rhs = self.rhs if rhs is None else rhs
+        capi.check(lib.sfem_apply_dirichlet(self.lp.n_own, A.nnz, P(A.rowptr), P(A.cols), P(A.vals), P(rhs), P(self.flag),
+                                            P(self.val), 1, ctx.stream), 'sfem_apply_dirichlet (local)')
+
+
 class DistScalarProblem:
     """Row-partitioned view of a :class:`ScalarProblem` (which every rank holds and assembles in full).
 
@@ -308,6 +412,10 @@ class DistScalarProblem:
         Pl, Rl = self.Pm[-1].csr, self.Rm[-1].csr
         capi.check(lib.sfem_mg_set_tail(self.mg, self.tail.handle, n_tail, Pl.nnz, P(Pl.rowptr), P(Pl.cols), P(Pl.vals),
                                         Rl.nnz, P(Rl.rowptr), P(Rl.cols), P(Rl.vals)), 'sfem_mg_set_tail')
+        self.asm = [_LocalAssembly(ctx, prob.levels[l], self.parts[l], self.A[l]) for l in range(nd)]
+        for ops in (self.Pm, self.Rm):            # transfer values depend on the mesh and the Dirichlet sets only
+            for o in ops:
+                o.refresh()
         lp0 = self.parts[0]
         self.owned = ctx.up(lp0.owned, np.int64)
         self.owned32 = _gather_map(ctx, lp0.owned)
@@ -318,9 +426,8 @@ class DistScalarProblem:
 
     def refresh_operators(self):
         """Pull this rank's rows out of the freshly assembled global operators and set up the smoothers."""
-        for ops in (self.A, self.Pm, self.Rm):
-            for o in ops:
-                o.refresh()
+        for o in self.A:
+            o.refresh()
         self.tail.setup()
         capi.check(self.ctx.lib.sfem_mg_setup(self.mg, self.ctx.stream), 'sfem_mg_setup')
 
@@ -328,6 +435,36 @@ class DistScalarProblem:
         self.refresh_operators()
         f = self.prob.fine
         _gather(self.ctx, self.parts[0].n_own, self.owned32, f.rhs, self.rhs)
+
+    def assemble_coarse_local(self, D, vel, mu, upwind, robin):
+        """Multigrid levels: the row-partitioned ones from their owned cells, the replicated tail in full; then the
+        smoother set-up of both handles."""
+        prob, nd = self.prob, self.nd
+        for l, lev in enumerate(prob.levels[1:], 1):
+            cu, cv = vel[l - 1]
+            if l < nd:
+                self.asm[l].assemble(D, cu, cv, mu, None, False, upwind=upwind, robin=robin)
+                self.asm[l].apply_bc(with_values=False)
+            else:
+                lev.assemble(D, cu, cv, mu, None, False, upwind=upwind, robin=robin)
+                lev.apply_bc(1)
+        self.tail.setup()
+        capi.check(self.ctx.lib.sfem_mg_setup(self.mg, self.ctx.stream), 'sfem_mg_setup')
+
+    def assemble_local(self, D, ux=None, uy=None, mu_const=0.0, mu_nodal=None, clamp=False, bc_values=None, robin=True,
+                       coarse_mu: Optional[float] = None):
+        """Distributed counterpart of ``ScalarProblem.assemble`` (symmetric elimination): every rank assembles ITS rows
+        of the system level and of the row-partitioned multigrid levels; ``ux`` / ``uy`` / ``mu_nodal`` are full
+        (replicated) vectors.  Bit-identical to extracting the rows of the globally assembled operators."""
+        prob, ctx = self.prob, self.ctx
+        f = prob.fine
+        f.set_bc_values(bc_values if bc_values is not None else {i: 0.0 for i in f.bc_dofs})
+        a0 = self.asm[0]
+        a0.assemble(D, ux, uy, mu_const, mu_nodal, clamp, robin=robin)
+        capi.check(ctx.lib.sfem_vec_set(self.parts[0].n_own, 0.0, P(self.rhs), ctx.stream), 'sfem_vec_set')
+        a0.apply_bc(rhs=self.rhs, with_values=True)
+        vel = prob._coarse_velocity(ux, uy) if ux is not None else [(None, None)] * len(prob.transfers)
+        self.assemble_coarse_local(D, vel, mu_const if coarse_mu is None else coarse_mu, ux is not None, robin)
 
     def solve(self, method='cg', rtol=1e-13, maxit=400, restart=80):
         ctx, f = self.ctx, self.prob.fine
@@ -399,8 +536,9 @@ class DistStokesProblem:
         self.rank, self.nranks = rank, nranks
         mesh = stokes.mesh
         n2, nv = stokes.n2, stokes.nv
-        pb, pbt, _, mp = dm.stokes_block_plans(mesh)
+        pb, pbt, bt_code, mp = dm.stokes_block_plans(mesh)
         self._pat = (pb, pbt, mp)
+        self._bt_code = bt_code
 
         def extra0(owner0):
             # the divergence block reads velocity pairs j = col // 2 from the rows of the pressure owner
@@ -467,6 +605,30 @@ class DistStokesProblem:
                                                   BT.nnz, self.n_alloc, self.nv_alloc)
         if not self.handle:
             raise capi.SulcusFemError("sfem_stokes_create_part failed: " + lib.sfem_last_error().decode())
+        # ---- local assembly plans (owned cells only): B / B^T share one divergence element buffer, Mp has its own
+        from .device import cell_geometry
+        geo_all = cell_geometry(st.mesh)
+        ops_b = [_flatten_contribs(pb.contrib_ptr, pb.contrib_code, self.B.slot_host),
+                 _flatten_contribs(pbt.contrib_ptr, self._bt_code, self.BT.slot_host)]
+        cells_b, maps_b = plan_local_gather(ops_b, 36)
+        self._div = dict(nc=len(cells_b), geo=ctx.up(np.ascontiguousarray(geo_all[:, cells_b]), np.float64),
+                         E=ctx.zeros(max(36 * len(cells_b), 1)),
+                         b=(ctx.up(maps_b[0][0], np.int32), ctx.up(np.concatenate([maps_b[0][1], [0]]), np.int32)),
+                         bt=(ctx.up(maps_b[1][0], np.int32), ctx.up(np.concatenate([maps_b[1][1], [0]]), np.int32)))
+        cells_m, maps_m = plan_local_gather([_flatten_contribs(mp.contrib_ptr, mp.contrib_code, self.Mp.slot_host)], 9)
+        self._mass = dict(nc=len(cells_m), geo=ctx.up(np.ascontiguousarray(geo_all[:, cells_m]), np.float64),
+                          E=ctx.zeros(max(9 * len(cells_m), 1)),
+                          m=(ctx.up(maps_m[0][0], np.int32), ctx.up(np.concatenate([maps_m[0][1], [0]]), np.int32)))
+        # Dirichlet data in the local layout: values (pairs with their ghosts; the pressure part is zero) and flags
+        a0 = self.vel.asm[0]
+        gl = np.zeros(self.n_alloc + 2)
+        have = np.flatnonzero(a0.l2g >= 0)
+        gil = np.asarray(st.g_il_host)
+        gl[2 * have] = gil[2 * a0.l2g[have]]
+        gl[2 * have + 1] = gil[2 * a0.l2g[have] + 1]
+        self.g_loc = ctx.up(gl, np.float64)
+        fl = np.where(a0.l2g >= 0, st.vel.fine.bc_flag_host[np.maximum(a0.l2g, 0)], 0).astype(np.uint8)
+        self.flag_il_loc = ctx.up(np.repeat(fl, 2), np.uint8)
         # gather maps: solver layout of the global problem ([u interleaved | p]) -> owned part of the local vectors
         src = np.concatenate([rows_bt, 2 * n2 + lp.owned])
         self.own_map = _gather_map(ctx, src)
@@ -494,6 +656,41 @@ class DistStokesProblem:
         for o in (self.B, self.BT, self.Mp):
             o.refresh()
         _gather(self.ctx, self.n_own, self.own_map, self.stokes.rhs_il, self.b)
+
+    def assemble_local(self):
+        """Distributed counterpart of ``StokesProblem.assemble(bc_mode=1)`` (direct block assembly, device.py): every
+        rank assembles ITS rows of K, B, B^T, Mp and of the row-partitioned velocity multigrid levels from the cells
+        that touch them, lifts the Dirichlet data into its part of the right-hand side and eliminates -- bit-identical
+        to extracting the rows of the globally assembled, eliminated blocks."""
+        ctx, lib, vel = self.ctx, self.ctx.lib, self.vel
+        n2o, nvo = self.n2_own, self.nv_own
+        a0 = vel.asm[0]
+        K, B, BT, Mp = vel.A[0].csr, self.B.csr, self.BT.csr, self.Mp.csr
+        a0.assemble(1.0, None, None, robin=False)                               # un-eliminated scalar stiffness rows
+        d = self._div
+        if d['nc']:
+            capi.check(lib.sfem_elem_th_div(d['nc'], P(d['geo']), P(d['E']), ctx.stream), 'sfem_elem_th_div (local)')
+        for M, (cp, cc) in ((B, d['b']), (BT, d['bt'])):
+            capi.check(lib.sfem_gather_csr(M.nnz, P(cp), P(cc), P(d['E']), P(M.vals), ctx.stream), 'sfem_gather_csr (local)')
+        # lifting  b = -[K g_u ; B g_u]  on the owned rows (g_u with its ghosts), then b = g on the Dirichlet rows
+        r = self.b
+        capi.check(lib.sfem_vec_set(self.n_alloc, 0.0, P(r), ctx.stream), 'sfem_vec_set')
+        K.spmv(self.g_loc, y=r, b=r, mode=1, nb=2)
+        rp = r[2 * n2o:]
+        B.spmv(self.g_loc, y=rp, b=rp, mode=1)
+        capi.check(lib.sfem_vec_select(2 * n2o, P(self.flag_il_loc), P(self.g_loc), P(r), P(r), ctx.stream), 'sfem_vec_select')
+        a0.apply_bc(with_values=False)                                           # K: rows and columns of Dirichlet dofs
+        capi.check(lib.sfem_csr_zero_flagged(nvo, P(B.rowptr), P(B.cols), P(B.vals), None, P(self.flag_il_loc), ctx.stream),
+                   'sfem_csr_zero_flagged')
+        capi.check(lib.sfem_csr_zero_flagged(2 * n2o, P(BT.rowptr), P(BT.cols), P(BT.vals), P(self.flag_il_loc), None,
+                                             ctx.stream), 'sfem_csr_zero_flagged')
+        # preconditioner data: velocity multigrid levels and the pressure mass matrix
+        vel.assemble_coarse_local(1.0, [(None, None)] * len(vel.prob.transfers), 0.0, False, False)
+        m = self._mass
+        if m['nc']:
+            capi.check(lib.sfem_elem_p1_mass(m['nc'], P(m['geo']), P(m['E']), ctx.stream), 'sfem_elem_p1_mass (local)')
+        capi.check(lib.sfem_gather_csr(Mp.nnz, P(m['m'][0]), P(m['m'][1]), P(m['E']), P(Mp.vals), ctx.stream),
+                   'sfem_gather_csr (local)')
 
     def solve(self, rtol=1e-12, maxit=2000):
         ctx, lib = self.ctx, self.ctx.lib

@@ -40,7 +40,8 @@ void sfem_launch_count_reset(void);
 /* Per-launch timing for bench.py's roofline: between start and stop every instrumented launch is
  * bracketed by CUDA events on its stream.  stop() synchronises the device and returns the number of
  * records copied: category (0 spmv, 1 spmv+dot, 2 chebyshev step, 3 residual+d0, 4 element kernels,
- * 5 gather, 6 vector ops, 7 other, 8 staged spmv), algorithmic bytes, milliseconds. */
+ * 5 gather, 6 vector ops, 7 other, 8 staged spmv, 9 peer-memory halo exchange / vector all-reduce), algorithmic bytes,
+ * milliseconds. */
 int sfem_profile_start(int max_records);
 int sfem_profile_stop(int cap, int* h_cat, double* h_bytes, float* h_ms);
 

@@ -271,6 +271,26 @@ def test_device_sorted_patterns_are_bit_identical_to_the_host_path(ctx):
         assert a.family_base == b.family_base and a.buffer_len == b.buffer_len
 
 
+def test_device_sell_plan_is_bit_identical_to_the_host_plan(ctx):
+    import torch
+    from sulcusfem import dofmap as dm, hostmesh as hm, sell as sl
+    mesh = hm.refine_n(hm.rectangle_mesh(10.0, 1.0, 50, 9), 1)
+    cd = dm.p2_cell_dofs(mesh)
+    n = dm.p2_num_dofs(mesh)
+    saved, dm.DEVICE_SORT = dm.DEVICE_SORT, None
+    try:
+        pat = dm.build_pattern(n, n, [(cd, cd)])
+    finally:
+        dm.DEVICE_SORT = saved
+    for sigma in (32, 256):
+        a = sl.build_plan(pat.rowptr, pat.cols, sigma)
+        b = sl.build_plan_device(torch.from_numpy(pat.rowptr).to(ctx.device), torch.from_numpy(pat.cols).to(ctx.device), sigma)
+        assert (a.nrows, a.nslices, a.padded) == (b['nrows'], b['nslices'], b['padded'])
+        for k in ('slice_ptr', 'perm', 'scols', 'src'):
+            x, y = getattr(a, k), b[k].cpu().numpy()
+            assert x.dtype == y.dtype and np.array_equal(x, y), k
+
+
 def test_dense_inverse(ctx):
     """Blocked (32 x 32) multi-CTA Gauss-Jordan: sizes below / at / across block boundaries, called back to back on one
     stream (the workspace is shared) and with a growing workspace."""

@@ -1,6 +1,8 @@
 """CPU: host-side logic (meshes, markers, DOF maps, sparsity, gather maps, hierarchy, front-end objects)."""
 import os
 
+import sys
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -654,3 +656,61 @@ def test_geometry_and_mu_eff_analysis_extractors_match_reference_schema():
                                 'Ratio_Opening', 'Relative_Error_Analytical', 'Relative_Error_Enhanced',
                                 'Relative_Error_Opening', 'Total_Mass', 'Mouth_Flux_Total']
     assert row['Aspect_Ratio'] == 2.0 and row['Mouth_Flux_Total'] == 0.5
+
+
+def test_dolfin_adapter_matches_dofs_and_facets_by_geometry():
+    """results are copied into genuine dolfin Functions by DOF-coordinate matching and dolfin facet
+    MeshFunctions are re-indexed by vertex pair.  Exercised with stand-in dolfin objects whose DOF / facet numberings are
+    random permutations (real dolfin's numbering is build dependent; dolfin itself is not installable here)."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fake_dolfin as fd
+    from sulcusfem import dofmap as dm, dolfin_adapter as da, hostmesh as hm
+    from sulcusfem.fem import Function, FunctionSpace, MixedElement, VectorFunctionSpace
+    from sulcusfem.unstructured import mesh_domain
+    rng = np.random.default_rng(7)
+    host0 = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.2, 'sulcus')
+    dmesh = fd.FakeMesh(host0, rng)
+    host = da.host_mesh_from_dolfin(dmesh)
+    assert np.array_equal(host.cells, host0.cells) and np.array_equal(host.coords, host0.coords)
+    assert da.host_mesh_from_dolfin(dmesh) is host                          # cached on the dolfin object
+    # facet markers
+    mk = hm.build_markers(host, 10.0, 1.0, 4.75, 5.25, 'sulcus')
+    for key in ('bc_markers', 'bottom_segment_markers', 'y0_markers'):
+        mf = fd.facet_function(dmesh, mk[key].values)
+        assert np.array_equal(da.marker_values(mf, dmesh, host), mk[key].values)
+    # spaces: P2 scalar, P2 vector (interleaved / permuted components), Taylor-Hood
+    P2, P1 = dm.p2_dof_coordinates(host), host.coords
+    n2, nv = len(P2), len(P1)
+    for kind, blocks, ours_space in (('P2', [P2], FunctionSpace(host, 'CG', 2)), ('P1', [P1], FunctionSpace(host, 'P', 1)),
+                                     ('P2v', [P2, P2], VectorFunctionSpace(host, 'P', 2))):
+        V = fd.FakeSpace(dmesh, blocks, rng)
+        theirs = da.dof_map(V, host, kind)
+        assert np.array_equal(theirs, V.perm)
+        f = Function(ours_space, rng.random(ours_space.dim()))
+        g = da.to_dolfin(f, V, make_function=fd.FakeFunction)
+        assert np.array_equal(g.vector().get_local()[V.perm], f.values)
+        back = da.from_dolfin(g, host, kind)
+        assert np.array_equal(back.values, f.values)
+    W = fd.FakeSpace(dmesh, [P2, P2, P1], rng)
+    assert np.array_equal(da.dof_map(W, host, 'TH'), W.perm)
+    Vc = W.sub(0).collapse()
+    assert Vc.dim() == 2 * n2 and np.array_equal(da.dof_map(Vc, host, 'P2v'), Vc.perm)
+    # a space on a different mesh must be refused
+    other = fd.FakeSpace(dmesh, [P2 + 1e-3], rng)
+    with pytest.raises(ValueError):
+        da.dof_map(other, host, 'P2')
+    # install(): the reference's `from solvers import ...` resolves to the adapter
+    saved = sys.modules.get('solvers')
+    try:
+        mod = da.install(make_function=fd.FakeFunction)
+        import solvers as s
+        assert s is mod and all(hasattr(s, n) for n in ('stokes_solver', 'stokes_solver_no_adv', 'pure_diffusion_solver',
+                                                        'pure_diffusion_solver_variable_mu', 'advdiff_solver',
+                                                        'advdiff_solver_variable_mu'))
+        u0, p0 = s.stokes_solver_no_adv(fd.FakeSpace(dmesh, [P2, P2], rng), fd.FakeSpace(dmesh, [P1], rng))
+        assert not u0.vector().get_local().any()
+    finally:
+        if saved is not None:
+            sys.modules['solvers'] = saved
+        else:
+            sys.modules.pop('solvers', None)

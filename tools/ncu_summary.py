@@ -21,7 +21,7 @@ KEYS = [
 
 
 def short(name):
-    name = re.sub(r'void |sfem::|\(anonymous namespace\)::|<unnamed>::', '', name)
+    name = re.sub(r'void |sfem::|\(anonymous namespace\)::|<?unnamed>::', '', name)
     m = re.match(r'([A-Za-z_0-9:]+(<[^(]*>)?)', name)
     return (m.group(1) if m else name)[:70]
 
