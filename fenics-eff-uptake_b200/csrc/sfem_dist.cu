@@ -64,6 +64,47 @@ __global__ void __launch_bounds__(256) k_halo_exchange(DistDev D, HaloDev H, dou
   if (threadIdx.x == 0) H.seq[b] = s + 1;
 }
 
+// ---- two halo patterns (Taylor-Hood apply: interleaved velocity ghosts of K + pressure ghosts of B^T, both of ONE Stokes
+// vector) served by one launch = one rendezvous with the neighbours instead of two
+__device__ __forceinline__ void halo_block(const DistDev& D, const HaloDev& H, double* __restrict__ x, int b, int nb) {
+  const int q = H.peer[b];
+  const unsigned long long s = H.seq[b];
+  const int par = (int)(s & 1ull);
+  __syncthreads();
+  {
+    const int cnt = H.send_cnt[b];
+    const int* idx = H.send_idx + H.send_ptr[b];
+    double* dst = D.mailbox[q] + H.peer_data_off[b] + (long long)par * H.cap[b];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int li = idx[i];
+      if (nb == 1) dst[i] = x[li];
+      else reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(x)[li];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* f = reinterpret_cast<unsigned long long*>(D.mailbox[q] + H.peer_flag_off[b]) + par;
+    st_release_sys(f, s + 1);
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(D.mailbox[D.rank] + H.my_flag_off[b]) + par;
+    spin_wait(mine, s + 1, D.err);
+  }
+  __syncthreads();
+  {
+    const int cnt = H.recv_cnt[b];
+    const volatile double* src = D.mailbox[D.rank] + H.my_data_off[b] + (long long)par * H.cap[b];
+    double* dst = x + (size_t)H.recv_off[b] * nb;
+    for (int i = threadIdx.x; i < cnt * nb; i += blockDim.x) dst[i] = src[i];
+  }
+  if (threadIdx.x == 0) H.seq[b] = s + 1;
+}
+
+__global__ void __launch_bounds__(256) k_halo_exchange_pair(DistDev D, HaloDev H1, double* __restrict__ x1, int nb1,
+                                                            HaloDev H2, double* __restrict__ x2, int nb2) {
+  if ((int)blockIdx.x < H1.nneigh) halo_block(D, H1, x1, blockIdx.x, nb1);
+  else halo_block(D, H2, x2, blockIdx.x - H1.nneigh, nb2);
+}
+
 // ---- vector all-reduce, phase 1: every block stores its chunk into all peers; the last block to
 // finish publishes the flags
 __global__ void __launch_bounds__(256) k_allreduce_vec_send(DistDev D, const double* __restrict__ x, int n,
@@ -142,6 +183,17 @@ int halo_exchange(const Halo* h, double* x, int nb, cudaStream_t st, int phase) 
   Prof prof(PC_HALO, 16.0 * nb * h->max_cnt * h->dev.nneigh, st);
   if (nb == 2) k_halo_exchange<2><<<h->dev.nneigh, 256, 0, st>>>(d->dev, h->dev, x, phase);
   else k_halo_exchange<1><<<h->dev.nneigh, 256, 0, st>>>(d->dev, h->dev, x, phase);
+  SFEM_LAUNCH_CHECK();
+  return SFEM_OK;
+}
+
+int halo_exchange_pair(const Halo* h1, double* x1, int nb1, const Halo* h2, double* x2, int nb2, cudaStream_t st) {
+  if (h1 == nullptr || h1->dev.nneigh == 0) return halo_exchange(h2, x2, nb2, st);
+  if (h2 == nullptr || h2->dev.nneigh == 0) return halo_exchange(h1, x1, nb1, st);
+  Dist* d = g_dist;
+  if (!d) { set_error("halo exchange without an active communicator"); return SFEM_ERR_ARG; }
+  Prof prof(PC_HALO, 16.0 * (nb1 * h1->max_cnt * h1->dev.nneigh + nb2 * h2->max_cnt * h2->dev.nneigh), st);
+  k_halo_exchange_pair<<<h1->dev.nneigh + h2->dev.nneigh, 256, 0, st>>>(d->dev, h1->dev, x1, nb1, h2->dev, x2, nb2);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }

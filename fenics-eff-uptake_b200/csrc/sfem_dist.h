@@ -72,6 +72,8 @@ DistDev dist_dev();                           // its device view (nranks = 1 whe
 
 // fills the ghost region of x (n_loc entries x nb) from the owners; no-op when h == nullptr
 int halo_exchange(const Halo* h, double* x, int nb, cudaStream_t st, int phase = 0);
+// both patterns in ONE launch (one rendezvous with the neighbours): the Taylor-Hood apply's velocity + pressure ghosts
+int halo_exchange_pair(const Halo* h1, double* x1, int nb1, const Halo* h2, double* x2, int nb2, cudaStream_t st);
 // x[0..n) <- sum over ranks (in rank order); n <= vec_cap
 int dist_allreduce_vec(Dist* d, double* x, int n, cudaStream_t st, int phase = 0);
 

@@ -14,9 +14,11 @@ struct Csr {
 };
 
 // sfem_spmv.cu  (nb = number of interleaved right-hand sides, 1 or 2)
-int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st, int nb = 1);
+// (exchange = false: the ghost entries of x are already current -- the caller ran the halo exchange itself)
+int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st, int nb = 1,
+         bool exchange = true);
 int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* nparts, cudaStream_t st, int nb = 1,
-             const double* dotx = nullptr, int mode = 0);   // partial sums of <dotx, y>; mode 2: y += A x first
+             const double* dotx = nullptr, int mode = 0, bool exchange = true);   // partial sums of <dotx, y>; mode 2: y += A x first
 // Chebyshev coefficients are read from device memory: c12 -> {c1, c2}, c0 -> {c0}
 int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
               const double* c12, int last, cudaStream_t st, int nb = 1);

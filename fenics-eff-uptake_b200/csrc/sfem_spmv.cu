@@ -97,12 +97,12 @@ static int launch_spmv(const Csr& A, const double* x, const double* b, double* y
   return SFEM_OK;
 }
 
-int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st, int nb) {
+int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cudaStream_t st, int nb, bool exchange) {
   if (A.nrows <= 0) return SFEM_OK;
   if (mode == 1 && b == nullptr) { set_error("spmv mode 1 needs b"); return SFEM_ERR_ARG; }
   if (nb != 1 && nb != 2) { set_error("spmv: nb must be 1 or 2"); return SFEM_ERR_ARG; }
   if (nb == 2 && (reinterpret_cast<uintptr_t>(x) & 15u)) { set_error("spmv: nb = 2 needs a 16-byte aligned x"); return SFEM_ERR_ARG; }
-  SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));   // distributed matrix: fill the ghosts of x
+  if (exchange) SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));   // distributed matrix: fill the ghosts of x
   { const int took = sell_spmv(A, x, b, y, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   { const int took = staged_spmv(A, x, b, y, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
@@ -115,10 +115,10 @@ int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cu
 }
 
 int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* nparts, cudaStream_t st, int nb,
-             const double* dotx, int mode) {
+             const double* dotx, int mode, bool exchange) {
   if (dotx == nullptr) dotx = x;
   if (mode != 0 && mode != 2) { set_error("spmv_dot: mode must be 0 or 2"); return SFEM_ERR_ARG; }
-  SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));
+  if (exchange) SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(x), nb, st));
   { const int took = sell_spmv_dot(A, x, dotx, y, partial, nparts, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   { const int took = staged_spmv_dot(A, x, dotx, y, partial, nparts, mode, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
@@ -192,8 +192,10 @@ int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x,
 // y_u = K z_u (both components, matrix read once) ; y_u += BT z_p with the partial sums of <z_u, y_u>
 int stokes_apply_u(const Csr& K, const Csr& BT, const double* zu, const double* zp, double* yu, double* partial,
                    int* nparts, cudaStream_t st) {
-  SFEM_TRY(spmv(K, zu, nullptr, yu, 0, st, 2));
-  return spmv_dot(BT, zp, yu, partial, nparts, st, 1, zu, 2);
+  // row-partitioned: the velocity ghosts (K) and the pressure ghosts (B^T) of the vector travel in one exchange launch
+  SFEM_TRY(halo_exchange_pair(find_halo(K.rowptr), const_cast<double*>(zu), 2, find_halo(BT.rowptr), const_cast<double*>(zp), 1, st));
+  SFEM_TRY(spmv(K, zu, nullptr, yu, 0, st, 2, false));
+  return spmv_dot(BT, zp, yu, partial, nparts, st, 1, zu, 2, false);
 }
 
 }  // namespace sfem

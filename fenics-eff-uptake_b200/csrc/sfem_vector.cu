@@ -357,14 +357,16 @@ int sfem_postprocess_concentration(int n, double* c, int fix_nonfinite, double* 
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 0) { set_error("empty vector"); return SFEM_ERR_ARG; }
   const int grid = grid_for(n, kThreads * 4, 4);
-  double* partial = nullptr;
-  SFEM_CUDA(cudaMalloc(&partial, (size_t)grid * 5 * sizeof(double)));
+  // per-thread scratch, allocated once (cudaMalloc / cudaFree per call would synchronise the whole device: a sweep calls
+  // this once per case, possibly from several solver threads at once)
+  static thread_local double* partial = nullptr;
+  if (partial == nullptr) SFEM_CUDA(cudaMalloc(&partial, (size_t)kMaxPartials * 5 * sizeof(double)));
   k_conc_stats<<<grid, kThreads, 0, st>>>(n, c, fix_nonfinite, partial);
   g_launches.fetch_add(1);
   std::vector<double> h((size_t)grid * 5);
   cudaError_t e = cudaMemcpyAsync(h.data(), partial, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) { cudaFree(partial); set_error(cudaGetErrorString(e)); return SFEM_ERR_CUDA; }
+  if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return SFEM_ERR_CUDA; }
   double nbad = 0, nneg = 0, mn = INFINITY, mx = -INFINITY, sum = 0;
   for (int b = 0; b < grid; ++b) {
     nbad += h[5 * b]; nneg += h[5 * b + 1];
@@ -376,7 +378,6 @@ int sfem_postprocess_concentration(int n, double* c, int fix_nonfinite, double* 
     g_launches.fetch_add(1);
     clamped = 1.0;
   }
-  cudaFree(partial);
   h_stats[0] = nbad; h_stats[1] = nneg; h_stats[2] = mn; h_stats[3] = mx; h_stats[4] = sum / n; h_stats[5] = clamped;
   return SFEM_OK;
 }

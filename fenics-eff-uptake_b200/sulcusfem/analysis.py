@@ -9,6 +9,8 @@ nested dictionaries the study drivers index.
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 from scipy.integrate import quad
 
@@ -387,15 +389,22 @@ def compute_concentration_profiles(results):
                       'mean_y0_total': (C_ext + C_m) / tot_L if tot_L > 0 else np.nan}}
 
 
+@functools.lru_cache(maxsize=256)
+def _arc_integral(h, w):
+    """int_0^1 sqrt(1 + (pi h / w cos(pi s))^2) ds by the reference's adaptive quadrature (same call, same tolerances);
+    memoised per geometry -- a mu sweep asks for it once per case."""
+    val, _ = quad(lambda s: np.sqrt(1.0 + (np.pi * h / w * np.cos(np.pi * s)) ** 2), 0.0, 1.0,
+                  epsabs=1e-10, epsrel=1e-10, limit=200)
+    return float(val)
+
+
 def compute_mu_eff_arc(results):
     """mu (1 + (L_sulcus - w)/L) with the arc length by adaptive quadrature (analysis.py:948-970)."""
     p = results['params']
     L, h, w, mu = float(p.L), float(p.sulci_h), float(p.sulci_w), float(p.mu)
     if w <= 0 or h <= 0 or L <= 0:
         return None
-    val, _ = quad(lambda s: np.sqrt(1.0 + (np.pi * h / w * np.cos(np.pi * s)) ** 2), 0.0, 1.0,
-                  epsabs=1e-10, epsrel=1e-10, limit=200)
-    return float(mu * (1.0 + (w * float(val) - w) / L))
+    return float(mu * (1.0 + (w * _arc_integral(h, w) - w) / L))
 
 
 def compute_mu_eff_enh(results, kappa=10.0):
