@@ -16,93 +16,49 @@ std::unordered_map<const int*, const Halo*> g_halos;
 std::atomic<int> g_nhalos{0};
 Dist* g_dist = nullptr;
 
-// ---- halo exchange: block b <-> neighbour b
+// ---- halo exchange: block b <-> neighbour b, flagged words (sfem_dist.h)
 // phase 0: send + wait + unpack (production); 1: send only; 2: wait + unpack only (single-GPU emulation in tests)
-template <int NB>
-__global__ void __launch_bounds__(256) k_halo_exchange(DistDev D, HaloDev H, double* __restrict__ x, int phase) {
-  const int b = blockIdx.x;
+__device__ __forceinline__ void halo_block(const DistDev& D, const HaloDev& H, double* __restrict__ x, int b, int nb,
+                                           int phase) {
   const int q = H.peer[b];
   const unsigned long long s = H.seq[b];
   const int par = (int)(s & 1ull);
+  const unsigned int flag = (unsigned int)(s + 1);
   __syncthreads();                                            // everyone has read seq before thread 0 bumps it
-  // pack + remote store
-  if (phase != 2) {
-    const int cnt = H.send_cnt[b];
+  if (phase != 2) {                                           // pack + remote store
+    const int cnt = H.send_cnt[b] * nb;
     const int* idx = H.send_idx + H.send_ptr[b];
-    double* dst = D.mailbox[q] + H.peer_data_off[b] + (long long)par * H.cap[b];
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(D.mailbox[q] + H.peer_data_off[b] + (long long)par * H.cap[b]);
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const int li = idx[i];
-      if (NB == 1) {
-        dst[i] = x[li];
-      } else {
-        const double2 v = reinterpret_cast<const double2*>(x)[li];
-        reinterpret_cast<double2*>(dst)[i] = v;
-      }
+      const int li = idx[nb == 1 ? i : (i >> 1)];
+      ll_store(dst + 2 * (long long)i, x[nb == 1 ? li : 2 * (long long)li + (i & 1)], flag);
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (phase != 2) {
-      unsigned long long* f = reinterpret_cast<unsigned long long*>(D.mailbox[q] + H.peer_flag_off[b]) + par;
-      st_release_sys(f, s + 1);
-    }
-    if (phase != 1) {
-      const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(D.mailbox[D.rank] + H.my_flag_off[b]) + par;
-      spin_wait(mine, s + 1, D.err);
-    }
-  }
-  __syncthreads();
   if (phase == 1) return;
-  // unpack: mailbox -> ghost region
-  {
-    const int cnt = H.recv_cnt[b];
-    const volatile double* src = D.mailbox[D.rank] + H.my_data_off[b] + (long long)par * H.cap[b];
-    double* dst = x + (size_t)H.recv_off[b] * NB;
-    for (int i = threadIdx.x; i < cnt * NB; i += blockDim.x) dst[i] = src[i];
-  }
-  if (threadIdx.x == 0) H.seq[b] = s + 1;
-}
-
-// ---- two halo patterns (Taylor-Hood apply: interleaved velocity ghosts of K + pressure ghosts of B^T, both of ONE Stokes
-// vector) served by one launch = one rendezvous with the neighbours instead of two
-__device__ __forceinline__ void halo_block(const DistDev& D, const HaloDev& H, double* __restrict__ x, int b, int nb) {
-  const int q = H.peer[b];
-  const unsigned long long s = H.seq[b];
-  const int par = (int)(s & 1ull);
-  __syncthreads();
-  {
-    const int cnt = H.send_cnt[b];
-    const int* idx = H.send_idx + H.send_ptr[b];
-    double* dst = D.mailbox[q] + H.peer_data_off[b] + (long long)par * H.cap[b];
+  {                                                           // poll + unpack: mailbox -> ghost region
+    const int cnt = H.recv_cnt[b] * nb;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(D.mailbox[D.rank] + H.my_data_off[b] + (long long)par * H.cap[b]);
+    double* dst = x + (size_t)H.recv_off[b] * nb;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const int li = idx[i];
-      if (nb == 1) dst[i] = x[li];
-      else reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(x)[li];
+      double v;
+      ll_wait(src + 2 * (long long)i, flag, &v, D.err);
+      dst[i] = v;
     }
   }
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long* f = reinterpret_cast<unsigned long long*>(D.mailbox[q] + H.peer_flag_off[b]) + par;
-    st_release_sys(f, s + 1);
-    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(D.mailbox[D.rank] + H.my_flag_off[b]) + par;
-    spin_wait(mine, s + 1, D.err);
-  }
-  __syncthreads();
-  {
-    const int cnt = H.recv_cnt[b];
-    const volatile double* src = D.mailbox[D.rank] + H.my_data_off[b] + (long long)par * H.cap[b];
-    double* dst = x + (size_t)H.recv_off[b] * nb;
-    for (int i = threadIdx.x; i < cnt * nb; i += blockDim.x) dst[i] = src[i];
-  }
   if (threadIdx.x == 0) H.seq[b] = s + 1;
 }
 
+__global__ void __launch_bounds__(256) k_halo_exchange(DistDev D, HaloDev H, double* __restrict__ x, int nb, int phase) {
+  halo_block(D, H, x, blockIdx.x, nb, phase);
+}
+
+// two halo patterns (Taylor-Hood apply: interleaved velocity ghosts of K + pressure ghosts of B^T, both of ONE Stokes
+// vector) served by one launch
 __global__ void __launch_bounds__(256) k_halo_exchange_pair(DistDev D, HaloDev H1, double* __restrict__ x1, int nb1,
                                                             HaloDev H2, double* __restrict__ x2, int nb2) {
-  if ((int)blockIdx.x < H1.nneigh) halo_block(D, H1, x1, blockIdx.x, nb1);
-  else halo_block(D, H2, x2, blockIdx.x - H1.nneigh, nb2);
+  if ((int)blockIdx.x < H1.nneigh) halo_block(D, H1, x1, blockIdx.x, nb1, 0);
+  else halo_block(D, H2, x2, blockIdx.x - H1.nneigh, nb2, 0);
 }
 
 // ---- vector all-reduce, phase 1: every block stores its chunk into all peers; the last block to
@@ -181,8 +137,7 @@ int halo_exchange(const Halo* h, double* x, int nb, cudaStream_t st, int phase) 
   Dist* d = g_dist;
   if (!d) { set_error("halo exchange without an active communicator"); return SFEM_ERR_ARG; }
   Prof prof(PC_HALO, 16.0 * nb * h->max_cnt * h->dev.nneigh, st);
-  if (nb == 2) k_halo_exchange<2><<<h->dev.nneigh, 256, 0, st>>>(d->dev, h->dev, x, phase);
-  else k_halo_exchange<1><<<h->dev.nneigh, 256, 0, st>>>(d->dev, h->dev, x, phase);
+  k_halo_exchange<<<h->dev.nneigh, 256, 0, st>>>(d->dev, h->dev, x, nb, phase);
   SFEM_LAUNCH_CHECK();
   return SFEM_OK;
 }
@@ -226,7 +181,7 @@ extern "C" {
 
 /* mailbox layout helper: words (8 bytes) reserved at the start of every mailbox for the all-reduces */
 long long sfem_dist_header_words(int nranks, long long vec_cap) {
-  return 2LL * nranks + 2LL * nranks * kAllreduceMaxK + 2LL * nranks + 2LL * nranks * vec_cap;
+  return 2LL * nranks + 4LL * nranks * kAllreduceMaxK + 2LL * nranks + 2LL * nranks * vec_cap;
 }
 
 sfem_dist_t sfem_dist_create(int rank, int nranks, long long mailbox_words, long long vec_cap) {
@@ -252,7 +207,7 @@ sfem_dist_t sfem_dist_create(int rank, int nranks, long long mailbox_words, long
   d.dev.mailbox[rank] = mb;
   d.dev.sc_flag_off = 0;
   d.dev.sc_data_off = 2LL * nranks;
-  d.dev.vec_flag_off = d.dev.sc_data_off + 2LL * nranks * kAllreduceMaxK;
+  d.dev.vec_flag_off = d.dev.sc_data_off + 4LL * nranks * kAllreduceMaxK;       // scalar slots are flagged pairs (2 words)
   d.dev.vec_data_off = d.dev.vec_flag_off + 2LL * nranks;
   d.dev.vec_cap = vec_cap;
   cudaDeviceSynchronize();

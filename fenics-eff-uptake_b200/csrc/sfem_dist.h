@@ -3,12 +3,13 @@
 // One process per GPU.  Every rank owns one device "mailbox" (cudaMalloc), exports it with CUDA IPC
 // and maps the mailboxes of all peers; after that the data path never calls a library collective:
 //   * halo exchange  = ONE kernel per exchange: block b packs the boundary values neighbour b needs and
-//     stores them straight into that neighbour's mailbox (remote st.global over NVLink), publishes a
-//     sequence flag with release semantics, then spins (acquire) on its own flag from the same neighbour
-//     and copies the received values into the ghost region of the vector;
+//     stores them straight into that neighbour's mailbox (remote 16-byte stores over NVLink) as FLAGGED
+//     words -- every double carries the sequence number of the exchange (see ll_store) -- then polls its
+//     own mailbox until the neighbour's words of this exchange have arrived and copies them into the ghost
+//     region of the vector: no fence, no separate flag, latency = one NVLink flight;
 //   * all-reduce of the few Krylov scalars = inside the one-block scalar kernels: every rank stores its
-//     partial sums into every peer's mailbox, waits for all flags and adds the nranks contributions in
-//     rank order -> bit-identical on all ranks and run to run;
+//     partial sums (flagged words) into every peer's mailbox, polls for the nranks contributions and adds
+//     them in rank order -> bit-identical on all ranks and run to run;
 //   * vector all-reduce (restriction onto the replicated coarse hierarchy) = same scheme, chunked.
 // Slots are double buffered by sequence parity; exchanges are symmetric (every pair sends both ways
 // each time), so a slot is only rewritten after its reader has moved on.  Spins carry a time-out that
@@ -29,7 +30,7 @@ struct DistDev {
   int* err = nullptr;                    // local error flag (time-out)
   // fixed layout at the start of every mailbox (in 8-byte words)
   long long sc_flag_off = 0;             // [2][nranks] flags of the scalar all-reduce
-  long long sc_data_off = 0;             // [2][nranks][kAllreduceMaxK]
+  long long sc_data_off = 0;             // [2][nranks][kAllreduceMaxK] flagged pairs = 2 words each
   long long vec_flag_off = 0;            // [2][nranks]
   long long vec_data_off = 0;            // [2][nranks][vec_cap]
   long long vec_cap = 0;
@@ -49,7 +50,7 @@ struct HaloDev {
   const long long* peer_flag_off = nullptr;   // [2] flags there
   const long long* my_data_off = nullptr;     // where the neighbour writes in my mailbox
   const long long* my_flag_off = nullptr;
-  const long long* cap = nullptr;             // words per parity of each channel (>= cnt * 2)
+  const long long* cap = nullptr;             // words per parity of each channel (>= 2 words per double sent: flagged pairs)
   unsigned long long* seq = nullptr;          // local, one counter per neighbour channel
 };
 
@@ -103,31 +104,87 @@ __device__ __forceinline__ bool spin_wait(const unsigned long long* flag, unsign
   return true;
 }
 
+// ---- flagged ("LL") words: a double travels as two 8-byte words {flag : 32 | half of the double : 32}, written with ONE
+// 16-byte store into the peer's mailbox.  An 8-byte word arrives atomically, so the receiver needs no fence and no separate
+// flag: it polls the slot until both words carry the sequence number of this exchange.  This removes the two system-scope
+// fence round trips of a data + fence + flag protocol from every exchange (the payloads here are a few kB: latency is all
+// that matters), at twice the bytes on the wire.
+__device__ __forceinline__ void ll_store(unsigned long long* dst2, double v, unsigned int flag) {
+  const unsigned long long lo = ((unsigned long long)flag << 32) | (unsigned int)__double2loint(v);
+  const unsigned long long hi = ((unsigned long long)flag << 32) | (unsigned int)__double2hiint(v);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst2), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ll_load(const unsigned long long* src2) {
+  ulonglong2 w;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w.x), "=l"(w.y) : "l"(src2) : "memory");
+  return w;
+}
+__device__ __forceinline__ bool ll_ready(const ulonglong2& w, unsigned int flag) {
+  return (unsigned int)(w.x >> 32) == flag && (unsigned int)(w.y >> 32) == flag;
+}
+__device__ __forceinline__ double ll_value(const ulonglong2& w) {
+  return __hiloint2double((int)(unsigned int)w.y, (int)(unsigned int)w.x);
+}
+// polls one slot until it carries `flag`; false on time-out (10 s)
+__device__ __forceinline__ bool ll_wait(const unsigned long long* src2, unsigned int flag, double* out, int* err) {
+  ulonglong2 w = ll_load(src2);
+  if (!ll_ready(w, flag)) {
+    const unsigned long long t0 = global_timer_ns();
+    do {
+      w = ll_load(src2);
+      if (global_timer_ns() - t0 > 10000000000ull) {
+        if (err) *err = 1;
+        *out = 0.0;
+        return false;
+      }
+    } while (!ll_ready(w, flag));
+  }
+  *out = ll_value(w);
+  return true;
+}
+
 // All-reduce (sum) of K <= kAllreduceMaxK scalars, called by ONE thread of a one-block kernel.
-// vals in/out.  With nranks == 1 it is a no-op.
+// vals in/out.  With nranks == 1 it is a no-op.  Flagged words: every rank stores its K values into every peer's mailbox
+// (posted 16-byte stores, no fence), then polls the nranks x K slots of its own mailbox -- all loads of a polling pass are
+// issued before the first one is tested -- and adds the contributions in rank order (bit-identical on all ranks).
 __device__ __forceinline__ void dist_allreduce_scalars(const DistDev& D, double* vals, int K) {
   if (D.nranks <= 1) return;
   const unsigned long long s = D.seq[0];
   const int par = (int)(s & 1ull);
+  const unsigned int flag = (unsigned int)(s + 1);
   for (int q = 0; q < D.nranks; ++q) {
-    double* dst = D.mailbox[q] + D.sc_data_off + ((long long)par * D.nranks + D.rank) * kAllreduceMaxK;
-    for (int k = 0; k < K; ++k) dst[k] = vals[k];
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(D.mailbox[q] + D.sc_data_off) +
+                              2 * ((long long)par * D.nranks + D.rank) * kAllreduceMaxK;
+    for (int k = 0; k < K; ++k) ll_store(dst + 2 * k, vals[k], flag);
   }
-  __threadfence_system();
-  for (int q = 0; q < D.nranks; ++q) {
-    unsigned long long* f = reinterpret_cast<unsigned long long*>(D.mailbox[q] + D.sc_flag_off) + par * D.nranks + D.rank;
-    st_release_sys(f, s + 1);
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(D.mailbox[D.rank] + D.sc_data_off) +
+                                   2 * (long long)par * D.nranks * kAllreduceMaxK;
+  if (K == 1) {
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+      ulonglong2 w[kMaxRanks];
+#pragma unroll
+      for (int q = 0; q < kMaxRanks; ++q)
+        if (q < D.nranks) w[q] = ll_load(mine + 2 * (long long)q * kAllreduceMaxK);
+      bool ok = true;
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < kMaxRanks; ++q)
+        if (q < D.nranks) { ok = ok && ll_ready(w[q], flag); acc += ll_value(w[q]); }
+      if (ok) { vals[0] = acc; break; }
+      if (global_timer_ns() - t0 > 10000000000ull) { if (D.err) *D.err = 1; break; }
+    }
+  } else {
+    double acc[kAllreduceMaxK];
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int q = 0; q < D.nranks; ++q)
+      for (int k = 0; k < K; ++k) {
+        double v;
+        ll_wait(mine + 2 * ((long long)q * kAllreduceMaxK + k), flag, &v, D.err);
+        acc[k] += v;
+      }
+    for (int k = 0; k < K; ++k) vals[k] = acc[k];
   }
-  double acc[kAllreduceMaxK];
-  for (int k = 0; k < K; ++k) acc[k] = 0.0;
-  const double* mine = D.mailbox[D.rank];
-  for (int q = 0; q < D.nranks; ++q) {
-    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + D.sc_flag_off) + par * D.nranks + q;
-    spin_wait(f, s + 1, D.err);
-    const volatile double* src = mine + D.sc_data_off + ((long long)par * D.nranks + q) * kAllreduceMaxK;
-    for (int k = 0; k < K; ++k) acc[k] += src[k];
-  }
-  for (int k = 0; k < K; ++k) vals[k] = acc[k];
   D.seq[0] = s + 1;
 }
 #endif

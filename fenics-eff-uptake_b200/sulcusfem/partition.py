@@ -122,7 +122,8 @@ def partition_level(owner: np.ndarray, nranks: int, rank: int, ghosts: List[np.n
         off = _even(mailbox_base[q])
         for p in range(nranks):
             if nbr[q, p]:
-                cap = _even(max(int(max(needs[q, p], needs[p, q])) * nb_max, 2))      # same slot size both ways
+                # same slot size both ways; every double travels as a flagged pair of words (csrc/sfem_dist.h)
+                cap = _even(max(2 * int(max(needs[q, p], needs[p, q])) * nb_max, 2))
                 chan[(q, p)] = (off, off + 2 * cap, cap)
                 off += 2 * cap + 2
         ends.append(off)
