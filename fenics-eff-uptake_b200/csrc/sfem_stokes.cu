@@ -24,6 +24,7 @@
 #include "sfem_dist.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace sfem {
@@ -279,6 +280,9 @@ int st_precond(sfem_stokes* h, const double* r, double* out, cudaStream_t st) {
     k_z_apply<<<grid_for(h->nv, kThreads * 2), kThreads, 0, st>>>(h->nv, h->zidx, h->zw, h->zcoef, out + nu); }
     SFEM_LAUNCH_CHECK();
   }
+  // experiment knob: relative scaling of the Schur block of the block-diagonal preconditioner (1 = none)
+  static const double schur_scale = [] { const char* e = std::getenv("SFEM_SCHUR_SCALE"); return e ? std::atof(e) : 1.0; }();
+  if (schur_scale != 1.0 && schur_scale > 0.0) SFEM_TRY(vec_axpby(h->nv, schur_scale, out + nu, 0.0, out + nu, st));
   return SFEM_OK;
 }
 
