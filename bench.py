@@ -636,7 +636,9 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-dd', action='store_true')         # N > 1: skip the domain-decomposed (config 5) leg
     ap.add_argument('--dd-replicate-below', type=int, default=200000)   # multigrid levels below this many unknowns stay replicated
-    ap.add_argument('--dd-refine', default=os.environ.get('SFEM_BENCH_DD_REFINE', ''))   # extra refinements for the dd leg, e.g. "3"
+    # N > 1: the dd leg also runs these refinement levels (the bench mesh, 6.1 M dofs, is too small for 8 GPUs; r = 3 =
+    # 24.4 M dofs adds ~50 s of set-up per rank); '' = the bench mesh only
+    ap.add_argument('--dd-refine', default=os.environ.get('SFEM_BENCH_DD_REFINE', '3'))
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

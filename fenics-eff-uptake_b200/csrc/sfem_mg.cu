@@ -244,6 +244,25 @@ int sfem_mg_setup(sfem_mg_t mg, void* stream) {
   return SFEM_OK;
 }
 
+/* Smoother set-up of the system level only (level 0: diagonal, Gershgorin bound, Chebyshev coefficients): for a
+ * parameter sweep in which only boundary rows of the system matrix change (Robin coefficient mu) and the coarse levels
+ * are kept from a nearby parameter value -- they are preconditioner data, the Krylov solve still converges to the
+ * residual of the exact system.  The handle must have been set up in full once. */
+int sfem_mg_setup_fine(sfem_mg_t mg, void* stream) {
+  if (!mg || !mg->ready) { set_error("sfem_mg_setup_fine: the handle needs one full sfem_mg_setup first"); return SFEM_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  SFEM_TRY(sell_ensure_all(st));
+  MgLevel& L = mg->levels[0];
+  SFEM_TRY(extract_diag_inv(L.A, L.dinv, st));
+  if (mg->levels.size() == 1 && mg->tail == nullptr) {
+    if (mg->coarse_inv == nullptr)
+      SFEM_TRY(cheb_setup(&L.A, L.dinv, 0.0, 30.0, kCoarseFallbackDegree, mg->scratch, L.coef, st, false));
+    return SFEM_OK;
+  }
+  const bool dist = find_halo(L.A.rowptr) != nullptr || mg->tail != nullptr;
+  return cheb_setup(&L.A, L.dinv, 0.0, mg->ratio, mg->degree, mg->scratch, L.coef, st, dist);
+}
+
 /* Multi-GPU: `mg` holds the row-partitioned levels; below its last level the replicated hierarchy `tail`
  * (n_tail dofs on its finest level) is solved redundantly.  P_last: n_own(last) x n_tail, R_last: n_tail x
  * n_own(last) restricted to the owned columns (the partial results are summed over the ranks). */

@@ -72,6 +72,7 @@ SIGNATURES = {
                             C.POINTER(_i), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p),
                             C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), _p, _i, _d, _i]),
     'sfem_mg_setup': (_i, [_p, _p]),
+    'sfem_mg_setup_fine': (_i, [_p, _p]),
     'sfem_mg_vcycle': (_i, [_p, _p, _p, _p]),
     'sfem_mg_set_tail': (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
     'sfem_mg_lambda_max': (_i, [_p, C.POINTER(_d)]),

@@ -319,6 +319,9 @@ class Multigrid:
                                                       ctx.stream), 'sfem_dense_inverse_csr')
         capi.check(ctx.lib.sfem_mg_setup(self.handle, ctx.stream), 'sfem_mg_setup')
 
+    def setup_fine(self):
+        capi.check(self.ctx.lib.sfem_mg_setup_fine(self.handle, self.ctx.stream), 'sfem_mg_setup_fine')
+
     def vcycle(self, b, x=None):
         x = self.ctx.empty(self.levels[0].n * self.nb) if x is None else x
         capi.check(self.ctx.lib.sfem_mg_vcycle(self.handle, P(b), P(x), self.ctx.stream), 'sfem_mg_vcycle')
@@ -383,11 +386,24 @@ class ScalarProblem:
         return out
 
     def assemble(self, D, ux=None, uy=None, mu_const=0.0, mu_nodal=None, clamp=False, bc_values=None,
-                 bc_mode=1, robin=True, coarse_mu: Optional[float] = None, fine=True):
+                 bc_mode=1, robin=True, coarse_mu: Optional[float] = None, fine=True, reuse_coarse=False):
         """Assemble the system level (+ BCs) and rediscretise the multigrid levels.  ``fine=False``:
         the system-level values were written by the caller (Stokes: K extracted from the Taylor-Hood
-        matrix); only the coarse levels are assembled."""
+        matrix); only the coarse levels are assembled.  ``reuse_coarse=True`` (mu sweeps, ``solvers.frozen_coarse_levels``):
+        keep the coarse levels of the previous full assembly (same D, no velocity) and redo the system level's smoother
+        set-up only; returns False -- and assembles in full -- when there is nothing compatible to reuse."""
         f = self.fine
+        key = (float(D), bool(robin), int(bc_mode))
+        if reuse_coarse and fine and ux is None and getattr(self, '_coarse_key', None) == key:
+            f.set_bc_values(bc_values if bc_values is not None else {i: 0.0 for i in f.bc_dofs})
+            f.assemble(D, None, None, mu_const, mu_nodal, clamp, robin=robin)
+            capi.check(self.ctx.lib.sfem_vec_set(f.n, 0.0, P(f.rhs), self.ctx.stream), 'sfem_vec_set')
+            f.apply_bc(bc_mode)
+            self.bc_mode = bc_mode
+            self.mg.setup_fine()
+            return True
+        self._coarse_key = key if (fine and ux is None) else None
+        self._coarse_mu = float(mu_const if coarse_mu is None else coarse_mu)
         if fine:
             f.set_bc_values(bc_values if bc_values is not None else {i: 0.0 for i in f.bc_dofs})
             f.assemble(D, ux, uy, mu_const, mu_nodal, clamp, robin=robin)

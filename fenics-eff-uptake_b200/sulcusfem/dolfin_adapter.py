@@ -180,10 +180,6 @@ class DolfinSolvers:
             host._sfem_markers = {k: v for k, v in cached.items() if k != 'mesh'}
         return cached, host
 
-    @staticmethod
-    def _value(c):
-        return c if isinstance(c, (int, float)) or hasattr(c, 'eval') and not hasattr(c, 'values') else float(c)
-
     def _scalar_space(self, host):
         return FunctionSpace(host, 'CG', 2)
 

@@ -16,6 +16,9 @@ then multigrid-preconditioned CG (pure diffusion), FGMRES (advection-diffusion) 
 """
 from __future__ import annotations
 
+import contextlib
+import threading
+
 import numpy as np
 
 from . import dofmap as dm
@@ -116,6 +119,34 @@ def _mu_nodal(mu_function, prob):
     return prob.ctx.up(vals, np.float64), vals, mean
 
 
+# ---------------------------------------------------------------------- mu sweeps: frozen coarse levels
+# In a Robin-coefficient sweep on one geometry (no_advection_analysis_A.py:1306-1347: 20 mu values, one mesh) only the
+# boundary rows of A(mu) = D K + mu M_Gamma change.  Inside ``frozen_coarse_levels()`` a constant-mu pure-diffusion solve
+# re-assembles the system level only and keeps the multigrid levels of the last full assembly as long as mu stays within
+# ``factor`` of the mu they were built for: the coarse levels are preconditioner data, CG still iterates on the exact
+# system to the same true residual (RTOL), so the fields are unchanged to solver tolerance (tests/test_gpu_studies.py) --
+# it saves ~30 coarse-level launches, the dense coarse inverse and ~30 host calls per case.
+_sweep = threading.local()
+
+
+@contextlib.contextmanager
+def frozen_coarse_levels(factor=4.0):
+    prev = getattr(_sweep, 'factor', None)
+    _sweep.factor = float(factor)
+    try:
+        yield
+    finally:
+        _sweep.factor = prev
+
+
+def _reuse_coarse(prob, mu):
+    factor = getattr(_sweep, 'factor', None)
+    ref = getattr(prob, '_coarse_mu', None)
+    if factor is None or ref is None or mu is None or not (mu > 0.0 and ref > 0.0):
+        return False
+    return max(mu / ref, ref / mu) <= factor
+
+
 def _solve_scalar(mesh_results, C, D, u, mu=None, mu_function=None, clamp=False, bottom_id=4):
     mesh = _check_space(C, 'P2')
     prob = scalar_problem(mesh, mesh_results['bc_markers'], bottom_id)
@@ -127,7 +158,8 @@ def _solve_scalar(mesh_results, C, D, u, mu=None, mu_function=None, clamp=False,
         kw = dict(mu_nodal=mu_dev, clamp=clamp, coarse_mu=max(mean, 0.0))
     elif mu is not None:
         kw = dict(mu_const=float(mu))
-    prob.assemble(float(D), ux, uy, bc_values={1: 1.0, 2: 0.0}, **kw)
+    reuse = ux is None and mu_function is None and mu is not None and _reuse_coarse(prob, float(mu))
+    prob.assemble(float(D), ux, uy, bc_values={1: 1.0, 2: 0.0}, reuse_coarse=reuse, **kw)
     method = 'cg' if ux is None else 'fgmres'
     x = prob.solve(method, rtol=RTOL)
     _accept_scalar(prob.last_info)

@@ -32,6 +32,7 @@ import numpy as np
 
 from .parameters import Parameters, StepUptakeOpen, create_geometry_variations
 from .simulation import run_simulation
+from .solvers import frozen_coarse_levels
 from .sweep import run_sharded
 
 
@@ -334,7 +335,7 @@ def _slim(result, **extra):
 
 
 def run_mu_sweep(output_dir=None, regimes: Optional[Dict[str, List[float]]] = None, w_dim=0.25, h_dim=0.25,
-                 mesh_size_dim=0.02, rank=None, world=None, quiet=True, streams=1):
+                 mesh_size_dim=0.02, rank=None, world=None, quiet=True, streams=1, frozen_coarse=True):
     """Reference ``run_mu_sweep``: 20 mu values in three uptake regimes on the 0.25 x 0.25 mm sulcus; the mesh,
     patterns and multigrid hierarchy are built once and reused by every mu.  Rank 0 writes
     ``mu_parameter_sweep_results.csv``."""
@@ -351,8 +352,11 @@ def run_mu_sweep(output_dir=None, regimes: Optional[Dict[str, List[float]]] = No
         p.validate()
         p.nondim()
         name = f"{reg}_mu_{factor:.1f}x"
-        res = _run(quiet, mode='no-adv', study_type="Phase A/Mu Parameter Sweep Simulations", config_name=name,
-                   domain_type='sulcus', params=p)
+        # one geometry, 20 Robin coefficients: the multigrid levels are kept while mu stays within 4x of the value they
+        # were assembled for (solvers.frozen_coarse_levels: preconditioner data only, same residual target)
+        with frozen_coarse_levels(4.0 if frozen_coarse else 1.0):
+            res = _run(quiet, mode='no-adv', study_type="Phase A/Mu Parameter Sweep Simulations", config_name=name,
+                       domain_type='sulcus', params=p)
         return extract_mu_sweep_data(_slim(res, regime=reg, mu_factor=factor, mu_dim_used=p.mu_dim, mu_used=p.mu,
                                            baseline_mu_dim=base), name)
     done = _sharded(cases, one, rank, world, streams, quiet)

@@ -12,6 +12,7 @@ from typing import Callable, List, Sequence
 # with its own CUDA stream and its own device problems (cache slot, see ``current_slot``); the host mesh, patterns and
 # multigrid hierarchy of a geometry are shared.  The C ABI is thread-safe per handle and releases the GIL.
 _tls = threading.local()
+_warm_slots = set()          # slots whose worker has run at least one case (its device problems exist)
 
 
 def current_slot() -> int:
@@ -27,8 +28,9 @@ def shard_cases(cases: Sequence, rank: int, world: int) -> List:
 
 def run_concurrent(indexed_cases: Sequence, run_case: Callable, streams: int) -> List:
     """Run ``(index, case)`` pairs on ``streams`` worker threads, one CUDA stream and one device-problem slot each;
-    returns ``(index, result)`` in index order.  The first case of every thread runs under a lock (it builds that slot's
-    device problems: pattern sorts and uploads are not worth overlapping and the per-mesh caches fill in a fixed order)."""
+    returns ``(index, result)`` in index order.  The first case a slot ever runs is taken under a lock (it builds that
+    slot's device problems: pattern sorts and uploads are not worth overlapping and the per-mesh caches fill in a fixed
+    order); later sweeps start all workers at once."""
     import torch
     streams = max(1, min(int(streams), len(indexed_cases)))
     if streams == 1:
@@ -45,10 +47,11 @@ def run_concurrent(indexed_cases: Sequence, run_case: Callable, streams: int) ->
             with torch.cuda.stream(st):
                 mine = indexed_cases[slot::streams]
                 for k, (i, c) in enumerate(mine):
-                    if k == 0:
-                        with first:
+                    if k == 0 and slot not in _warm_slots:
+                        with first:                     # first case ever of this slot: builds its device problems
                             out[i] = run_case(c)
                             st.synchronize()
+                        _warm_slots.add(slot)
                     else:
                         out[i] = run_case(c)
                 st.synchronize()

@@ -194,6 +194,8 @@ sfem_mg_t sfem_mg_create(int nlevels, const int* h_n, const int* h_A_nnz,
  * (re)compute D^-1, the Gershgorin bound of lambda_max(D^-1 A) and the Chebyshev coefficients of
  * every level from the current operator values -- all on the device, no host synchronisation */
 int sfem_mg_setup(sfem_mg_t mg, void* stream);
+/* set-up of the system level only: mu sweeps that keep the coarse levels of a nearby mu (preconditioner data) */
+int sfem_mg_setup_fine(sfem_mg_t mg, void* stream);
 int sfem_mg_vcycle(sfem_mg_t mg, const double* b, double* x, void* stream);   /* x = M^-1 b */
 /* Multi-GPU: `mg` holds the row-partitioned levels (halo patterns attached to their matrices with
  * sfem_halo_attach BEFORE sfem_mg_create); below its last level the replicated hierarchy `tail` (n_tail

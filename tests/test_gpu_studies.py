@@ -198,3 +198,35 @@ def test_geometry_analysis_rows(tmp_path):
     assert abs(row['Mu_Eff_Simulation'] - me['mu_eff_sim']) <= 1e-8 * abs(me['mu_eff_sim'])
     assert abs(row['Mu_Eff_Opening'] - me['mu_eff_open']) <= 1e-8 * abs(me['mu_eff_open'])
     assert abs(row['Total_Mass'] - co.mass_metrics(om, c, 'sulcus', mk['domain_markers'])['total_mass']) < 1e-10
+
+
+def test_mu_sweep_with_frozen_coarse_levels_and_concurrent_streams():
+    """The mu sweep keeps the multigrid levels of a nearby mu (solvers.frozen_coarse_levels) and can keep several cases
+    in flight (sweep.run_concurrent): both are throughput devices only -- every row must equal the plain serial sweep to
+    solver tolerance, and CG must not need many more iterations behind the frozen levels."""
+    from sulcusfem import studies, solvers, simulation
+    from sulcusfem.parameters import Parameters
+    regimes = {'small_uptake': [0.1, 0.25, 0.5, 1.0, 2.0, 3.0], 'high_uptake': [50.0, 100.0, 150.0]}
+    plain = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, frozen_coarse=False)
+    frozen = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, frozen_coarse=True)
+    conc = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, frozen_coarse=True, streams=3)
+    assert list(plain['Config']) == list(frozen['Config']) == list(conc['Config'])
+    for col in ('Mu_Eff_Simulation', 'Mu_Eff_Opening', 'Total_Mass', 'Mouth_Flux_Total'):
+        for other in (frozen, conc):
+            assert np.allclose(other[col], plain[col], rtol=1e-9, atol=1e-13), col
+    # iteration counts behind frozen levels: solve mu = 3 with levels built for mu = 1 (ratio 3 < 4) and compare
+    p = Parameters(mode='no-adv', mesh_size_dim=H)
+    p.sulci_w_dim = p.sulci_h_dim = 0.25
+    base = float(getattr(Parameters, 'MU_DIM_NO_ADV'))
+    its = {}
+    for frozen_mode in (False, True):
+        out = []
+        for f in (1.0, 3.0):
+            p.mu_dim = base * f
+            p.validate()
+            p.nondim()
+            with solvers.frozen_coarse_levels(4.0 if frozen_mode else 1.0):
+                r = simulation.run_simulation('no-adv', 'T', 'c', 'sulcus', p)
+            out.append(r['c'].solver_info['iterations'])
+        its[frozen_mode] = out
+    assert its[True][1] <= its[False][1] + 4, its

@@ -44,13 +44,14 @@ def test_distributed_full_step_matches_single_gpu(world):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}',
            '--master-addr', '127.0.0.1', '--master-port', str(29700 + world),
            os.path.join(ROOT, 'bench.py'), '--gpus', str(world), '--h', '0.04', '--refine', '0', '--steps', '2',
-           '--warmup', '1', '--no-cpu', '--dd-replicate-below', '3000']
+           '--warmup', '1', '--no-cpu', '--dd-replicate-below', '3000', '--dd-refine', '']
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith('{')][-1]
     out = json.loads(line)
     dd = out['dd_strong'][0]
-    assert dd['n_gpus'] == world and dd['parity_ok'], dd
+    assert len(out['dd_strong']) == 1 and dd['n_gpus'] == world and dd['parity_ok'], dd
+    assert dd['local_assembly_equals_replicated']             # distributed assembly == rows of the replicated one, bit for bit
     assert dd['distributed_levels']['velocity'] >= 2          # a multi-level row-partitioned hierarchy was exercised
     it1, itn = dd['iterations']['single'], dd['iterations']['distributed']
     assert abs(it1['stokes'] - itn['stokes']) <= 3 and abs(it1['advdiff'] - itn['advdiff']) <= 2

@@ -231,3 +231,55 @@ def test_stokes_vector_layout_with_contiguous_owned_part(nranks):
         got_p = Bl @ np.nan_to_num(z[:2 * lu.n_loc], nan=0.0)
         assert np.allclose(got_u, yu[lu.owned], rtol=1e-13, atol=1e-13)
         assert np.allclose(got_p, yp[lp.owned], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize('nranks', [2, 3])
+def test_local_gather_plan_reproduces_the_owned_rows_bit_for_bit(nranks):
+    """Distributed assembly (dist.plan_local_gather): a rank's gather map = the global one restricted to its rows and
+    re-addressed to an element buffer that holds only the cells those rows touch (+ the whole Robin facet family).  Applied
+    to the same element matrices it must give exactly the owned rows of the globally gathered matrix (same contributions
+    in the same order -> identical floating-point sums)."""
+    from sulcusfem import dist, dofmap as dm, hostmesh as hm, partition as pt
+    from sulcusfem.unstructured import mesh_domain
+    m = mesh_domain(10.0, 1.0, 0.5, 1.0, 0.25, 'sulcus')
+    mk = hm.build_markers(m, 10.0, 1.0, 4.75, 5.25, 'sulcus')
+    bm = mk['bc_markers'].values
+    cd = dm.p2_cell_dofs(m)
+    n = dm.p2_num_dofs(m)
+    f, _, _ = dm.boundary_facets(m, bm, 4)
+    fd = dm.p2_facet_dofs(m, f)
+    pat = dm.build_pattern(n, n, [(cd, cd), (fd, fd)])
+    rng = np.random.default_rng(5)
+    Ecell = rng.random((m.num_cells, 36))
+    Efac = rng.random((len(f), 9))
+    E = np.concatenate([Ecell.ravel(), Efac.ravel()])
+    fb = pat.family_base[1]
+    vals = np.array([E[pat.contrib_code[pat.contrib_ptr[s]:pat.contrib_ptr[s + 1]]].sum() for s in range(pat.nnz)])
+    # numpy's pairwise .sum() is not the device's sequential order; use an explicit left-to-right sum on both sides
+    def seq(codes_of_slot, buf):
+        acc = 0.0
+        for c in codes_of_slot:
+            acc += buf[c]
+        return acc
+    X = dm.p2_dof_coordinates(m)
+    owner = pt.slab_owner(X[:, 0], nranks, X[:, 1])
+    gh = pt.ghost_sets(owner, nranks, [(pat.rowptr, pat.cols, owner)])
+    seen_cells = 0
+    for r in range(nranks):
+        lp = pt.partition_level(owner, nranks, r, gh, [9] * nranks, nb_max=1)
+        rp, lc, slot = pt.localize_csr(pat.rowptr, pat.cols, lp.owned, lp.g2l)
+        lens, codes = dist._flatten_contribs(pat.contrib_ptr, pat.contrib_code, slot)
+        cells, maps = dist.plan_local_gather([(lens, codes)], 36, fb)
+        ptr, code = maps[0]
+        assert len(cells) < m.num_cells and ptr[-1] == len(code) == len(codes)
+        seen_cells += len(cells)
+        Eloc = np.concatenate([Ecell[cells].ravel(), Efac.ravel()])
+        for k in range(0, len(slot), 7):
+            g = seq(pat.contrib_code[pat.contrib_ptr[slot[k]]:pat.contrib_ptr[slot[k] + 1]], E)
+            l = seq(code[ptr[k]:ptr[k + 1]], Eloc)
+            assert g == l                                   # bit for bit
+        # every cell that holds an owned dof is present, no cell without one
+        touches = np.isin(cd, lp.owned).any(axis=1)
+        assert np.array_equal(cells, np.flatnonzero(touches))
+    assert seen_cells < 1.5 * m.num_cells                   # one cell layer of overlap, not replication
+    del vals
