@@ -249,6 +249,8 @@ struct sfem_stokes {
   double* h_pin = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   WorkStream ws;
+  cudaStream_t side = nullptr;         // second stream: the pressure block of the preconditioner (st_precond)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   GraphExec iter[2];
   const double* graph_x = nullptr;     // the x pointer baked into the graphs
   unsigned long long graph_epoch = 0;  // registry epoch of their capture (sfem_graph.h)
@@ -265,9 +267,9 @@ int st_apply(sfem_stokes* h, const double* zin, double* y, cudaStream_t st) {
   return SFEM_OK;
 }
 
-int st_precond(sfem_stokes* h, const double* r, double* out, cudaStream_t st) {
+// S^-1 r_p: pressure-mass Chebyshev sweep + lubrication coarse correction (7 short launches on nv unknowns)
+int st_precond_pressure(sfem_stokes* h, const double* r, double* out, cudaStream_t st) {
   const size_t nu = 2 * (size_t)h->n2;
-  SFEM_TRY(mg_vcycle_level(h->mg, 0, r, out, st));
   // P1 mass matrix with Jacobi scaling has its spectrum in [1/2, 2]: 4 Chebyshev steps ~ exact solve
   SFEM_TRY(smooth(h->Mp, h->mp_dinv, h->mp_coef, 4, r + nu, out + nu, h->mp_r, h->mp_d0, h->mp_d1, true, st));
   if (h->nz > 0) {
@@ -280,9 +282,31 @@ int st_precond(sfem_stokes* h, const double* r, double* out, cudaStream_t st) {
     k_z_apply<<<grid_for(h->nv, kThreads * 2), kThreads, 0, st>>>(h->nv, h->zidx, h->zw, h->zcoef, out + nu); }
     SFEM_LAUNCH_CHECK();
   }
-  // experiment knob: relative scaling of the Schur block of the block-diagonal preconditioner (1 = none)
+  // experiment knob: relative scaling of the Schur block of the block-diagonal preconditioner (1 = none; measured flat,
+  // profiles/r02_ncu_hot_kernels.md)
   static const double schur_scale = [] { const char* e = std::getenv("SFEM_SCHUR_SCALE"); return e ? std::atof(e) : 1.0; }();
   if (schur_scale != 1.0 && schur_scale > 0.0) SFEM_TRY(vec_axpby(h->nv, schur_scale, out + nu, 0.0, out + nu, st));
+  return SFEM_OK;
+}
+
+// M^-1 r = ( V-cycle(K) r_u , S^-1 r_p ).  The two blocks touch disjoint data, so the pressure block (7 latency-bound
+// launches, ~70 us at r = 2) runs on a second stream next to the velocity V-cycle; inside a capture the fork / join
+// events become graph edges, i.e. the replayed iteration has two parallel branches.  Same kernels, same order inside
+// each branch: results are bit-identical to the serial sequence.  (Row-partitioned: the pressure branch owns the scalar
+// all-reduce and the pressure halo, the velocity branch the velocity halos and the vector all-reduce -- separate mailbox
+// channels and sequence counters.)
+int st_precond(sfem_stokes* h, const double* r, double* out, cudaStream_t st) {
+  static const bool fork = [] { const char* e = std::getenv("SFEM_STOKES_FORK"); return !(e && e[0] == '0'); }();
+  if (!fork || profiling_active() || h->side == nullptr) {
+    SFEM_TRY(mg_vcycle_level(h->mg, 0, r, out, st));
+    return st_precond_pressure(h, r, out, st);
+  }
+  SFEM_CUDA(cudaEventRecord(h->ev_fork, st));
+  SFEM_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  SFEM_TRY(st_precond_pressure(h, r, out, h->side));
+  SFEM_CUDA(cudaEventRecord(h->ev_join, h->side));
+  SFEM_TRY(mg_vcycle_level(h->mg, 0, r, out, st));
+  SFEM_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
   return SFEM_OK;
 }
 
@@ -361,7 +385,10 @@ sfem_stokes_t sfem_stokes_create_part(int n2, int nv,
   if (cudaMalloc(&h->buf, total * sizeof(double)) != cudaSuccess || cudaMemset(h->buf, 0, total * sizeof(double)) != cudaSuccess ||
       cudaMallocHost(&h->h_pin, 8 * sizeof(double)) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming) != cudaSuccess || h->ws.init() != SFEM_OK) {
+      cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming) != cudaSuccess || h->ws.init() != SFEM_OK ||
+      cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     set_error("sfem_stokes_create: allocation failed");
     sfem_stokes_destroy(h);
     return nullptr;
@@ -383,6 +410,9 @@ void sfem_stokes_destroy(sfem_stokes_t h) {
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaFree(h->buf);
   h->ws.destroy();
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   delete h;
 }
 
