@@ -117,6 +117,55 @@ __global__ void __launch_bounds__(256) k_allreduce_vec_recv(DistDev D, double* _
   }
 }
 
+// ---- vector all-reduce in ONE launch: reduce-scatter + all-gather over flagged words.  Thread i owns element i of every
+// chunk (chunk q = the part rank q reduces): it sends x[q][i] to rank q, polls the R - 1 contributions to its own chunk,
+// adds them in rank order, sends the sum to every peer and polls the R - 1 sums of the other chunks.  (R - 1) / R of the
+// vector travels twice -- against R - 1 full copies for the send-to-all scheme above -- and there is no fence, no ticket and
+// no second kernel on the critical path; the reduced value of an element is computed by ONE rank, so all ranks hold
+// bit-identical vectors.  Slots: [phase 2][parity 2][sender R][chunk] flagged pairs inside the mailbox's vector region.
+__global__ void __launch_bounds__(256) k_allreduce_vec_ll(DistDev D, double* __restrict__ x, int n,
+                                                          unsigned int* __restrict__ ticket) {
+  const unsigned long long s = D.seq[1];
+  const int par = (int)(s & 1ull);
+  const unsigned int flag = (unsigned int)(s + 1);
+  const int R = D.nranks, me = D.rank;
+  const long long chunk = ((long long)n + R - 1) / R;
+  auto slot = [&](int owner_rank, int phase, int sender, long long i) {
+    return reinterpret_cast<unsigned long long*>(D.mailbox[owner_rank] + D.vec_data_off) +
+           2 * ((((long long)phase * 2 + par) * R + sender) * chunk + i);
+  };
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunk; i += (long long)gridDim.x * blockDim.x) {
+    for (int q = 0; q < R; ++q) {                                   // reduce-scatter: send
+      if (q == me) continue;
+      const long long idx = q * chunk + i;
+      ll_store(slot(q, 0, me, i), idx < n ? x[idx] : 0.0, flag);
+    }
+    double acc = 0.0;
+    for (int q = 0; q < R; ++q) {                                   // my chunk: contributions in rank order
+      double v;
+      if (q == me) { const long long idx = me * chunk + i; v = idx < n ? x[idx] : 0.0; }
+      else ll_wait(slot(me, 0, q, i), flag, &v, D.err);
+      acc += v;
+    }
+    for (int q = 0; q < R; ++q)                                     // all-gather: send the reduced element
+      if (q != me) ll_store(slot(q, 1, me, i), acc, flag);
+    for (int q = 0; q < R; ++q) {
+      double v = acc;
+      if (q != me) ll_wait(slot(me, 1, q, i), flag, &v, D.err);
+      const long long idx = q * chunk + i;
+      if (idx < n) x[idx] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket + 2, 1u);
+    if (t == gridDim.x - 1) {
+      ticket[2] = 0;
+      D.seq[1] = s + 1;
+    }
+  }
+}
+
 __global__ void k_allreduce_scalars_test(DistDev D, double* vals, int K) {
   if (threadIdx.x == 0) dist_allreduce_scalars(D, vals, K);
 }
@@ -157,8 +206,14 @@ int dist_allreduce_vec(Dist* d, double* x, int n, cudaStream_t st, int phase) {
   if (!d || d->dev.nranks <= 1 || n <= 0) return SFEM_OK;
   if (n > d->dev.vec_cap) { set_error("vector all-reduce larger than the mailbox capacity"); return SFEM_ERR_ARG; }
   unsigned int* ticket = reinterpret_cast<unsigned int*>(d->dev.seq + 8);
-  const int grid = grid_for(n, 256 * 2, 1);
   Prof prof(PC_HALO, 16.0 * n * d->dev.nranks, st);
+  if (phase == 0) {          // production: reduce-scatter + all-gather over flagged words, one launch
+    const long long chunk = ((long long)n + d->dev.nranks - 1) / d->dev.nranks;
+    k_allreduce_vec_ll<<<grid_for(chunk, 256, 2), 256, 0, st>>>(d->dev, x, n, ticket);
+    SFEM_LAUNCH_CHECK();
+    return SFEM_OK;
+  }
+  const int grid = grid_for(n, 256 * 2, 1);
   if (phase != 2) {
     k_allreduce_vec_send<<<grid, 256, 0, st>>>(d->dev, x, n, ticket);
     SFEM_LAUNCH_CHECK();
@@ -181,7 +236,11 @@ extern "C" {
 
 /* mailbox layout helper: words (8 bytes) reserved at the start of every mailbox for the all-reduces */
 long long sfem_dist_header_words(int nranks, long long vec_cap) {
-  return 2LL * nranks + 4LL * nranks * kAllreduceMaxK + 2LL * nranks + 2LL * nranks * vec_cap;
+  // vector region: [2 phases][2 parities][nranks][chunk] flagged pairs (k_allreduce_vec_ll) or [2][nranks][vec_cap] plain
+  // words (the two-kernel test path), whichever is larger
+  const long long ll_words = 8LL * (vec_cap + nranks) + 16;
+  const long long plain = 2LL * nranks * vec_cap;
+  return 2LL * nranks + 4LL * nranks * kAllreduceMaxK + 2LL * nranks + (ll_words > plain ? ll_words : plain);
 }
 
 sfem_dist_t sfem_dist_create(int rank, int nranks, long long mailbox_words, long long vec_cap) {

@@ -532,6 +532,23 @@ def test_mailbox_halo_exchange_and_vector_allreduce_emulated(ctx):
             for v in vs:
                 assert np.allclose(v.cpu().numpy(), want, rtol=1e-15)
                 assert np.array_equal(v.cpu().numpy(), vs[0].cpu().numpy())       # bit-identical on every rank
+        # production vector all-reduce (phase 0): reduce-scatter + all-gather over flagged words in ONE launch per rank;
+        # the emulated ranks run concurrently on their own streams (every kernel polls for its peers' words)
+        streams = [torch.cuda.Stream() for _ in range(R)]
+        torch.cuda.synchronize()
+        for nvals in (vec_cap - 7, 1, R, 2 * R + 1):
+            for trial in range(3):                       # both parities of the slots get reused
+                vs = [torch.from_numpy(rng.random(nvals)).to(ctx.device) for _ in range(R)]
+                want = vs[0].cpu().numpy().copy()
+                for v in vs[1:]:
+                    want = want + v.cpu().numpy()        # rank order, like the kernel
+                torch.cuda.synchronize()
+                for r in range(R):
+                    with torch.cuda.stream(streams[r]):
+                        capi.check(lib.sfem_dist_allreduce_vec(dists[r].handle, P(vs[r]), nvals, 0, ctx.stream))
+                torch.cuda.synchronize()
+                for v in vs:
+                    assert np.array_equal(v.cpu().numpy(), want), (nvals, trial)      # bit-identical on every rank
         assert not any(d.error() for d in dists)
         for h in halos:
             lib.sfem_halo_destroy(h.handle)
