@@ -20,8 +20,9 @@ int spmv(const Csr& A, const double* x, const double* b, double* y, int mode, cu
 int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* nparts, cudaStream_t st, int nb = 1,
              const double* dotx = nullptr, int mode = 0, bool exchange = true);   // partial sums of <dotx, y>; mode 2: y += A x first
 // Chebyshev coefficients are read from device memory: c12 -> {c1, c2}, c0 -> {c0}
+// (b0 != nullptr: first step of a sweep that starts from x = 0 -- the residual is read from b0, x is taken as zero)
 int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
-              const double* c12, int last, cudaStream_t st, int nb = 1);
+              const double* c12, int last, cudaStream_t st, int nb = 1, const double* b0 = nullptr);
 int resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
              const double* c0, cudaStream_t st, int nb = 1);
 // y_u = K z_u + BT z_p (interleaved velocity), partial sums of <z_u, y_u>
@@ -33,7 +34,7 @@ int staged_spmv(const Csr& A, const double* x, const double* b, double* y, int m
 int staged_spmv_dot(const Csr& A, const double* x, const double* dx, double* y, double* partial, int* nparts, int mode,
                     int nb, cudaStream_t st);
 int staged_cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
-                     const double* c12, int last, int nb, cudaStream_t st);
+                     const double* c12, int last, int nb, cudaStream_t st, const double* b0 = nullptr);
 int staged_resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
                     const double* c0, int nb, cudaStream_t st);
 
@@ -42,7 +43,7 @@ int sell_spmv(const Csr& A, const double* x, const double* b, double* y, int mod
 int sell_spmv_dot(const Csr& A, const double* x, const double* dx, double* y, double* partial, int* nparts, int mode,
                   int nb, cudaStream_t st);
 int sell_cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
-                   const double* c12, int last, int nb, cudaStream_t st);
+                   const double* c12, int last, int nb, cudaStream_t st, const double* b0 = nullptr);
 int sell_resid_d0(const Csr& A, const double* dinv, const double* b, const double* x, double* r, double* d,
                   const double* c0, int nb, cudaStream_t st);
 void sell_mark_dirty(const double* csr_vals);     // called by every entry that writes CSR values

@@ -26,7 +26,9 @@ namespace {
 
 // n = rows * nb entries; dinv is per row
 // NB == 2: one thread per dof streams the interleaved pair as double2 (b, r, d, x are 16-byte aligned)
-template <int NB>
+// start of a sweep from x = 0:  d_0 = D^-1 b / theta.  FULL: also r = b, x = d_0 (a one-step sweep); otherwise only d_0 is
+// written -- the first fused step reads its residual from b and takes x as zero (EpiCheb::b0).
+template <int NB, bool FULL>
 __global__ void __launch_bounds__(kThreads) k_cheb_init0(int nrows, const double* __restrict__ dinv,
                                                          const double* __restrict__ b, double* __restrict__ r,
                                                          double* __restrict__ d, double* __restrict__ x,
@@ -36,14 +38,19 @@ __global__ void __launch_bounds__(kThreads) k_cheb_init0(int nrows, const double
     const double s = c0 * dinv[i];
     if (NB == 2) {
       const double2 bi = reinterpret_cast<const double2*>(b)[i];
-      reinterpret_cast<double2*>(r)[i] = bi;
-      reinterpret_cast<double2*>(d)[i] = make_double2(s * bi.x, s * bi.y);
-      reinterpret_cast<double2*>(x)[i] = make_double2(0.0, 0.0);
+      const double2 di = make_double2(s * bi.x, s * bi.y);
+      reinterpret_cast<double2*>(d)[i] = di;
+      if (FULL) {
+        reinterpret_cast<double2*>(r)[i] = bi;
+        reinterpret_cast<double2*>(x)[i] = di;
+      }
     } else {
       const double bi = b[i];
-      r[i] = bi;
       d[i] = s * bi;
-      x[i] = 0.0;
+      if (FULL) {
+        r[i] = bi;
+        x[i] = s * bi;
+      }
     }
   }
 }
@@ -120,19 +127,28 @@ int cheb_setup(const Csr* A, const double* dinv, double fixed_lmax, double ratio
 int smooth(const Csr& A, const double* dinv, const double* coef, int degree, const double* b, double* x,
            double* r, double* d0, double* d1, bool zero_init, cudaStream_t st, int nb) {
   const int n = A.nrows * nb;
+  const int gi = grid_for(A.nrows, kThreads * 2);
   if (zero_init) {
-    { Prof prof(PC_VEC, 32.0 * n + 8.0 * A.nrows, st);
-    if (nb == 2) k_cheb_init0<2><<<grid_for(A.nrows, kThreads * 2), kThreads, 0, st>>>(A.nrows, dinv, b, r, d0, x, coef);
-    else k_cheb_init0<1><<<grid_for(A.nrows, kThreads * 2), kThreads, 0, st>>>(A.nrows, dinv, b, r, d0, x, coef); }
+    if (degree <= 1) {                                        // one-step sweep: x = d_0, r = b
+      Prof prof(PC_VEC, 32.0 * n + 8.0 * A.nrows, st);
+      if (nb == 2) k_cheb_init0<2, true><<<gi, kThreads, 0, st>>>(A.nrows, dinv, b, r, d0, x, coef);
+      else k_cheb_init0<1, true><<<gi, kThreads, 0, st>>>(A.nrows, dinv, b, r, d0, x, coef);
+    } else {                                                  // only d_0: the first fused step reads b and takes x = 0
+      Prof prof(PC_VEC, 16.0 * n + 8.0 * A.nrows, st);
+      if (nb == 2) k_cheb_init0<2, false><<<gi, kThreads, 0, st>>>(A.nrows, dinv, b, r, d0, x, coef);
+      else k_cheb_init0<1, false><<<gi, kThreads, 0, st>>>(A.nrows, dinv, b, r, d0, x, coef);
+    }
     SFEM_LAUNCH_CHECK();
+    if (degree <= 1) return SFEM_OK;
   } else {
     SFEM_TRY(resid_d0(A, dinv, b, x, r, d0, coef + 1, st, nb));
+    if (degree <= 1) return vec_axpby(n, 1.0, d0, 1.0, x, st);
   }
-  if (degree <= 1) return vec_axpby(n, 1.0, d0, 1.0, x, st);
   double* dold = d0;
   double* dnew = d1;
   for (int i = 0; i < degree - 1; ++i) {
-    SFEM_TRY(cheb_step(A, dinv, dold, dnew, r, x, coef + 2 + 2 * i, i == degree - 2, st, nb));
+    SFEM_TRY(cheb_step(A, dinv, dold, dnew, r, x, coef + 2 + 2 * i, i == degree - 2, st, nb,
+                       (zero_init && i == 0) ? b : nullptr));
     double* t = dold; dold = dnew; dnew = t;
   }
   return SFEM_OK;

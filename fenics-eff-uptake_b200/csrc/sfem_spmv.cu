@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_cheb_step(int nrows, const int*
                                                         const int* __restrict__ cols, const double* __restrict__ vals,
                                                         const double* __restrict__ dinv, const double* __restrict__ d_old,
                                                         double* __restrict__ d_new, double* __restrict__ r,
-                                                        double* __restrict__ x, const double* __restrict__ c12, int last) {
-  EpiCheb<NB> epi{dinv, d_old, d_new, r, x, c12[0], c12[1], last};
+                                                        double* __restrict__ x, const double* __restrict__ c12, int last,
+                                                        const double* __restrict__ b0) {
+  EpiCheb<NB> epi{dinv, d_old, d_new, r, x, c12[0], c12[1], last, b0};
   row_engine<LANES, NB>(nrows, rowptr, cols, vals, d_old, epi);
 }
 
@@ -144,22 +145,22 @@ int spmv_dot(const Csr& A, const double* x, double* y, double* partial, int* npa
 }
 
 int cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
-              const double* c12, int last, cudaStream_t st, int nb) {
+              const double* c12, int last, cudaStream_t st, int nb, const double* b0) {
   SFEM_TRY(halo_exchange(find_halo(A.rowptr), const_cast<double*>(d_old), nb, st));
-  { const int took = sell_cheb_step(A, dinv, d_old, d_new, r, x, c12, last, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
-  { const int took = staged_cheb_step(A, dinv, d_old, d_new, r, x, c12, last, nb, st); if (took != 0) return took < 0 ? took : SFEM_OK; }
+  { const int took = sell_cheb_step(A, dinv, d_old, d_new, r, x, c12, last, nb, st, b0); if (took != 0) return took < 0 ? took : SFEM_OK; }
+  { const int took = staged_cheb_step(A, dinv, d_old, d_new, r, x, c12, last, nb, st, b0); if (took != 0) return took < 0 ? took : SFEM_OK; }
   const int lanes = lanes_for(A, nb);
-  Prof prof(PC_CHEB, 12.0 * A.nnz + 12.0 * A.nrows + 48.0 * nb * A.nrows, st);
+  Prof prof(PC_CHEB, 12.0 * A.nnz + 12.0 * A.nrows + (b0 ? 40.0 : 48.0) * nb * A.nrows, st);
   if (nb == 1) {
     SFEM_DISPATCH_LANES(lanes, {
       const int grid = grid_for(A.nrows, kThreads / LN, kSpmvBlocksPerSm);
-      k_cheb_step<LN, 1><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, d_old, d_new, r, x, c12, last);
+      k_cheb_step<LN, 1><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, d_old, d_new, r, x, c12, last, b0);
     });
   } else {
     SFEM_DISPATCH_LANES(lanes, {
       constexpr int L2 = LN < 2 ? 2 : LN;
       const int grid = grid_for(A.nrows, kThreads / L2, kSpmvBlocksPerSm);
-      k_cheb_step<L2, 2><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, d_old, d_new, r, x, c12, last);
+      k_cheb_step<L2, 2><<<grid, kThreads, 0, st>>>(A.nrows, A.rowptr, A.cols, A.vals, dinv, d_old, d_new, r, x, c12, last, b0);
     });
   }
   SFEM_LAUNCH_CHECK();

@@ -287,17 +287,17 @@ int sell_spmv_dot(const Csr& A, const double* x, const double* dx, double* y, do
 }
 
 int sell_cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
-                   const double* c12, int last, int nb, cudaStream_t st) {
-  if (nb == 2 && !aligned16(d_old, d_new, r, x)) return 0;
+                   const double* c12, int last, int nb, cudaStream_t st, const double* b0) {
+  if (nb == 2 && (!aligned16(d_old, d_new, r, x) || (b0 && !aligned16(b0)))) return 0;
   SellPlan P;
   const int f = find_sell(A, &P, st);
   if (f <= 0) return f;
-  Prof prof(PC_CHEB, 12.0 * A.nnz + 12.0 * A.nrows + 48.0 * nb * A.nrows, st);
+  Prof prof(PC_CHEB, 12.0 * A.nnz + 12.0 * A.nrows + (b0 ? 40.0 : 48.0) * nb * A.nrows, st);
   int rc;
-  if (nb == 1) rc = launch_sell<1, EpiChebPtr<1>, false>(P, d_old, EpiChebPtr<1>{dinv, d_old, d_new, r, x, c12, last}, nullptr, nullptr, st);
+  if (nb == 1) rc = launch_sell<1, EpiChebPtr<1>, false>(P, d_old, EpiChebPtr<1>{dinv, d_old, d_new, r, x, c12, last, b0}, nullptr, nullptr, st);
   // heaviest epilogue (7 vector streams x 2 right-hand sides): 4-step chunks at 3 blocks per SM beat 3-step chunks at 4
   // blocks (spills) and 2-step chunks at 4 blocks -- V-cycle at r = 2: 0.667 / 0.713 / 0.675 ms
-  else rc = launch_sell<2, EpiChebPtr<2>, false, 4, 3>(P, d_old, EpiChebPtr<2>{dinv, d_old, d_new, r, x, c12, last}, nullptr, nullptr, st);
+  else rc = launch_sell<2, EpiChebPtr<2>, false, 4, 3>(P, d_old, EpiChebPtr<2>{dinv, d_old, d_new, r, x, c12, last, b0}, nullptr, nullptr, st);
   return rc == SFEM_OK ? 1 : rc;
 }
 

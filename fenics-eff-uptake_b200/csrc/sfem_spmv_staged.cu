@@ -306,13 +306,13 @@ int staged_spmv_dot(const Csr& A, const double* x, const double* dx, double* y, 
 }
 
 int staged_cheb_step(const Csr& A, const double* dinv, const double* d_old, double* d_new, double* r, double* x,
-                     const double* c12, int last, int nb, cudaStream_t st) {
+                     const double* c12, int last, int nb, cudaStream_t st, const double* b0) {
   Plan P;
   if (!find_plan(A, &P, nb)) return 0;
   Prof prof(PC_CHEB, 12.0 * A.nnz + 12.0 * A.nrows + 48.0 * nb * A.nrows, st);
   int rc;
-  if (nb == 1) rc = launch_staged<1, EpiChebPtr<1>, false>(P, A, d_old, EpiChebPtr<1>{dinv, d_old, d_new, r, x, c12, last}, nullptr, nullptr, st);
-  else rc = launch_staged<2, EpiChebPtr<2>, false>(P, A, d_old, EpiChebPtr<2>{dinv, d_old, d_new, r, x, c12, last}, nullptr, nullptr, st);
+  if (nb == 1) rc = launch_staged<1, EpiChebPtr<1>, false>(P, A, d_old, EpiChebPtr<1>{dinv, d_old, d_new, r, x, c12, last, b0}, nullptr, nullptr, st);
+  else rc = launch_staged<2, EpiChebPtr<2>, false>(P, A, d_old, EpiChebPtr<2>{dinv, d_old, d_new, r, x, c12, last, b0}, nullptr, nullptr, st);
   return rc == SFEM_OK ? 1 : rc;
 }
 
