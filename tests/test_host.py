@@ -714,3 +714,25 @@ def test_dolfin_adapter_matches_dofs_and_facets_by_geometry():
             sys.modules['solvers'] = saved
         else:
             sys.modules.pop('solvers', None)
+
+
+def test_frozen_coarse_levels_policy():
+    """solvers.frozen_coarse_levels: the multigrid levels of a mu sweep are reused only inside the context, only for a
+    mu within the given factor of the mu they were assembled for, and the setting is per thread (sweep workers)."""
+    import threading
+    from types import SimpleNamespace
+    from sulcusfem import solvers
+    prob = SimpleNamespace(_coarse_mu=2.0)
+    assert not solvers._reuse_coarse(prob, 2.0)                       # outside the context: always a full assembly
+    with solvers.frozen_coarse_levels(4.0):
+        assert solvers._reuse_coarse(prob, 2.0) and solvers._reuse_coarse(prob, 8.0) and solvers._reuse_coarse(prob, 0.5)
+        assert not solvers._reuse_coarse(prob, 8.1) and not solvers._reuse_coarse(prob, 0.49)
+        assert not solvers._reuse_coarse(prob, 0.0) and not solvers._reuse_coarse(SimpleNamespace(), 2.0)
+        seen = []
+        t = threading.Thread(target=lambda: seen.append(solvers._reuse_coarse(prob, 2.0)))
+        t.start(); t.join()
+        assert seen == [False]                                        # another thread has its own setting
+        with solvers.frozen_coarse_levels(1.0):
+            assert solvers._reuse_coarse(prob, 2.0) and not solvers._reuse_coarse(prob, 2.1)
+        assert solvers._reuse_coarse(prob, 8.0)                       # restored
+    assert not solvers._reuse_coarse(prob, 2.0)
