@@ -225,22 +225,105 @@ def advdiff_solver_variable_mu(mesh_results, u, C, D, mu_function, mesh_type="su
 
 
 # ====================================================================== diffusion only
-def pure_diffusion_solver(mesh_results, C, D, mu, mesh_type="sulcus"):
-    """Steady diffusion with constant Robin uptake (reference solvers.py:113-174)."""
-    prob, x = _solve_scalar(mesh_results, C, D, None, mu=mu)
+def _pure_diffusion_stats(prob, x):
+    """The validation block of the reference's pure_diffusion_solver (solvers.py:154-173) as (stats, printed lines)."""
     st = _post(prob, x, fix_nonfinite=False)
+    lines = []
     if st['negative'] > 0:
         if st['clamped']:
             st = _post(prob, x, fix_nonfinite=False)
         else:
-            print(f"WARNING: {st['negative']} negative concentration values found!")
-            print(f"  Most negative: {st['min']:.6e}")
-            print(f"  Min: {st['min']:.6e}, Max: {st['max']:.6e}")
-            print("  Check: mesh quality, boundary conditions, solver settings")
+            lines += [f"WARNING: {st['negative']} negative concentration values found!",
+                      f"  Most negative: {st['min']:.6e}",
+                      f"  Min: {st['min']:.6e}, Max: {st['max']:.6e}",
+                      "  Check: mesh quality, boundary conditions, solver settings"]
     else:
-        print("✓ All concentration values are non-negative")
-    print(f"Solution stats: min={st['min']:.6e}, max={st['max']:.6e}, mean={st['mean']:.6e}")
+        lines.append("✓ All concentration values are non-negative")
+    lines.append(f"Solution stats: min={st['min']:.6e}, max={st['max']:.6e}, mean={st['mean']:.6e}")
+    return st, lines
+
+
+def pure_diffusion_solver(mesh_results, C, D, mu, mesh_type="sulcus"):
+    """Steady diffusion with constant Robin uptake (reference solvers.py:113-174).  A field that
+    :func:`presolve_pure_diffusion` already computed for this (mesh, D, mu) is handed out instead of solving again."""
+    pre = _cache(_check_space(C, 'P2')).get('presolved')
+    if pre:
+        hit = pre.pop(_presolve_key(D, mu), None)
+        if hit is not None:
+            f, lines = hit
+            print("\n".join(lines))
+            return f
+    prob, x = _solve_scalar(mesh_results, C, D, None, mu=mu)
+    _, lines = _pure_diffusion_stats(prob, x)
+    print("\n".join(lines))
     return _to_function(C, prob, x)
+
+
+# ---------------------------------------------------------------------- batched Robin sweeps (SURVEY 8(e))
+# The reference's mu sweeps (no_advection_analysis_A.py:1306-1347: 20 mu on one mesh; no_advection_analysis_B.py:110-141:
+# 3 mu per geometry) call pure_diffusion_solver once per mu.  A(mu) = D K + mu M_Gamma differs between the cases in its
+# boundary rows only, so up to BATCH coefficients are solved in ONE Krylov loop (sfem_krylov_cg_batch: interleaved
+# right-hand sides, per-column CG scalars, one shared multigrid hierarchy assembled for the batch's geometric-mean mu).
+BATCH = 8
+BATCH_SPAN = 64.0         # largest mu / smallest mu inside one batch (the hierarchy is assembled for their geometric mean)
+
+
+def _presolve_key(D, mu):
+    return (float(D), float(mu))
+
+
+def pure_diffusion_solver_batch(mesh_results, C, D, mus, mesh_type="sulcus"):
+    """``[pure_diffusion_solver(mesh_results, C, D, mu) for mu in mus]`` in batched solves of up to ``BATCH`` coefficients
+    (nearby coefficients share a batch: the list is processed in ascending order of mu).  Returns the Functions in the
+    order of ``mus``; each carries ``solver_info`` and prints the reference's validation lines."""
+    out = _solve_batches(mesh_results, C, D, mus)
+    fs = []
+    for f, lines in out:
+        print("\n".join(lines))
+        fs.append(f)
+    return fs
+
+
+def presolve_pure_diffusion(mesh_results, C, D, mus):
+    """Solve all ``mus`` of one geometry in batches and park the fields on the mesh; the next
+    ``pure_diffusion_solver(mesh_results, C, D, mu)`` call for each of them (e.g. from ``run_simulation``) returns the
+    parked field.  Returns the number of parked fields."""
+    mesh = _check_space(C, 'P2')
+    mus = [float(m) for m in mus]
+    out = _solve_batches(mesh_results, C, D, mus)
+    pre = _cache(mesh).setdefault('presolved', {})
+    for mu, hit in zip(mus, out):
+        pre[_presolve_key(D, mu)] = hit
+    import torch
+    torch.cuda.current_stream().synchronize()      # the parked fields may be consumed on other streams (sweep workers)
+    return len(out)
+
+
+def _solve_batches(mesh_results, C, D, mus):
+    mesh = _check_space(C, 'P2')
+    prob = scalar_problem(mesh, mesh_results['bc_markers'], 4)
+    mus = [float(m) for m in mus]
+    order = sorted(range(len(mus)), key=lambda i: mus[i])
+    out = [None] * len(mus)
+    chunks, cur = [], []
+    for i in order:              # a batch holds <= BATCH coefficients within a factor BATCH_SPAN (one shared preconditioner)
+        if cur and (len(cur) >= BATCH or (mus[cur[0]] > 0.0 and mus[i] > BATCH_SPAN * mus[cur[0]])):
+            chunks.append(cur)
+            cur = []
+        cur.append(i)
+    if cur:
+        chunks.append(cur)
+    for idx in chunks:
+        X, infos = prob.solve_batch(float(D), [mus[i] for i in idx], {1: 1.0, 2: 0.0}, rtol=RTOL)
+        for c, i in enumerate(idx):
+            _accept_scalar(infos[c])
+            x = prob.batch_column(X, len(idx), c)
+            _, lines = _pure_diffusion_stats(prob, x)
+            f = Function(C, prob.ctx.down(x))
+            f._dev = (x,)
+            f.solver_info = dict(infos[c])
+            out[i] = (f, lines)
+    return out
 
 
 def pure_diffusion_solver_variable_mu(mesh_results, C, D, mu_function, mesh_type="rectangular", bottom_id=4, u=None):

@@ -154,9 +154,11 @@ def phase_b_row(gkey, gcfg, mu, conc_s, conc_r, flux_s, flux_r):
 
 
 def run_no_adv_mu_sweep(output_dir=None, mu_factors: Iterable[float] = None, geometries: Optional[Dict] = None,
-                        mesh_size_dim=0.02, rank=None, world=None, quiet=True, prefetch=True, streams=1):
+                        mesh_size_dim=0.02, rank=None, world=None, quiet=True, prefetch=True, streams=1, batch=True):
     """Reference ``run_no_adv_mu_sweep`` (23 geometries x 3 mu x {sulcus, rectangle} = 138 solves by default).
-    Returns the DataFrame with the reference's columns; rank 0 writes ``no_adv_mu_sweep_results.csv``."""
+    ``batch`` (default): the mu values of every mesh of this rank are solved in one batched Krylov loop first
+    (``presolve_no_adv``).  Returns the DataFrame with the reference's columns; rank 0 writes
+    ``no_adv_mu_sweep_results.csv``."""
     rank, world = _world(rank, world)
     mu_factors = list(MU_FACTORS_PHASE_B if mu_factors is None else mu_factors)
     configs = geometries if geometries is not None else create_geometry_variations(Parameters(mode='no-adv'), max_width=1.0)
@@ -165,6 +167,10 @@ def run_no_adv_mu_sweep(output_dir=None, mu_factors: Iterable[float] = None, geo
     _prefetch([[(_params_no_adv(mu, cfg['sulci_w_dim'], cfg['sulci_h_dim'], mesh_size_dim), 'sulcus'),
                 (_params_no_adv(mu, cfg['sulci_w_dim'], cfg['sulci_h_dim'], mesh_size_dim), 'rectangular')]
                for mu, _, cfg in cases], rank, world, prefetch)
+    if batch:
+        presolve_no_adv([(_params_no_adv(mu, cfg['sulci_w_dim'], cfg['sulci_h_dim'], mesh_size_dim), dom)
+                         for i, (mu, _, cfg) in enumerate(cases) if i % world == rank
+                         for dom in ('sulcus', 'rectangular')], quiet)
     done = _sharded(cases, lambda c: phase_b_case(c, mesh_size_dim, quiet), rank, world, streams, quiet)
     df = _frame([row for _, row in done], ['mu_factor', 'geometry'])
     p0 = Parameters(mode='no-adv')
@@ -334,23 +340,52 @@ def _slim(result, **extra):
     return out
 
 
+def presolve_no_adv(jobs, quiet=True):
+    """Batched pre-solve of no-advection cases: ``jobs`` = (params, domain_type) pairs; the pairs that
+    share a mesh and a diffusivity are solved together, up to ``solvers.BATCH`` Robin coefficients per Krylov loop
+    (``solvers.presolve_pure_diffusion``), and the fields are parked on the mesh for the ``run_simulation`` calls that
+    follow.  Returns the number of parked fields."""
+    from .fem import FunctionSpace
+    from .simulation import _mesh_key, _simulation_generate_mesh
+    from .solvers import presolve_pure_diffusion
+    groups = {}
+    for p, dom in jobs:
+        groups.setdefault((_mesh_key(p, dom)[0], float(p.D)), []).append((p, dom))
+    n = 0
+    with contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext():
+        for (_, D), members in groups.items():
+            p0, dom = members[0]
+            mr = _simulation_generate_mesh(p0, dom)
+            mus = sorted({float(p.mu) for p, _ in members})
+            n += presolve_pure_diffusion(mr, FunctionSpace(mr['mesh'], "CG", 2), D, mus)
+    return n
+
+
 def run_mu_sweep(output_dir=None, regimes: Optional[Dict[str, List[float]]] = None, w_dim=0.25, h_dim=0.25,
-                 mesh_size_dim=0.02, rank=None, world=None, quiet=True, streams=1, frozen_coarse=True):
+                 mesh_size_dim=0.02, rank=None, world=None, quiet=True, streams=1, frozen_coarse=True, batch=True):
     """Reference ``run_mu_sweep``: 20 mu values in three uptake regimes on the 0.25 x 0.25 mm sulcus; the mesh,
-    patterns and multigrid hierarchy are built once and reused by every mu.  Rank 0 writes
-    ``mu_parameter_sweep_results.csv``."""
+    patterns and multigrid hierarchy are built once and reused by every mu.  ``batch`` (default): this rank's mu
+    values are solved up to 8 at a time in batched Krylov loops before the per-case drivers run (``presolve_no_adv``);
+    ``batch=False`` solves case by case (``frozen_coarse`` then keeps the multigrid levels between nearby mu).
+    Rank 0 writes ``mu_parameter_sweep_results.csv``."""
     rank, world = _world(rank, world)
     regimes = REGIMES if regimes is None else regimes
     base = float(getattr(Parameters, 'MU_DIM_NO_ADV'))
     cases = [(reg, f) for reg, fs in regimes.items() for f in fs]
 
-    def one(case):
-        reg, factor = case
+    def params_of(factor):
         p = Parameters(mode='no-adv', mesh_size_dim=mesh_size_dim)
         p.sulci_w_dim, p.sulci_h_dim = w_dim, h_dim
         p.mu_dim = base * factor
         p.validate()
         p.nondim()
+        return p
+    if batch:
+        presolve_no_adv([(params_of(f), 'sulcus') for i, (_, f) in enumerate(cases) if i % world == rank], quiet)
+
+    def one(case):
+        reg, factor = case
+        p = params_of(factor)
         name = f"{reg}_mu_{factor:.1f}x"
         # one geometry, 20 Robin coefficients: the multigrid levels are kept while mu stays within 4x of the value they
         # were assembled for (solvers.frozen_coarse_levels: preconditioner data only, same residual target)

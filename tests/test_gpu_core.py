@@ -324,6 +324,60 @@ def test_diffusion_solve_matches_lu(ctx, small, engine):
         assert _rel(c, ref) < 1e-10      # north_star: fields within 1e-10 relative L2
 
 
+@pytest.mark.parametrize('mus', [[0.05, 0.3, 1.0, 4.0, 25.0, 150.0, 600.0, 0.7], [2.0], [0.1, 10.0, 1.0],
+                                 [0.2, 0.4, 0.8, 1.6, 3.2], [5.0, 5.0, 0.0, 40.0, 7.0, 9.0, 11.0]])
+def test_batched_robin_sweep_matches_lu(ctx, small, mus):
+    """sfem_krylov_cg_batch (the mu sweep of one geometry in one Krylov loop, no_advection_analysis_A.py:
+    1306-1347): every column against the oracle's sparse LU of its own A(mu) -- batch sizes 1 .. 8 including the
+    non-power-of-two block shapes, coefficients over four decades behind ONE multigrid hierarchy, a repeated and a zero
+    coefficient."""
+    from oracle import cpu_oracle as co
+    from sulcusfem.device import ScalarProblem
+    mesh, mk, om = small
+    bm = mk['bc_markers'].values
+    prob = ScalarProblem(mesh, bm, ctx=ctx)
+    nb = len(mus)
+    Xd, infos = prob.solve_batch(1.0, mus, {1: 1.0, 2: 0.0}, rtol=1e-13)
+    X = Xd.cpu().numpy().reshape(-1, nb)
+    print('cg_batch', nb, [(i['iterations'], i['relres']) for i in infos])
+    for c, mu in enumerate(mus):
+        ref, _, _ = co.solve_concentration(om, bm, 1.0, mu=mu)
+        assert infos[c]['converged'], infos[c]
+        assert infos[c]['iterations'] < (80 if max(mus) <= 64 * min(m for m in mus if m > 0) else 400), infos[c]
+        assert _rel(X[:, c], ref) < 1e-10, (mu, _rel(X[:, c], ref))
+        assert np.array_equal(prob.batch_column(Xd, nb, c).cpu().numpy(), X[:, c])
+    # the same problem object still serves single solves (the batch leaves a fully assembled hierarchy behind)
+    prob.assemble(1.0, mu_const=mus[0], bc_values={1: 1.0, 2: 0.0})
+    c1 = prob.solve('cg', rtol=1e-13).cpu().numpy()
+    assert _rel(c1, X[:, 0]) < 1e-10
+    # run-to-run reproducibility of the batched path (fixed summation orders)
+    Xd2, _ = prob.solve_batch(1.0, mus, {1: 1.0, 2: 0.0}, rtol=1e-13)
+    assert np.array_equal(Xd2.cpu().numpy().reshape(-1, nb), X)
+
+
+def test_batched_sweep_through_the_solver_entry_points(ctx, small):
+    """pure_diffusion_solver_batch / presolve_pure_diffusion: Functions equal to the per-case pure_diffusion_solver
+    (reference solvers.py:113-174) to solver tolerance, parked fields are handed out exactly once."""
+    from sulcusfem import solvers
+    from sulcusfem.fem import Constant, FunctionSpace
+    mesh, mk, om = small
+    mr = {'mesh': mesh}
+    mr.update(mk)
+    C = FunctionSpace(mesh, "CG", 2)
+    mus = [30.0, 0.1, 1.0, 3.0, 0.3, 10.0, 100.0, 0.03, 300.0, 2.0]          # 10 coefficients: two batches
+    single = [solvers.pure_diffusion_solver(mr, C, Constant(0.7), Constant(mu)) for mu in mus]
+    batch = solvers.pure_diffusion_solver_batch(mr, C, Constant(0.7), mus)
+    for f1, fb, mu in zip(single, batch, mus):
+        assert _rel(fb.values, f1.values) < 1e-10, mu
+        assert fb.solver_info['method'] == 'cg_batch' and fb.solver_info['converged']
+        assert np.array_equal(fb.device_components()[0].cpu().numpy(), fb.values)
+    assert solvers.presolve_pure_diffusion(mr, C, Constant(0.7), mus[:3]) == 3
+    f = solvers.pure_diffusion_solver(mr, C, Constant(0.7), Constant(mus[1]))
+    assert f.solver_info['method'] == 'cg_batch' and _rel(f.values, single[1].values) < 1e-10
+    f = solvers.pure_diffusion_solver(mr, C, Constant(0.7), Constant(mus[1]))          # parked field already taken
+    assert f.solver_info['method'] == 'cg'
+
+
 def test_advdiff_solve_matches_lu(ctx, small, engine):
     import torch
     from oracle import cpu_oracle as co

@@ -207,12 +207,15 @@ def test_mu_sweep_with_frozen_coarse_levels_and_concurrent_streams():
     from sulcusfem import studies, solvers, simulation
     from sulcusfem.parameters import Parameters
     regimes = {'small_uptake': [0.1, 0.25, 0.5, 1.0, 2.0, 3.0], 'high_uptake': [50.0, 100.0, 150.0]}
-    plain = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, frozen_coarse=False)
-    frozen = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, frozen_coarse=True)
-    conc = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, frozen_coarse=True, streams=3)
-    assert list(plain['Config']) == list(frozen['Config']) == list(conc['Config'])
+    plain = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, frozen_coarse=False, batch=False)
+    frozen = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, frozen_coarse=True, batch=False)
+    conc = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, frozen_coarse=True, streams=3, batch=False)
+    # batched Krylov loops (the default): 9 coefficients = one batch of 8 + one of 1; serial and with 3 cases in flight
+    batched = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H)
+    batched_conc = studies.run_mu_sweep(None, regimes=regimes, mesh_size_dim=H, streams=3)
+    assert list(plain['Config']) == list(frozen['Config']) == list(conc['Config']) == list(batched['Config'])
     for col in ('Mu_Eff_Simulation', 'Mu_Eff_Opening', 'Total_Mass', 'Mouth_Flux_Total'):
-        for other in (frozen, conc):
+        for other in (frozen, conc, batched, batched_conc):
             assert np.allclose(other[col], plain[col], rtol=1e-9, atol=1e-13), col
     # iteration counts behind frozen levels: solve mu = 3 with levels built for mu = 1 (ratio 3 < 4) and compare
     p = Parameters(mode='no-adv', mesh_size_dim=H)

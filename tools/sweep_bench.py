@@ -60,18 +60,40 @@ def main():
     # a longer sweep (100 mu values) so that thread start-up does not dominate; 3 repetitions per stream count (worker
     # threads share the GIL: the concurrent numbers scatter from run to run -- median and best are reported)
     many = {'dense': [float(v) for v in __import__('numpy').geomspace(0.1, 150.0, 100)]}
-    out['mu_sweep_100'] = {}
-    for k in [1] + [int(v) for v in str(args.streams).split(',') if v.strip() and int(v) > 1]:
-        studies.run_mu_sweep(None, regimes={'dense': many['dense'][:max(k, 2)]}, mesh_size_dim=args.h, streams=k)
-        ts = []
-        for _ in range(3):
-            dfm, tm = timed(lambda: studies.run_mu_sweep(None, regimes=many, mesh_size_dim=args.h, streams=k))
-            ts.append(tm)
-        ts.sort()
-        out['mu_sweep_100'][str(k)] = {'wall_s_median': ts[1], 'solves_per_s_median': len(dfm) / ts[1],
-                                       'solves_per_s_best': len(dfm) / ts[0], 'solves_per_s_worst': len(dfm) / ts[2]}
-    dfp, tp = timed(lambda: studies.run_mu_sweep(None, regimes=many, mesh_size_dim=args.h, streams=1, frozen_coarse=False))
-    out['mu_sweep_100']['1_full_reassembly_every_case'] = {'solves_per_s': len(dfp) / tp}
+    # batched = the default (up to 8 mu per Krylov loop, sfem_krylov_cg_batch); per_case = one CG solve per mu
+    ref_rows = None
+    for mode, batch in (('mu_sweep_100', True), ('mu_sweep_100_per_case', False)):
+        out[mode] = {}
+        for k in [1] + [int(v) for v in str(args.streams).split(',') if v.strip() and int(v) > 1]:
+            studies.run_mu_sweep(None, regimes={'dense': many['dense'][:max(k, 2)]}, mesh_size_dim=args.h, streams=k, batch=batch)
+            ts = []
+            for _ in range(3):
+                dfm, tm = timed(lambda: studies.run_mu_sweep(None, regimes=many, mesh_size_dim=args.h, streams=k, batch=batch))
+                ts.append(tm)
+            ts.sort()
+            out[mode][str(k)] = {'wall_s_median': ts[1], 'solves_per_s_median': len(dfm) / ts[1],
+                                 'solves_per_s_best': len(dfm) / ts[0], 'solves_per_s_worst': len(dfm) / ts[2]}
+            if ref_rows is None:
+                ref_rows = dfm
+            out[mode][str(k)]['rows_match_first_run'] = bool(
+                (abs(dfm['Mu_Eff_Simulation'] - ref_rows['Mu_Eff_Simulation']) <= 1e-9 * abs(ref_rows['Mu_Eff_Simulation'])).all())
+    dfp, tp = timed(lambda: studies.run_mu_sweep(None, regimes=many, mesh_size_dim=args.h, streams=1, frozen_coarse=False, batch=False))
+    out['mu_sweep_100_per_case']['1_full_reassembly_every_case'] = {'solves_per_s': len(dfp) / tp}
+    # the batched solves alone (device time of the Krylov loops, no per-case post-processing): 100 mu = 13 batches
+    from sulcusfem import solvers
+    from sulcusfem.fem import FunctionSpace
+    p0 = studies.Parameters(mode='no-adv', mesh_size_dim=args.h)
+    p0.sulci_w_dim = p0.sulci_h_dim = 0.25
+    p0.validate()
+    p0.nondim()
+    with contextlib.redirect_stdout(io.StringIO()):
+        mr = simulation._simulation_generate_mesh(p0, 'sulcus')
+        Cs = FunctionSpace(mr['mesh'], "CG", 2)
+        mus100 = [p0.mu * f for f in many['dense']]
+        solvers.pure_diffusion_solver_batch(mr, Cs, p0.D, mus100[:8])
+        fs, tb = timed(lambda: solvers.pure_diffusion_solver_batch(mr, Cs, p0.D, mus100))
+    out['batched_solver_only'] = {'solves': len(fs), 'wall_s': tb, 'solves_per_s': len(fs) / tb,
+                                  'iterations': sorted({f.solver_info['iterations'] for f in fs})}
     df2, t2 = timed(lambda: studies.run_advdiff_step_validation(None, mesh_size_dim=args.h))
     df2, t2w = timed(lambda: studies.run_advdiff_step_validation(None, mesh_size_dim=args.h))
     out['advdiff_validation'] = {'solves': len(df2), 'wall_s_first': t2, 'wall_s_cached_geometry': t2w,
