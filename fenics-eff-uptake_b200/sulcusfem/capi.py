@@ -79,7 +79,8 @@ SIGNATURES = {
     'sfem_mg_destroy': (None, [_p]),
     'sfem_krylov_cg': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _d, _i, C.POINTER(_d), _p]),
     'sfem_krylov_fgmres': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _d, _i, _i, C.POINTER(_d), _p]),
-    'sfem_krylov_cg_batch': (_i, [_i, _i, _p, _p, _p, _p, _i, C.POINTER(_d), _p, _p, _p, _p, _p, _d, _i, C.POINTER(_d), _p]),
+    'sfem_krylov_cg_batch': (_i, [_i, _i, _p, _p, _i, C.POINTER(_p), C.POINTER(_p), _i, C.POINTER(_d), _d, _p, _p, _p, _p, _p,
+                                  _d, _i, C.POINTER(_d), _p]),
     'sfem_batch_column': (_i, [_i, _i, _i, _p, _p, _p]),
     'sfem_stokes_create': (_p, [_i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p,
                                 _i, _p, _p, _p, _p, _p, _p]),

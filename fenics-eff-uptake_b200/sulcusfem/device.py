@@ -444,13 +444,14 @@ class ScalarProblem:
 
 
     # ------------------------------------------------------------------ batched Robin sweep (sfem_krylov_cg_batch)
-    BATCH_MAX = 8
+    BATCH_MAX = 16
 
     def batch_operators(self, D: float, bc_values: Dict[int, float]):
-        """The two value arrays of A(mu) = A0 + mu M on the system level's pattern -- A0 = D K with identity Dirichlet
-        rows, M = the Robin boundary mass matrix with ZERO Dirichlet rows / columns -- and the lifted right-hand sides
-        b0, bM (b(mu) = b0 + mu bM).  Built with the same element / facet / gather / Dirichlet kernels as a single
-        assembly, once per (D, Dirichlet constants); a sweep then needs no per-mu assembly at all."""
+        """The two value arrays of A_l(mu) = A0_l + mu M_l on the pattern of EVERY level -- A0_l = D K_l with identity
+        Dirichlet rows, M_l = the Robin boundary mass matrix with ZERO Dirichlet rows / columns -- and, for the system
+        level, the lifted right-hand sides b0, bM (b(mu) = b0 + mu bM).  Built with the same element / facet / gather /
+        Dirichlet kernels as a single assembly, once per (D, Dirichlet constants); a sweep then needs no per-mu
+        assembly of the operators at all."""
         key = (float(D), tuple((int(i), float(v)) for i, v in bc_values.items()))
         ops = getattr(self, '_batch_ops', None)
         if ops is not None and ops['key'] == key:
@@ -459,47 +460,66 @@ class ScalarProblem:
         if not f.nf:
             raise capi.SulcusFemError("batched Robin sweep: the problem has no Robin boundary")
         f.set_bc_values(bc_values)
-        zeros = ctx.zeros(f.n)
-        # A0 = D K: element kernel, facet family zeroed, symmetric elimination with lifting into b0
-        f.assemble(float(D), None, None, 0.0, None, False, robin=False)
-        b0 = ctx.zeros(f.n)
-        f.apply_bc(1, rhs=b0)
-        vals0 = f.A.vals_buf.clone()
-        # M = M_Gamma: element kernel with D = 0 (zeros), facet kernel with mu = 1; bM = -M g, then rows and columns of
-        # the Dirichlet dofs are zeroed (their rows of A0 + mu M stay identity rows, their entries of b stay g)
-        f.assemble(0.0, None, None, 1.0, None, False, robin=True)
-        bM = ctx.zeros(f.n)
-        f.A.spmv(f.bc_val, y=bM, b=zeros, mode=1)
-        capi.check(lib.sfem_csr_zero_flagged(f.n, P(f.A.rowptr), P(f.A.cols), P(f.A.vals), P(f.bc_flag), P(f.bc_flag),
-                                             ctx.stream), 'sfem_csr_zero_flagged')
-        capi.check(lib.sfem_vec_select(f.n, P(f.bc_flag), P(zeros), P(bM), P(bM), ctx.stream), 'sfem_vec_select')
-        valsM = f.A.vals_buf.clone()
-        f.A.mark_dirty()
-        self._coarse_key = None                  # the system level no longer holds an assembled A(mu)
-        self._batch_ops = dict(key=key, vals0=vals0, valsM=valsM, b0=b0, bM=bM)
+        vals0, valsM = [], []
+        b0 = bM = None
+        for l, lev in enumerate(self.levels):
+            # A0_l = D K_l: element kernel, facet family zeroed, symmetric elimination (level 0: lifting into b0)
+            lev.assemble(float(D), None, None, 0.0, None, False, robin=False)
+            rhs0 = ctx.zeros(lev.n)
+            lev.apply_bc(1, rhs=rhs0)
+            vals0.append(lev.A.vals_buf.clone())
+            # M_l: element kernel with D = 0 (zeros), facet kernel with mu = 1; level 0: bM = -M g; then the rows and
+            # columns of the Dirichlet dofs are zeroed (their rows of A0 + mu M stay identity rows, b stays g there)
+            lev.assemble(0.0, None, None, 1.0, None, False, robin=True)
+            if l == 0:
+                zeros = ctx.zeros(lev.n)
+                bM = ctx.zeros(lev.n)
+                lev.A.spmv(lev.bc_val, y=bM, b=zeros, mode=1)
+                capi.check(lib.sfem_vec_select(lev.n, P(lev.bc_flag), P(zeros), P(bM), P(bM), ctx.stream), 'sfem_vec_select')
+                b0 = rhs0
+            capi.check(lib.sfem_csr_zero_flagged(lev.n, P(lev.A.rowptr), P(lev.A.cols), P(lev.A.vals), P(lev.bc_flag),
+                                                 P(lev.bc_flag), ctx.stream), 'sfem_csr_zero_flagged')
+            valsM.append(lev.A.vals_buf.clone())
+            lev.A.mark_dirty()
+        self._coarse_key = None                  # no level holds an assembled A(mu) any more
+        nl = len(self.levels)
+        PtrArr = C.c_void_p * nl
+        self._batch_ops = dict(key=key, vals0=vals0, valsM=valsM, b0=b0, bM=bM,
+                               p0=PtrArr(*[t.data_ptr() for t in vals0]), pM=PtrArr(*[t.data_ptr() for t in valsM]))
         return self._batch_ops
 
     def solve_batch(self, D: float, mus: Sequence[float], bc_values: Dict[int, float], rtol=1e-13, maxit=400,
-                    mu_ref: Optional[float] = None):
+                    mu_ref: Optional[float] = None, shared_coarse=False):
         """Solve the pure-diffusion Robin problem for every mu of ``mus`` (at most ``BATCH_MAX``) in one batched PCG.
-        The multigrid hierarchy is assembled for ``mu_ref`` (default: geometric mean of the positive mus).  Returns
-        (X, infos): X the interleaved solutions [n][nb] on the device, infos one ``last_info`` dictionary per mu."""
+        The multigrid hierarchy is assembled for ``mu_ref`` (default: geometric mean of the positive mus): it supplies
+        the structure and the dense inverse of the coarsest level; every column smooths with its own operator on
+        every level (``shared_coarse=True``: only on the system level, the coarse levels of ``mu_ref`` serve all
+        columns -- the first version, kept for comparison).  Returns (X, infos): X the interleaved solutions [n][nb] on
+        the device, infos one ``last_info`` dictionary per mu."""
         ctx, f = self.ctx, self.fine
         mus = [float(m) for m in mus]
         nb = len(mus)
         if not 1 <= nb <= self.BATCH_MAX:
             raise ValueError(f"solve_batch takes 1..{self.BATCH_MAX} coefficients")
+        if min(mus) < 0.0:
+            raise ValueError("solve_batch: Robin coefficients must be >= 0")
         ops = self.batch_operators(D, bc_values)
         if mu_ref is None:
             pos = [m for m in mus if m > 0.0]
             mu_ref = float(np.exp(np.mean(np.log(pos)))) if pos else 0.0
-        self.assemble(float(D), mu_const=float(mu_ref), bc_values=bc_values)      # preconditioner: hierarchy of A(mu_ref)
+        self.assemble(float(D), mu_const=float(mu_ref), bc_values=bc_values)      # hierarchy of A(mu_ref)
         capi.check(ctx.lib.sfem_vec_select(f.n, P(f.bc_flag), P(f.bc_val), None, P(self.x), ctx.stream), 'sfem_vec_select')
         X = ctx.empty(f.n * nb)
         info = (C.c_double * (4 * nb))()
         h_mu = (C.c_double * nb)(*mus)
         A = f.A
-        rc = ctx.lib.sfem_krylov_cg_batch(f.n, A.nnz, P(A.rowptr), P(A.cols), P(ops['vals0']), P(ops['valsM']), nb, h_mu,
+        nl = len(self.levels)
+        p0, pM = ops['p0'], ops['pM']
+        if shared_coarse:
+            PtrArr = C.c_void_p * nl
+            p0 = PtrArr(*([ops['vals0'][0].data_ptr()] + [None] * (nl - 1)))
+            pM = PtrArr(*([ops['valsM'][0].data_ptr()] + [None] * (nl - 1)))
+        rc = ctx.lib.sfem_krylov_cg_batch(f.n, A.nnz, P(A.rowptr), P(A.cols), nl, p0, pM, nb, h_mu, float(mu_ref),
                                           self.mg.handle, P(ops['b0']), P(ops['bM']), P(self.x), P(X), float(rtol),
                                           int(maxit), info, ctx.stream)
         capi.check(rc, 'sfem_krylov_cg_batch')

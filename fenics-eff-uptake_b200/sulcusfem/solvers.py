@@ -264,7 +264,7 @@ def pure_diffusion_solver(mesh_results, C, D, mu, mesh_type="sulcus"):
 # 3 mu per geometry) call pure_diffusion_solver once per mu.  A(mu) = D K + mu M_Gamma differs between the cases in its
 # boundary rows only, so up to BATCH coefficients are solved in ONE Krylov loop (sfem_krylov_cg_batch: interleaved
 # right-hand sides, per-column CG scalars, one shared multigrid hierarchy assembled for the batch's geometric-mean mu).
-BATCH = 8
+BATCH = int(__import__('os').environ.get('SFEM_BATCH', 8))      # coefficients per Krylov loop (library limit: 16)
 BATCH_SPAN = 64.0         # largest mu / smallest mu inside one batch (the hierarchy is assembled for their geometric mean)
 
 

@@ -216,18 +216,25 @@ int sfem_krylov_fgmres(int n, int nnz, const int* rowptr, const int* cols, const
                        const double* b, double* x, double rtol, int restart, int maxit,
                        double* h_info, void* stream);
 /* Batched multi-parameter PCG: the Robin-coefficient sweep of ONE geometry in one Krylov loop.
- * Solves (A0 + mu_c M) x_c = b0 + mu_c bM for c = 0..nb-1 (1 <= nb <= 8); vals0 / valsM are two value arrays on the
- * SAME CSR pattern (A0 = D K and M = M_Gamma, both with the Dirichlet rows / columns eliminated: identity rows in A0,
- * zero rows in M; b0 / bM the lifted right-hand sides), h_mu[nb] lives on the host, x0[n] is the shared initial guess
- * (the Dirichlet values) and X[n][nb] receives the solutions interleaved by column.  `mg` is an nb = 1 handle set up
- * for one reference mu inside the batch's range: it preconditions every column (preconditioner data only -- each
- * column iterates on its exact operator until ALL columns reach ||b_c - A_c x_c|| <= rtol ||b_c||).
+ * Solves (A0 + mu_c M) x_c = b0 + mu_c bM for c = 0..nb-1 (1 <= nb <= 16) with vectors interleaved by column.
+ *   rowptr / cols      CSR pattern of the system level (n rows, nnz entries)
+ *   lvl_vals0 / lvl_valsM   host arrays [nlevels] of device pointers: two value arrays per multigrid level on that
+ *                      level's pattern -- A0_l = D K_l and M_l = M_Gamma,l, Dirichlet rows / columns eliminated
+ *                      (identity rows in A0_l, zero rows in M_l); entry 0 is the system level (required); a NULL
+ *                      entry l >= 1 makes that level use the handle's operator (assembled for mu_ref) for all columns
+ *   h_mu[nb] (host), mu_ref   the coefficients (>= 0) and the coefficient the handle was assembled for
+ *   mg                 nb = 1 handle with `nlevels` levels, set up for mu_ref: supplies patterns, transfers and the dense
+ *                      inverse of the coarsest A(mu_ref); every column's smoothers run on its OWN operator on every
+ *                      level, its coarsest system is solved by a Chebyshev iteration preconditioned with that inverse
+ *   b0 / bM            lifted right-hand sides (b_c = b0 + mu_c bM), x0[n] the shared initial guess (Dirichlet values)
+ *   X[n][nb]           solutions; every column iterates until ALL reach ||b_c - A_c x_c|| <= rtol ||b_c||
  * h_info[4 * nb]: per column {iterations, true relative residual, converged(1/0), recurrence estimate}.
  * replaces: the serial loop of sparse LU solves  no_advection_analysis_A.py:1306-1347 (run_mu_sweep: 20 mu values on
  * one mesh), no_advection_analysis_B.py:86-200 (mu x geometry), each a pure_diffusion_solver call  solvers.py:113-174 */
-int sfem_krylov_cg_batch(int n, int nnz, const int* rowptr, const int* cols, const double* vals0, const double* valsM,
-                         int nb, const double* h_mu, sfem_mg_t mg, const double* b0, const double* bM, const double* x0,
-                         double* X, double rtol, int maxit, double* h_info, void* stream);
+int sfem_krylov_cg_batch(int n, int nnz, const int* rowptr, const int* cols, int nlevels, const double* const* lvl_vals0,
+                         const double* const* lvl_valsM, int nb, const double* h_mu, double mu_ref, sfem_mg_t mg,
+                         const double* b0, const double* bM, const double* x0, double* X, double rtol, int maxit,
+                         double* h_info, void* stream);
 /* out[i] = X[i][c]: one column of an interleaved batch (the field handed back as a dolfin-style Function) */
 int sfem_batch_column(int n, int nb, int c, const double* X, double* out, void* stream);
 /* Taylor-Hood Stokes solver: preconditioned MINRES on the block form of the assembled matrix.

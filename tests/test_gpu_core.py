@@ -325,10 +325,11 @@ def test_diffusion_solve_matches_lu(ctx, small, engine):
 
 
 @pytest.mark.parametrize('mus', [[0.05, 0.3, 1.0, 4.0, 25.0, 150.0, 600.0, 0.7], [2.0], [0.1, 10.0, 1.0],
-                                 [0.2, 0.4, 0.8, 1.6, 3.2], [5.0, 5.0, 0.0, 40.0, 7.0, 9.0, 11.0]])
+                                 [0.2, 0.4, 0.8, 1.6, 3.2], [5.0, 5.0, 0.0, 40.0, 7.0, 9.0, 11.0],
+                                 [0.3 * 1.25 ** k for k in range(16)]])
 def test_batched_robin_sweep_matches_lu(ctx, small, mus):
     """sfem_krylov_cg_batch (the mu sweep of one geometry in one Krylov loop, no_advection_analysis_A.py:
-    1306-1347): every column against the oracle's sparse LU of its own A(mu) -- batch sizes 1 .. 8 including the
+    1306-1347): every column against the oracle's sparse LU of its own A(mu) -- batch sizes 1 .. 16 including the
     non-power-of-two block shapes, coefficients over four decades behind ONE multigrid hierarchy, a repeated and a zero
     coefficient."""
     from oracle import cpu_oracle as co
@@ -343,13 +344,17 @@ def test_batched_robin_sweep_matches_lu(ctx, small, mus):
     for c, mu in enumerate(mus):
         ref, _, _ = co.solve_concentration(om, bm, 1.0, mu=mu)
         assert infos[c]['converged'], infos[c]
-        assert infos[c]['iterations'] < (80 if max(mus) <= 64 * min(m for m in mus if m > 0) else 400), infos[c]
+        assert infos[c]['iterations'] < 80, infos[c]
         assert _rel(X[:, c], ref) < 1e-10, (mu, _rel(X[:, c], ref))
         assert np.array_equal(prob.batch_column(Xd, nb, c).cpu().numpy(), X[:, c])
     # the same problem object still serves single solves (the batch leaves a fully assembled hierarchy behind)
     prob.assemble(1.0, mu_const=mus[0], bc_values={1: 1.0, 2: 0.0})
     c1 = prob.solve('cg', rtol=1e-13).cpu().numpy()
     assert _rel(c1, X[:, 0]) < 1e-10
+    if nb == 5:       # sharing the reference coefficient's coarse levels between the columns converges to the same fields
+        Xs, infos_s = prob.solve_batch(1.0, mus, {1: 1.0, 2: 0.0}, rtol=1e-13, shared_coarse=True)
+        assert all(i['converged'] for i in infos_s) and infos_s[0]['iterations'] >= infos[0]['iterations']
+        assert _rel(Xs.cpu().numpy().reshape(-1, nb), X) < 1e-10
     # run-to-run reproducibility of the batched path (fixed summation orders)
     Xd2, _ = prob.solve_batch(1.0, mus, {1: 1.0, 2: 0.0}, rtol=1e-13)
     assert np.array_equal(Xd2.cpu().numpy().reshape(-1, nb), X)

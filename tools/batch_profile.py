@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, 'fenics-eff-uptake_b200'))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--h', type=float, default=0.02)
-    ap.add_argument('--nbs', default='1,2,4,8')
+    ap.add_argument('--nbs', default='1,2,4,8,16')
     ap.add_argument('--reps', type=int, default=7)
     ap.add_argument('--ncu', action='store_true')
     args = ap.parse_args()
@@ -60,6 +60,12 @@ def main():
         ms = ts[len(ts) // 2]
         out['batches'][str(nb)] = {'ms_per_batch': ms, 'ms_per_solve': ms / nb, 'iterations': its,
                                    'ms_per_iteration_upper_bound': ms / max(its + 1, 1)}
+        if nb > 1:                                                # first version: coarse levels of mu_ref for all columns
+            _, infos = prob.solve_batch(p0.D, mus, bcv, shared_coarse=True)
+            out['batches'][str(nb)]['iterations_shared_coarse_levels'] = infos[0]['iterations']
+            wide = [p0.mu * f for f in np.geomspace(0.1, 6.4, nb)]    # a batch at the span limit of solvers.BATCH_SPAN
+            _, infos = prob.solve_batch(p0.D, wide, bcv)
+            out['batches'][str(nb)]['iterations_span_64'] = infos[0]['iterations']
     # the single-solve path on the same problem for comparison
     prob.assemble(p0.D, mu_const=p0.mu, bc_values=bcv)
     prob.solve('cg', rtol=1e-13)
