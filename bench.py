@@ -185,6 +185,7 @@ class Case:
         X = dm.p2_dof_coordinates(self.mesh)
         d1 = dm.dirichlet_dofs_p2(self.mesh, self.bm, 1)
         self.stokes.set_bcs({1: (4.0 * X[d1, 1] * (H_CH - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+        self.stokes.set_channel_flow_guess(L_CH, H_CH)       # what solvers.stokes_solver does: analytic channel flow as x0
         self.stokes._inflow_H = float(H_CH)
         torch.cuda.synchronize()
         t5 = time.perf_counter()
@@ -290,6 +291,70 @@ def same_mesh_leg(ctx, h, flush_l2, reps=5):
            "note": "GPU = this repo's API path (host in / host out) and device-resident step; CPU = oracle port "
                    "(numpy assembly + SuperLU + one extended-precision refinement), 1 thread; same mesh, same parameters"}
     del case
+    return rec
+
+
+def sweep_leg(with_oracle, h=0.02):
+    """BASELINE configs[3] / SURVEY 8(e) on the driver's clock: the reference's Phase A mu sweep
+    (no_advection_analysis_A.py:1257-1347: 20 Robin coefficients on the 0.25 x 0.25 mm sulcus, mesh size 0.02) through
+    ``studies.run_mu_sweep`` -- batched Krylov loops (sfem_krylov_cg_batch, the default) against one CG solve per
+    coefficient, wall clock around the driver call on a cached geometry, rows compared; with the CPU legs enabled two
+    coefficients are also solved by the oracle's sparse LU on the same mesh (field parity bar 1e-10, and the CPU time
+    per solve the reference's serial loop would need)."""
+    import contextlib
+    import io
+    import torch
+    from sulcusfem import simulation, solvers, studies
+    from sulcusfem.fem import FunctionSpace
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        return r, time.perf_counter() - t
+    many = {'dense': [float(v) for v in np.geomspace(0.1, 150.0, 100)]}
+    df0, t_first = timed(lambda: studies.run_mu_sweep(None, mesh_size_dim=h))
+    rec = {"h": h, "cases_reference_sweep": len(df0), "wall_s_first_call_with_geometry_build": t_first}
+    for name, kw in (("batched", dict(batch=True)), ("per_case", dict(batch=False))):
+        studies.run_mu_sweep(None, mesh_size_dim=h, **kw)
+        ts20, ts100 = [], []
+        for _ in range(3):
+            df20, t = timed(lambda: studies.run_mu_sweep(None, mesh_size_dim=h, **kw))
+            ts20.append(t)
+            df100, t = timed(lambda: studies.run_mu_sweep(None, regimes=many, mesh_size_dim=h, **kw))
+            ts100.append(t)
+        rec[name] = {"solves_per_s_20_cases": len(df20) / float(np.median(ts20)),
+                     "solves_per_s_100_cases": len(df100) / float(np.median(ts100))}
+        rec[name + "_rows"] = df20
+    a, b = rec.pop("batched_rows"), rec.pop("per_case_rows")
+    cols = ('Mu_Eff_Simulation', 'Mu_Eff_Opening', 'Total_Mass', 'Mouth_Flux_Total')
+    rec["rows_batched_vs_per_case_max_rel"] = float(max(np.max(np.abs(a[c] - b[c]) / np.abs(b[c])) for c in cols))
+    rec["speedup_batched_over_per_case_100_cases"] = rec["batched"]["solves_per_s_100_cases"] / rec["per_case"]["solves_per_s_100_cases"]
+    ok = rec["rows_batched_vs_per_case_max_rel"] <= 1e-9
+    if with_oracle:
+        from oracle import cpu_oracle as co
+        p = studies.Parameters(mode='no-adv', mesh_size_dim=h)
+        p.sulci_w_dim = p.sulci_h_dim = 0.25
+        p.validate()
+        p.nondim()
+        with contextlib.redirect_stdout(io.StringIO()):
+            mr = simulation._simulation_generate_mesh(p, 'sulcus')
+            mus = [p.mu * f for f in (0.1, 1.0, 12.5, 150.0)]
+            fs = solvers.pure_diffusion_solver_batch(mr, FunctionSpace(mr['mesh'], "CG", 2), p.D, mus)
+        om = co.Mesh(mr['mesh'].coords, mr['mesh'].cells)
+        errs, cpu_s = [], []
+        for k in (1, 3):
+            t0 = time.perf_counter()
+            ref, _, _ = co.solve_concentration(om, mr['bc_markers'].values, p.D, mu=mus[k])
+            cpu_s.append(time.perf_counter() - t0)
+            errs.append(_rel(fs[k].values, ref))
+        rec["parity_vs_oracle_lu"] = {"mu_factors": [1.0, 150.0], "rel_l2_c": errs, "bar": 1e-10, "p2_dofs": int(om.n_p2),
+                                      "batch_iterations": fs[0].solver_info['iterations']}
+        rec["cpu_oracle_s_per_solve"] = float(np.mean(cpu_s))
+        rec["ratio_batched_over_cpu_oracle"] = rec["batched"]["solves_per_s_100_cases"] * rec["cpu_oracle_s_per_solve"]
+        ok = ok and max(errs) <= 1e-10
+    rec["ok"] = bool(ok)
     return rec
 
 
@@ -598,6 +663,11 @@ def run_gpu(args, rank, world):
                          f"same mesh: same_mesh[0]",
                "host_cores": os.cpu_count()}
 
+    # ---- BASELINE configs[3]: the reference's mu sweep (batched Krylov loops), N = 1 only
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = sweep_leg(with_oracle=not args.no_cpu)
+
     value = world * ndof * args.steps / (ms_total / 1e3)
     line = {
         "metric": "fem_dofs_per_s", "value": value, "unit": "DOFs/s", "n_gpus": world, "steps": args.steps,
@@ -612,7 +682,7 @@ def run_gpu(args, rank, world):
                 "api": "sulcusfem.solvers.stokes_solver + advdiff_solver + analysis.compute_*_metrics"},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "setup_s": t_setup, "setup_breakdown_s": case.setup,
-        "same_mesh": same, "dd_strong": dd,
+        "same_mesh": same, "dd_strong": dd, "mu_sweep": sweep,
         "functionals": {"uptake_flux": fm['uptake_flux'], "total_mass": mm['total_mass']},
     }
     line["config"]["dofs"] = ndof
@@ -620,6 +690,9 @@ def run_gpu(args, rank, world):
     bad = [r for r in same if not r["parity"]["ok"]]
     if bad:
         print("PARITY FAILURE in the same-mesh leg: " + json.dumps([r["parity"] for r in bad]), file=sys.stderr)
+        sys.exit(3)
+    if sweep is not None and not sweep["ok"]:
+        print("PARITY FAILURE in the mu-sweep leg: " + json.dumps(sweep), file=sys.stderr)
         sys.exit(3)
 
 
@@ -634,6 +707,7 @@ def main():
     ap.add_argument('--cpu-h', type=float, default=0.03)    # reference arm: ~4-9 s of single-thread CPU work per step (168 k dofs)
     ap.add_argument('--same-h', type=float, default=0.02)   # same-mesh leg / cpu_baseline: the reference's default mesh size (385 k dofs)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-sweep', action='store_true')      # skip the mu-sweep leg (BASELINE configs[3])
     ap.add_argument('--no-dd', action='store_true')         # N > 1: skip the domain-decomposed (config 5) leg
     ap.add_argument('--dd-replicate-below', type=int, default=200000)   # multigrid levels below this many unknowns stay replicated
     # N > 1: the dd leg also runs these refinement levels (the bench mesh, 6.1 M dofs, is too small for 8 GPUs; r = 3 =

@@ -85,6 +85,7 @@ SIGNATURES = {
     'sfem_stokes_create': (_p, [_i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p,
                                 _i, _p, _p, _p, _p, _p, _p]),
     'sfem_stokes_solve': (_i, [_p, _p, _p, _d, _i, C.POINTER(_d), _p]),
+    'sfem_stokes_solve_from': (_i, [_p, _p, _p, _p, _d, _i, C.POINTER(_d), _p]),
     'sfem_stokes_destroy': (None, [_p]),
     'sfem_dist_header_words': (C.c_longlong, [_i, C.c_longlong]),
     'sfem_dist_create': (_p, [_i, _i, C.c_longlong, C.c_longlong]),

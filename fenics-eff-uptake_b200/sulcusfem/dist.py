@@ -695,10 +695,20 @@ class DistStokesProblem:
     def solve(self, rtol=1e-12, maxit=2000):
         ctx, lib = self.ctx, self.ctx.lib
         capi.check(lib.sfem_vec_set(self.n_alloc, 0.0, P(self.x), ctx.stream), 'sfem_vec_set')
-        _gather(ctx, self.n_own, self.own_map, self.stokes.g_il, self.x)       # initial guess: the Dirichlet values
         info = (C.c_double * 4)()
-        capi.check(lib.sfem_stokes_solve(self.handle, P(self.b), P(self.x), float(rtol), int(maxit), info, ctx.stream),
-                   'sfem_stokes_solve (distributed)')
+        x0 = getattr(self.stokes, 'x0_il', None)
+        if x0 is not None:       # same starting vector and anchored stopping level as the single-GPU solve
+            if getattr(self, 'xref', None) is None:
+                self.xref = ctx.zeros(self.n_alloc)
+            capi.check(lib.sfem_vec_set(self.n_alloc, 0.0, P(self.xref), ctx.stream), 'sfem_vec_set')
+            _gather(ctx, self.n_own, self.own_map, self.stokes.g_il, self.xref)
+            _gather(ctx, self.n_own, self.own_map, x0, self.x)
+            capi.check(lib.sfem_stokes_solve_from(self.handle, P(self.b), P(self.x), P(self.xref), float(rtol), int(maxit),
+                                                  info, ctx.stream), 'sfem_stokes_solve_from (distributed)')
+        else:
+            _gather(ctx, self.n_own, self.own_map, self.stokes.g_il, self.x)   # initial guess: the Dirichlet values
+            capi.check(lib.sfem_stokes_solve(self.handle, P(self.b), P(self.x), float(rtol), int(maxit), info, ctx.stream),
+                       'sfem_stokes_solve (distributed)')
         if self.world.error():
             raise capi.SulcusFemError("multi-GPU exchange timed out (a peer did not answer)")
         self.last_info = {'iterations': int(info[0]), 'relres': float(info[1]), 'converged': bool(info[2]),

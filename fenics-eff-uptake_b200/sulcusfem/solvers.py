@@ -264,8 +264,9 @@ def pure_diffusion_solver(mesh_results, C, D, mu, mesh_type="sulcus"):
 # 3 mu per geometry) call pure_diffusion_solver once per mu.  A(mu) = D K + mu M_Gamma differs between the cases in its
 # boundary rows only, so up to BATCH coefficients are solved in ONE Krylov loop (sfem_krylov_cg_batch: interleaved
 # right-hand sides, per-column CG scalars, one shared multigrid hierarchy assembled for the batch's geometric-mean mu).
-BATCH = int(__import__('os').environ.get('SFEM_BATCH', 8))      # coefficients per Krylov loop (library limit: 16)
-BATCH_SPAN = 64.0         # largest mu / smallest mu inside one batch (the hierarchy is assembled for their geometric mean)
+BATCH = int(__import__('os').environ.get('SFEM_BATCH', 16))     # coefficients per Krylov loop (library limit: 16)
+BATCH_SPAN = 64.0         # largest mu / smallest mu inside one batch: bounds the Chebyshev steps of the coarsest-level solve
+                          # (every column runs on its own operators; iteration counts do not depend on the span -- measured)
 
 
 def _presolve_key(D, mu):
@@ -368,6 +369,7 @@ def stokes_solver(mesh_results, W, L_domain, H, mesh_type="sulcus"):
             X = dm.p2_dof_coordinates(mesh)
             d1 = dm.dirichlet_dofs_p2(mesh, bm, 1)
             prob.set_bcs({1: (4.0 * X[d1, 1] * (H - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
+            prob.set_channel_flow_guess(float(L_domain), float(H))
             prob._inflow_H = float(H)
         prob.assemble(bc_mode=1)
         ux, uy, p = prob.solve(rtol=STOKES_RTOL)

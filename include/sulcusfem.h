@@ -273,6 +273,12 @@ sfem_stokes_t sfem_stokes_create_part(int n2, int nv,
                                       const int* zidx, const double* zw, const double* Cc,
                                       int BT_nnz, long long n_alloc, long long nv_alloc);
 int sfem_stokes_solve(sfem_stokes_t h, const double* b, double* x, double rtol, int maxit, double* h_info, void* stream);
+/* Same solve started from a better vector x (e.g. the analytic channel flow of the inlet profile, solvers.py:252-258)
+ * with the stopping level anchored to xref, the plain starting vector (Dirichlet values, zero elsewhere):
+ * stops when the preconditioned residual is <= rtol * gamma(xref) -- exactly the absolute level sfem_stokes_solve
+ * reaches from xref, so the accuracy is unchanged and only iterations are saved.  x and xref in the solver layout. */
+int sfem_stokes_solve_from(sfem_stokes_t h, const double* b, double* x, const double* xref, double rtol, int maxit,
+                           double* h_info, void* stream);
 void sfem_stokes_destroy(sfem_stokes_t h);
 
 /* ------------------------------------------------------------------ multi-GPU (one process per GPU) ---

@@ -344,7 +344,7 @@ def test_batched_robin_sweep_matches_lu(ctx, small, mus):
     for c, mu in enumerate(mus):
         ref, _, _ = co.solve_concentration(om, bm, 1.0, mu=mu)
         assert infos[c]['converged'], infos[c]
-        assert infos[c]['iterations'] < 80, infos[c]
+        assert infos[c]['iterations'] < (40 if max(mus) <= 64 * min(m for m in mus if m > 0) else 400), infos[c]
         assert _rel(X[:, c], ref) < 1e-10, (mu, _rel(X[:, c], ref))
         assert np.array_equal(prob.batch_column(Xd, nb, c).cpu().numpy(), X[:, c])
     # the same problem object still serves single solves (the batch leaves a fully assembled hierarchy behind)
@@ -458,6 +458,18 @@ def test_stokes_solve_matches_lu(ctx, small, engine):
     ctx.lib.sfem_profile_stop(0, None, None, None)
     assert sp_.last_info['iterations'] == it_graph
     assert float((sp_.x - x_graph).abs().max()) == 0.0
+    # analytic channel flow as the starting vector, stopping level anchored to the plain guess (sfem_stokes_solve_from):
+    # same fields against the LU, fewer iterations
+    it_plain = sp_.last_info['iterations']
+    sp_.set_channel_flow_guess(10.0, 1.0)
+    sp_.assemble(bc_mode=1)
+    uxg, uyg, pg = [t.cpu().numpy() for t in sp_.solve(rtol=1e-14)]
+    print('minres from the channel-flow guess', sp_.last_info, 'plain guess:', it_plain)
+    assert sp_.last_info['converged'] and sp_.last_info['iterations'] < it_plain
+    assert np.linalg.norm(np.concatenate([uxg - rx, uyg - ry])) / un < 1e-10
+    assert _rel(pg, rp) < 1e-9
+    sp_.set_bcs({1: (4 * X[d1, 1] * (1 - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})     # drops the guess again
+    assert sp_.x0_il is None
     # without the lubrication coarse correction: same solution, more iterations
     sp0 = StokesProblem(mesh, bm, ctx=ctx, schur_correction=False)
     sp0.set_bcs({1: (4 * X[d1, 1] * (1 - X[d1, 1]), 0.0), 4: (0.0, 0.0), 3: (0.0, 0.0)})
@@ -465,7 +477,7 @@ def test_stokes_solve_matches_lu(ctx, small, engine):
     ux0, uy0, p0 = [t.cpu().numpy() for t in sp0.solve(rtol=1e-14)]
     print('minres (mass-matrix Schur only)', sp0.last_info)
     assert np.linalg.norm(np.concatenate([ux0 - rx, uy0 - ry])) / un < 1e-10
-    assert sp0.last_info['iterations'] > sp_.last_info['iterations']
+    assert sp0.last_info['iterations'] > it_plain
 
 
 def test_functionals_match_oracle(ctx, small):
