@@ -143,10 +143,22 @@ __global__ void __launch_bounds__(kThreads) k_dense_gemv(int n, const double* __
     double acc[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) acc[c] = 0.0;
-    for (int j = lane; j < n; j += 32) {
-      const double mj = m[j];
+    // four matrix entries (and their right-hand-side values) per round: the 18 column steps of a 556-row inverse are
+    // otherwise a chain of dependent L2 round trips (the launch ran 12.6 us, ncu r02)
+    for (int j0 = lane; j0 < n; j0 += 128) {
+      double mj[4], xv[4][NB];
 #pragma unroll
-      for (int c = 0; c < NB; ++c) acc[c] = fma(mj, x[(size_t)j * NB + c], acc[c]);
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 32 * u;
+        const bool ok = j < n;
+        mj[u] = ok ? m[j] : 0.0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) xv[u][c] = ok ? x[(size_t)j * NB + c] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[c] = fma(mj[u], xv[u][c], acc[c]);
     }
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
