@@ -5,7 +5,7 @@ set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="$here/../sulcusfem/libsulcusfem.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-srcs=(sfem_vector.cu sfem_spmv.cu sfem_spmv_staged.cu sfem_spmv_sell.cu sfem_assembly.cu sfem_mg.cu sfem_krylov.cu sfem_batch.cu sfem_stokes.cu
+srcs=(sfem_vector.cu sfem_spmv.cu sfem_spmv_staged.cu sfem_spmv_sell.cu sfem_assembly.cu sfem_mg.cu sfem_mg_tail.cu sfem_krylov.cu sfem_batch.cu sfem_stokes.cu
       sfem_functionals.cu sfem_points.cu sfem_api.cu sfem_dist.cu)
 flags=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC ${SFEM_PTXAS_V:+-Xptxas -v})
 cd "$here"

@@ -155,6 +155,7 @@ int smooth(const Csr& A, const double* dinv, const double* coef, int degree, con
 }
 
 int mg_vcycle_level(sfem_mg* mg, int l, const double* b, double* x, cudaStream_t st) {
+  if (l == mg_tail_start(mg)) return mg_tail_vcycle(mg, l, b, x, st);      // small levels: one fused launch (sfem_mg_tail.cu)
   MgLevel& L = mg->levels[l];
   const int last = (int)mg->levels.size() - 1;
   const int nb = mg->nb;

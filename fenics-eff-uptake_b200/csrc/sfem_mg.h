@@ -52,4 +52,7 @@ int smooth(const Csr& A, const double* dinv, const double* coef, int degree, con
 int cheb_setup(const Csr* A, const double* dinv, double fixed_lmax, double ratio, int degree, double* scratch,
                double* coef, cudaStream_t st, bool distributed = false);
 int mg_vcycle_level(sfem_mg* mg, int l, const double* b, double* x, cudaStream_t st);
+// sfem_mg_tail.cu: the levels l >= mg_tail_start(mg) (-1: none) run as one fused cluster kernel
+int mg_tail_start(const sfem_mg* mg);
+int mg_tail_vcycle(sfem_mg* mg, int l, const double* b, double* x, cudaStream_t st);
 }  // namespace sfem

@@ -75,6 +75,7 @@ SIGNATURES = {
     'sfem_mg_setup_fine': (_i, [_p, _p]),
     'sfem_mg_vcycle': (_i, [_p, _p, _p, _p]),
     'sfem_mg_set_tail': (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
+    'sfem_mg_set_tail_rows': (_i, [_i]),
     'sfem_mg_lambda_max': (_i, [_p, C.POINTER(_d)]),
     'sfem_mg_destroy': (None, [_p]),
     'sfem_krylov_cg': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _d, _i, C.POINTER(_d), _p]),

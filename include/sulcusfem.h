@@ -203,6 +203,11 @@ int sfem_mg_vcycle(sfem_mg_t mg, const double* b, double* x, void* stream);   /*
  * P_last: n_own(last) x n_tail; R_last: n_tail x n_own(last), owned columns only. */
 int sfem_mg_set_tail(sfem_mg_t mg, sfem_mg_t tail, int n_tail, int P_nnz, const int* P_rowptr, const int* P_cols,
                      const double* P_vals, int R_nnz, const int* R_rowptr, const int* R_cols, const double* R_vals);
+/* Experiment knob: multigrid levels with at most `rows` unknowns (and the dense coarsest solve below them) run as ONE
+ * fused thread-block-cluster kernel per V-cycle instead of ~7 launch-latency-bound launches per level.  0 = off, the
+ * default (environment SFEM_TAIL_ROWS): correct to rounding but measured slower than the separate launches
+ * (csrc/sfem_mg_tail.cu, profiles/r02_fused_tail.md).  Returns the previous setting. */
+int sfem_mg_set_tail_rows(int rows);
 int sfem_mg_lambda_max(sfem_mg_t mg, double* h_out);                            /* per level, host */
 void sfem_mg_destroy(sfem_mg_t mg);
 

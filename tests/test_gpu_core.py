@@ -190,6 +190,50 @@ def test_vcycle_two_rhs_equals_two_cycles(ctx, small, engine):
     assert _rel(z2[:, 0], za) < 1e-13 and _rel(z2[:, 1], zb) < 1e-13
 
 
+def test_fused_tail_vcycle_matches_separate_launches(ctx, small):
+    """sfem_mg_tail.cu: the small levels of a V-cycle in one thread-block-cluster kernel (phases separated by the
+    cluster barrier) against the same cycle as separate launches -- whole hierarchy fused (level 0 has < 10 k rows on
+    this mesh), fused from an inner level, one and two right-hand sides; then the Krylov solves on top of it."""
+    import torch
+    from sulcusfem.device import ScalarProblem, StokesProblem
+    mesh, mk, om = small
+    bm = mk['bc_markers'].values
+    lib = ctx.lib
+    prob = ScalarProblem(mesh, bm, ctx=ctx)
+    prob.assemble(1.0, mu_const=2.0, bc_values={1: 1.0, 2: 0.0})
+    sp_ = StokesProblem(mesh, bm, ctx=ctx)
+    sp_.vel.assemble(1.0, robin=False)
+    gen = torch.Generator(device='cpu').manual_seed(7)
+    old = lib.sfem_mg_set_tail_rows(0)
+    try:
+        for mg, nb in ((prob.mg, 1), (sp_.vel.mg, 2)):
+            n = mg.levels[0].n
+            sizes = [l.n for l in mg.levels]
+            b = torch.randn(n * nb, generator=gen, dtype=torch.float64).to(ctx.device)
+            lib.sfem_mg_set_tail_rows(0)
+            ref = mg.vcycle(b).clone()
+            for rows in (1 << 20, sizes[1], sizes[-2]):               # everything / from level 1 / last sparse level + dense
+                lib.sfem_mg_set_tail_rows(int(rows))
+                x = mg.vcycle(b).clone()
+                err = float((x - ref).norm() / ref.norm())
+                print('fused tail', nb, sizes, rows, err)
+                assert err < 1e-13, (nb, rows, err)
+                x2 = mg.vcycle(b)
+                assert torch.equal(x2, x)                              # run-to-run reproducible
+        # solves with the fused tail: same iteration counts (+-1) and fields as with separate launches
+        res = {}
+        for rows in (0, 1 << 20):
+            lib.sfem_mg_set_tail_rows(rows)
+            prob.assemble(1.0, mu_const=2.0, bc_values={1: 1.0, 2: 0.0})
+            c = prob.solve('cg', rtol=1e-13).clone()
+            res[rows] = (c, prob.last_info['iterations'])
+            assert prob.last_info['converged']
+        assert abs(res[0][1] - res[1 << 20][1]) <= 1
+        assert float((res[0][0] - res[1 << 20][0]).norm() / res[0][0].norm()) < 1e-11
+    finally:
+        lib.sfem_mg_set_tail_rows(old)
+
+
 def test_p2_assembly_matches_oracle(ctx, small):
     import torch
     from oracle import cpu_oracle as co
