@@ -70,14 +70,27 @@ def _inside_polygon(poly, pts):
     return inside
 
 
-def _triangulate(points, poly, h_min):
+def _inside_channel_domain(poly, pts, box):
+    """``_inside_polygon`` for the channel polygons of this module, same answers, ~20x cheaper: above the channel floor
+    (y > 0) the polygon is the rectangle (0, L) x (0, H) -- the ray cast only ever meets the two side walls there -- and
+    below it (y < 0) only the span of the sulcus can be inside; the edge loop runs on those few points (and on y == 0)."""
+    L, H, xL, xR = box
+    x, y = pts[:, 0], pts[:, 1]
+    inside = (y > 0.0) & (y < H) & ((x < L) != (x < 0.0))
+    rest = np.flatnonzero((y == 0.0) | ((y < 0.0) & (x >= xL) & (x <= xR)))
+    if len(rest):
+        inside[rest] = _inside_polygon(poly, pts[rest])
+    return inside
+
+
+def _triangulate(points, poly, h_min, box=None):
     tri = Delaunay(points)
     t = tri.simplices
     p = points[t]
     area = 0.5 * np.abs((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1])
                         - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 0, 1]))
     cen = p.mean(axis=1)
-    keep = (area > 1e-10 * h_min * h_min) & _inside_polygon(poly, cen)
+    keep = (area > 1e-10 * h_min * h_min) & (_inside_polygon(poly, cen) if box is None else _inside_channel_domain(poly, cen, box))
     return t[keep]
 
 
@@ -108,14 +121,15 @@ def _validate(cells, n_points, boundary_segs, interior_segs):
 
 def _smooth(points, cells, fixed_mask):
     n = len(points)
-    e = np.concatenate([cells[:, [0, 1]], cells[:, [1, 2]], cells[:, [0, 2]]], axis=0)
-    e = np.unique(np.sort(e, axis=1), axis=0)
-    acc = np.zeros((n, 2))
-    deg = np.zeros(n)
-    np.add.at(acc, e[:, 0], points[e[:, 1]])
-    np.add.at(acc, e[:, 1], points[e[:, 0]])
-    np.add.at(deg, e[:, 0], 1)
-    np.add.at(deg, e[:, 1], 1)
+    e = np.concatenate([cells[:, [0, 1]], cells[:, [1, 2]], cells[:, [0, 2]]], axis=0).astype(np.int64)
+    e.sort(axis=1)
+    key = np.unique(e[:, 0] * n + e[:, 1])                     # unique edges in lexicographic (v0, v1) order
+    e0, e1 = key // n, key % n
+    # neighbour sums: first-endpoint contributions, then second-endpoint contributions, each in edge order -- one
+    # sequential bincount over the concatenated lists adds in exactly the order the np.add.at version did (same bits)
+    idx, nbr = np.concatenate([e0, e1]), np.concatenate([e1, e0])
+    acc = np.stack([np.bincount(idx, weights=points[nbr, c], minlength=n) for c in range(2)], axis=1)
+    deg = np.bincount(idx, minlength=n).astype(np.float64)
     new = points.copy()
     free = ~fixed_mask & (deg > 0)
     new[free] = acc[free] / deg[free, None]
@@ -248,19 +262,20 @@ def _mesh_domain_graded(L, H, w, d, h, domain_type, refinement_factor, smooth_pa
         lvl.append(np.full(len(P), l))
     lat = np.concatenate(pts, axis=0)
     poly = bpts
-    lat = lat[_inside_polygon(poly, lat)]
+    box = (float(L), float(H), float(xL), float(xR)) if domain_type == 'sulcus' else (float(L), float(H), 1.0, 0.0)
+    lat = lat[_inside_channel_domain(poly, lat, box)]
     dist, _ = cKDTree(fixed).query(lat)
     lat = lat[dist >= 0.8 * qsize(lat)]
     points = np.concatenate([fixed, lat], axis=0)
     fixed_mask = np.zeros(len(points), dtype=bool)
     fixed_mask[:len(fixed)] = True
     h_min = min(h_f, h_cav)
-    cells = _triangulate(points, poly, h_min)
+    cells = _triangulate(points, poly, h_min, box)
     if not _validate(cells, len(points), bsegs, isegs):
         raise RuntimeError("graded mesher: boundary/mouth recovery failed")
     for _ in range(smooth_passes):
         trial = _smooth(points, cells, fixed_mask)
-        tcells = _triangulate(trial, poly, h_min)
+        tcells = _triangulate(trial, poly, h_min, box)
         if _validate(tcells, len(trial), bsegs, isegs):
             points, cells = trial, tcells
         else:
@@ -325,7 +340,8 @@ def mesh_domain(L=10.0, H=1.0, w=0.5, d=1.0, h=0.02, domain_type='sulcus', smoot
         near = (fine[:, 1] < 1.5 * h)
         lat = np.concatenate([lat[~((lat[:, 1] < 1.5 * h) & (lat[:, 0] > xL - 2 * h) & (lat[:, 0] < xR + 2 * h))], fine[near]])
     poly = bpts
-    lat = lat[_inside_polygon(poly, lat)]
+    box = (float(L), float(H), float(xL), float(xR)) if domain_type == 'sulcus' else (float(L), float(H), 1.0, 0.0)
+    lat = lat[_inside_channel_domain(poly, lat, box)]
     tree = cKDTree(fixed)
     dist, idx = tree.query(lat)
     # local spacing of the nearest fixed sample: cavity samples use h_cav
@@ -335,12 +351,12 @@ def mesh_domain(L=10.0, H=1.0, w=0.5, d=1.0, h=0.02, domain_type='sulcus', smoot
     points = np.concatenate([fixed, lat], axis=0)
     fixed_mask = np.zeros(len(points), dtype=bool)
     fixed_mask[:len(fixed)] = True
-    cells = _triangulate(points, poly, h_cav)
+    cells = _triangulate(points, poly, h_cav, box)
     if not _validate(cells, len(points), bsegs, isegs):
         raise RuntimeError("unstructured mesher: boundary/mouth recovery failed")
     for _ in range(smooth_passes):
         trial = _smooth(points, cells, fixed_mask)
-        tcells = _triangulate(trial, poly, h_cav)
+        tcells = _triangulate(trial, poly, h_cav, box)
         if _validate(tcells, len(trial), bsegs, isegs):
             points, cells = trial, tcells
         else:
