@@ -42,9 +42,10 @@ class Transfer:
     nested: bool = False        # coarse dofs are a prefix of the fine dofs (midpoint transfer)
 
 
-def _finish(n_fine, n_coarse, rows, cols, vals, nested=False) -> Transfer:
-    order = np.lexsort((cols, rows))
-    rows, cols, vals = rows[order], cols[order], vals[order]
+def _finish(n_fine, n_coarse, rows, cols, vals, nested=False, presorted=False) -> Transfer:
+    if not presorted:                                      # (rows ascending, columns ascending inside a row)
+        order = np.lexsort((cols, rows))
+        rows, cols, vals = rows[order], cols[order], vals[order]
     rowptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n_fine))]).astype(np.int32)
     cols = cols.astype(np.int32)
     t_rowptr, t_cols, perm = dm.transpose_csr(n_fine, n_coarse, rowptr, cols)
@@ -58,7 +59,9 @@ def midpoint_transfer(mesh: HostMesh) -> Transfer:
     rows = np.concatenate([np.arange(nv), nv + np.repeat(np.arange(ne), 2)]).astype(np.int64)
     cols = np.concatenate([np.arange(nv), mesh.edges.astype(np.int64).ravel()])
     vals = np.concatenate([np.ones(nv), np.full(2 * ne, 0.5)])
-    return _finish(nv + ne, nv, rows, cols, vals, nested=True)
+    # rows come out in order and an edge lists its vertices as (low, high): already sorted, no lexsort of 3 nv entries
+    presorted = bool(ne == 0 or np.all(mesh.edges[:, 0] < mesh.edges[:, 1]))
+    return _finish(nv + ne, nv, rows, cols, vals, nested=True, presorted=presorted)
 
 
 def locate_points(mesh: HostMesh, pts: np.ndarray, k: int = 16):
