@@ -15,6 +15,10 @@ N > 1: every rank solves its own independent sweep case (no data-path collective
            inputs and host results, wall clock around each call (H2D / D2H inside).
 `roofline` dominant kernel family, from a per-launch CUDA-event profile of one extra step.
 `cpu_baseline` the CPU oracle (numpy assembly + SuperLU) on a bounded sample of the workload.
+`same_mesh` GPU and CPU oracle on the SAME unrefined mesh with the parity of every field (exit code 3 on a miss).
+`mu_sweep` BASELINE configs[3]: the reference's 20-coefficient mu sweep through studies.run_mu_sweep -- batched Krylov
+           loops against one solve per coefficient, rows compared, two coefficients against the oracle's LU.
+`dd_strong` (N > 1) BASELINE config 5: the same step, one case row-partitioned over all ranks.
 """
 from __future__ import annotations
 
@@ -651,6 +655,14 @@ def run_gpu(args, rank, world):
                 "by_category": per_cat, "profiled_step_kernel_ms": float(mss.sum()),
                 "note": "profiled step runs un-graphed with a CUDA event pair around every launch; traffic: see profiles/"}
 
+    # ---- BASELINE configs[3]: the reference's mu sweep (batched Krylov loops), N = 1 only; wall-clock numbers of a
+    # Python driver loop, so it runs before the CPU legs fill the heap with the oracle's factorisations
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        import gc
+        gc.collect()
+        sweep = sweep_leg(with_oracle=not args.no_cpu)
+
     # ---- CPU baseline (oracle port) + same-mesh GPU legs with parity, rank 0 at N = 1 only
     cpu, same = None, []
     if not args.no_cpu and world == 1:
@@ -662,11 +674,6 @@ def run_gpu(args, rank, world):
                          f"reference's default mesh size): numpy assembly + SuperLU, {r0['cpu_ms'] / 1e3:.1f} s; the GPU on this "
                          f"same mesh: same_mesh[0]",
                "host_cores": os.cpu_count()}
-
-    # ---- BASELINE configs[3]: the reference's mu sweep (batched Krylov loops), N = 1 only
-    sweep = None
-    if world == 1 and not args.no_sweep:
-        sweep = sweep_leg(with_oracle=not args.no_cpu)
 
     value = world * ndof * args.steps / (ms_total / 1e3)
     line = {
