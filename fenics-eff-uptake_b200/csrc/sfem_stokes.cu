@@ -483,7 +483,7 @@ static int stokes_solve_impl(sfem_stokes_t h, const double* b, double* x, const 
       h->graph_epoch = graph_epoch();
       h->graph_nranks = dist_dev().nranks;
     }
-    const double target = rtol * (xref != nullptr ? gamma_ref : gamma1);
+    const double target = rtol * ((xref != nullptr && gamma_ref > 0.0) ? gamma_ref : gamma1);   // (a zero reference level: plain test)
     bool done = false;
     for (it = 1; it <= maxit && !done; ++it) {
       const int q = (it - 1) & 1;
@@ -517,7 +517,7 @@ static int stokes_solve_impl(sfem_stokes_t h, const double* b, double* x, const 
   SFEM_TRY(h->ws.join(user));
   const double rel = (bnorm > 0.0) ? std::sqrt(rr) / bnorm : std::sqrt(rr);
   h_info[0] = it; h_info[1] = rel;
-  const double glevel = (xref != nullptr) ? gamma_ref : gamma1;
+  const double glevel = (xref != nullptr && gamma_ref > 0.0) ? gamma_ref : gamma1;
   h_info[2] = (gamma1 == 0.0 || std::fabs(eta) <= rtol * glevel) ? 1.0 : 0.0;
   h_info[3] = (glevel > 0.0) ? std::fabs(eta) / glevel : 0.0;
   return SFEM_OK;

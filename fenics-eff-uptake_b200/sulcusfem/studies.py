@@ -496,7 +496,7 @@ def extract_mu_eff_analysis_data(result, config_name, mu_value, mu_factor):
 
 
 def run_geometry_analysis(output_dir=None, mu_factors=(0.1, 1.0, 10), geometries: Optional[Dict] = None, mesh_size_dim=0.02,
-                          rank=None, world=None, quiet=True, prefetch=True, streams=1):
+                          rank=None, world=None, quiet=True, prefetch=True, streams=1, batch=True):
     """Reference ``run_geometry_analysis`` (no_advection_analysis_A.py:1463-1581): every geometry of
     ``create_geometry_variations`` x mu factors (23 x 3 = 69 sulcus solves by default); the device problems of a
     geometry are reused by its mu values.  Rank 0 writes ``geometry_analysis_results.csv``."""
@@ -519,6 +519,8 @@ def run_geometry_analysis(output_dir=None, mu_factors=(0.1, 1.0, 10), geometries
         p.nondim()
         return p
     _prefetch([[(params_of(cfg, f), 'sulcus')] for _, cfg, f in cases], rank, world, prefetch)
+    if batch:        # the mu values of a geometry in one batched Krylov loop (presolve_no_adv)
+        presolve_no_adv([(params_of(cfg, f), 'sulcus') for i, (_, cfg, f) in enumerate(cases) if i % world == rank], quiet)
 
     def one(case):
         g, cfg, f = case
