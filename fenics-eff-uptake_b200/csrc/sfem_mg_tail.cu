@@ -21,9 +21,11 @@
 // launches took ~70 us.  Every one of its ~20 phases is a chain of four dependent L2 round trips (rowptr -> cols / vals
 // -> gather -> store acknowledged by the fence) on 8 SMs with 8 192 threads: two entries per thread on the 7.5 k level,
 // three rows per warp in the dense solve, ~4 us per phase -- no better than a launch that spreads the same work over
-// 148 SMs.  What would make it pay: the matrices of these levels resident in the cluster's shared memory (1.5 MB over
-// 16 CTAs) so that a phase is ONE round trip.  Until then the knob stays at 0; sfem_mg_set_tail_rows / SFEM_TAIL_ROWS
-// switch it on for experiments.
+// 148 SMs.  The micro-benchmark tools/micro/cluster_phase.cu settles it: a dependent CUDA-graph node with a store / a
+// gather / three dependent loads costs 0.85 / 1.45 / 1.70 us, the same phase between two cluster barriers 0.75 / 1.33 /
+// 1.90 us (cluster.sync() alone 0.3 us) -- there is nothing to gain from fusing launches on this machine, with or
+// without the matrices in shared memory.  The knob stays at 0; sfem_mg_set_tail_rows / SFEM_TAIL_ROWS switch the kernel
+// on for experiments.
 #include "sfem_mg.h"
 
 #include <cooperative_groups.h>
