@@ -661,7 +661,10 @@ def run_gpu(args, rank, world):
     if world == 1 and not args.no_sweep:
         import gc
         gc.collect()
-        sweep = sweep_leg(with_oracle=not args.no_cpu)
+        try:
+            sweep = sweep_leg(with_oracle=not args.no_cpu)
+        except Exception as e:                   # an auxiliary leg must not cost the headline line; reported and exit code 3
+            sweep = {"ok": False, "error": f"{type(e).__name__}: {e}"[:500]}
 
     # ---- CPU baseline (oracle port) + same-mesh GPU legs with parity, rank 0 at N = 1 only
     cpu, same = None, []
