@@ -669,14 +669,17 @@ def run_gpu(args, rank, world):
     # ---- CPU baseline (oracle port) + same-mesh GPU legs with parity, rank 0 at N = 1 only
     cpu, same = None, []
     if not args.no_cpu and world == 1:
-        for hh in dict.fromkeys([args.same_h, args.cpu_h]):
-            same.append(same_mesh_leg(ctx, hh, flush_l2))
-        r0 = same[0]
-        cpu = {"value": r0["cpu_dofs_per_s"], "unit": "DOFs/s", "cores": 1, "kind": "port",
-               "sample": f"one step of the same workload on the unrefined h={r0['h']} mesh ({r0['dofs']} dofs; h=0.02 is the "
-                         f"reference's default mesh size): numpy assembly + SuperLU, {r0['cpu_ms'] / 1e3:.1f} s; the GPU on this "
-                         f"same mesh: same_mesh[0]",
-               "host_cores": os.cpu_count()}
+        try:
+            for hh in dict.fromkeys([args.same_h, args.cpu_h]):
+                same.append(same_mesh_leg(ctx, hh, flush_l2))
+            r0 = same[0]
+            cpu = {"value": r0["cpu_dofs_per_s"], "unit": "DOFs/s", "cores": 1, "kind": "port",
+                   "sample": f"one step of the same workload on the unrefined h={r0['h']} mesh ({r0['dofs']} dofs; h=0.02 is the "
+                             f"reference's default mesh size): numpy assembly + SuperLU, {r0['cpu_ms'] / 1e3:.1f} s; the GPU on this "
+                             f"same mesh: same_mesh[0]",
+                   "host_cores": os.cpu_count()}
+        except Exception as e:                   # reported in the line (and exit code 3) instead of losing the headline numbers
+            same.append({"error": f"{type(e).__name__}: {e}"[:500], "parity": {"ok": False}})
 
     value = world * ndof * args.steps / (ms_total / 1e3)
     line = {
