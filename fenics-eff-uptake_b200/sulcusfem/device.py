@@ -495,7 +495,8 @@ class ScalarProblem:
         the structure and the dense inverse of the coarsest level; every column smooths with its own operator on
         every level (``shared_coarse=True``: only on the system level, the coarse levels of ``mu_ref`` serve all
         columns -- the first version, kept for comparison).  Returns (X, infos): X the interleaved solutions [n][nb] on
-        the device, infos one ``last_info`` dictionary per mu."""
+        the device (a buffer owned by the problem, overwritten by the next call of the same width), infos one
+        ``last_info`` dictionary per mu."""
         ctx, f = self.ctx, self.fine
         mus = [float(m) for m in mus]
         nb = len(mus)
@@ -509,7 +510,12 @@ class ScalarProblem:
             mu_ref = float(np.exp(np.mean(np.log(pos)))) if pos else 0.0
         self.assemble(float(D), mu_const=float(mu_ref), bc_values=bc_values)      # hierarchy of A(mu_ref)
         capi.check(ctx.lib.sfem_vec_select(f.n, P(f.bc_flag), P(f.bc_val), None, P(self.x), ctx.stream), 'sfem_vec_select')
-        X = ctx.empty(f.n * nb)
+        # one result buffer per batch width, reused by later calls (a stable address keeps the captured iteration graph
+        # valid): the returned X is overwritten by the next solve_batch of the same width -- copy out what must survive
+        bufs = self.__dict__.setdefault('_batch_X', {})
+        X = bufs.get(nb)
+        if X is None:
+            X = bufs[nb] = ctx.empty(f.n * nb)
         info = (C.c_double * (4 * nb))()
         h_mu = (C.c_double * nb)(*mus)
         A = f.A

@@ -63,7 +63,7 @@ def test_gershgorin_bound_of_a_batch_is_attained_at_an_end_point(robin_pair):
 
 def test_chebyshev_coarse_solve_reaches_the_promised_reduction(robin_pair):
     """The coefficient recurrence of the coarsest-level solve (host code of sfem_krylov_cg_batch, restated): m steps chosen
-    from the widest window give at least a 50-fold reduction of the energy-norm error for every column."""
+    from the widest window give at least the promised (20-fold) reduction of the energy-norm error for every column."""
     A0, M = robin_pair
     mu_ref, mus, eps = 1.0, [0.125, 0.7, 1.0, 8.0], 0.01
     inv = np.linalg.inv(A0 + mu_ref * M)
@@ -72,7 +72,7 @@ def test_chebyshev_coarse_solve_reaches_the_promised_reduction(robin_pair):
     kmax = max(h / l for h, l in zip(hi, lo))
     rr = (np.sqrt(kmax) - 1) / (np.sqrt(kmax) + 1)
     m = 1
-    while m < 8 and 2 * rr ** m / (1 + rr ** (2 * m)) > 0.02:
+    while m < 8 and 2 * rr ** m / (1 + rr ** (2 * m)) > 0.05:
         m += 1
     rng = np.random.default_rng(3)
     b = rng.standard_normal(A0.shape[0])
@@ -91,7 +91,7 @@ def test_chebyshev_coarse_solve_reaches_the_promised_reduction(robin_pair):
             rho = rho_new
         exact = np.linalg.solve(A, b)
         e, e0 = x - exact, exact
-        assert np.sqrt(e @ A @ e) <= 0.02 * np.sqrt(e0 @ A @ e0), (mu, m)
+        assert np.sqrt(e @ A @ e) <= 0.05 * np.sqrt(e0 @ A @ e0), (mu, m)
 
 
 def test_batches_are_formed_by_width_and_span_and_results_keep_the_callers_order(monkeypatch):
