@@ -246,13 +246,11 @@ def _pure_diffusion_stats(prob, x):
 def pure_diffusion_solver(mesh_results, C, D, mu, mesh_type="sulcus"):
     """Steady diffusion with constant Robin uptake (reference solvers.py:113-174).  A field that
     :func:`presolve_pure_diffusion` already computed for this (mesh, D, mu) is handed out instead of solving again."""
-    pre = _cache(_check_space(C, 'P2')).get('presolved')
-    if pre:
-        hit = pre.pop(_presolve_key(D, mu), None)
-        if hit is not None:
-            f, lines = hit
-            print("\n".join(lines))
-            return f
+    hit = _take_presolved(_check_space(C, 'P2'), _presolve_key(D, mu))
+    if hit is not None:
+        f, lines = hit
+        print("\n".join(lines))
+        return f
     prob, x = _solve_scalar(mesh_results, C, D, None, mu=mu)
     _, lines = _pure_diffusion_stats(prob, x)
     print("\n".join(lines))
@@ -273,6 +271,43 @@ def _presolve_key(D, mu):
     return (float(D), float(mu))
 
 
+# Parked fields live in the per-mesh cache: 'presolved' {key: (Function, printed lines)}; 'presolve_pending' = keys a
+# background pre-solve (presolve_pure_diffusion(background=True)) has announced but not delivered yet.
+_presolve_cv = threading.Condition()
+_presolve_stream = None
+_presolve_pool = None          # one persistent worker thread: its library work spaces and captured graphs survive between sweeps
+PRESOLVE_SLOT = 1000           # device-problem slot of the worker (never shared with the per-case path of any other thread)
+
+
+def _take_presolved(mesh, key, timeout=120.0):
+    """The parked field of ``key`` (None if there is none); waits while a background pre-solve still owes it."""
+    c = _cache(mesh)
+    with _presolve_cv:
+        while True:
+            pre = c.get('presolved')
+            if pre and key in pre:
+                return pre.pop(key)
+            pend = c.get('presolve_pending')
+            if not pend or key not in pend:
+                return None
+            if not _presolve_cv.wait(timeout):
+                pend.discard(key)          # the worker is stuck or gone: the caller solves this case itself
+                return None
+
+
+def _publish_presolved(mesh, keys, hits):
+    c = _cache(mesh)
+    with _presolve_cv:
+        pre = c.setdefault('presolved', {})
+        pend = c.get('presolve_pending')
+        for k, h in zip(keys, hits):
+            if h is not None:
+                pre[k] = h
+            if pend is not None:
+                pend.discard(k)
+        _presolve_cv.notify_all()
+
+
 def pure_diffusion_solver_batch(mesh_results, C, D, mus, mesh_type="sulcus"):
     """``[pure_diffusion_solver(mesh_results, C, D, mu) for mu in mus]`` in batched solves of up to ``BATCH`` coefficients
     (nearby coefficients share a batch: the list is processed in ascending order of mu).  Returns the Functions in the
@@ -285,22 +320,54 @@ def pure_diffusion_solver_batch(mesh_results, C, D, mus, mesh_type="sulcus"):
     return fs
 
 
-def presolve_pure_diffusion(mesh_results, C, D, mus):
+def presolve_pure_diffusion(mesh_results, C, D, mus, background=False):
     """Solve all ``mus`` of one geometry in batches and park the fields on the mesh; the next
     ``pure_diffusion_solver(mesh_results, C, D, mu)`` call for each of them (e.g. from ``run_simulation``) returns the
-    parked field.  Returns the number of parked fields."""
+    parked field.  ``background=True``: the batches are solved by a worker thread on its own CUDA stream and device
+    problem while the caller goes on (a consumer that asks for a field not delivered yet waits for it), so the
+    per-case post-processing of one batch overlaps the Krylov loops of the next.  Returns the number of fields."""
     mesh = _check_space(C, 'P2')
     mus = [float(m) for m in mus]
-    out = _solve_batches(mesh_results, C, D, mus)
-    pre = _cache(mesh).setdefault('presolved', {})
-    for mu, hit in zip(mus, out):
-        pre[_presolve_key(D, mu)] = hit
+    keys = [_presolve_key(D, mu) for mu in mus]
+    if not background:
+        _solve_batches(mesh_results, C, D, mus, publish=lambda idx, hits: _publish_presolved(mesh, [keys[i] for i in idx], hits))
+        import torch
+        torch.cuda.current_stream().synchronize()  # the parked fields may be consumed on other streams (sweep workers)
+        return len(mus)
+    global _presolve_pool
     import torch
-    torch.cuda.current_stream().synchronize()      # the parked fields may be consumed on other streams (sweep workers)
-    return len(out)
+    from concurrent.futures import ThreadPoolExecutor
+    if _presolve_pool is None:
+        _presolve_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix='sfem-presolve')
+    with _presolve_cv:
+        _cache(mesh).setdefault('presolve_pending', set()).update(keys)
+    device = torch.cuda.current_device()
+    torch.cuda.current_stream().synchronize()      # whatever the caller queued (mesh uploads) is visible to the worker
+
+    def work():
+        from . import sweep
+        try:
+            torch.cuda.set_device(device)
+            sweep._tls.slot = PRESOLVE_SLOT
+            global _presolve_stream
+            if _presolve_stream is None:
+                _presolve_stream = torch.cuda.Stream()     # one stream for the worker's lifetime (captured graphs are keyed on it)
+            st = _presolve_stream
+            with torch.cuda.stream(st):
+                _solve_batches(mesh_results, C, D, mus,
+                               publish=lambda idx, hits: (st.synchronize(), _publish_presolved(mesh, [keys[i] for i in idx], hits)))
+        except BaseException as e:               # the consumers fall back to their own solves
+            import warnings
+            warnings.warn(f"background pre-solve failed ({type(e).__name__}: {e}); cases are solved one by one")
+        finally:
+            _publish_presolved(mesh, keys, [None] * len(keys))       # nothing stays pending
+    _presolve_pool.submit(work)
+    return len(mus)
 
 
-def _solve_batches(mesh_results, C, D, mus):
+def _solve_batches(mesh_results, C, D, mus, publish=None):
+    """Batched solves of ``mus``; returns [(Function, printed lines)] in the caller's order.  ``publish(indices, hits)``
+    is called after every batch with the positions (in ``mus``) and results it produced."""
     mesh = _check_space(C, 'P2')
     prob = scalar_problem(mesh, mesh_results['bc_markers'], 4)
     mus = [float(m) for m in mus]
@@ -324,6 +391,8 @@ def _solve_batches(mesh_results, C, D, mus):
             f._dev = (x,)
             f.solver_info = dict(infos[c])
             out[i] = (f, lines)
+        if publish is not None:
+            publish(list(idx), [out[i] for i in idx])
     return out
 
 

@@ -340,11 +340,16 @@ def _slim(result, **extra):
     return out
 
 
-def presolve_no_adv(jobs, quiet=True):
+PRESOLVE_IN_BACKGROUND = os.environ.get('SFEM_PRESOLVE_BACKGROUND', '1') != '0'
+
+
+def presolve_no_adv(jobs, quiet=True, background=None):
     """Batched pre-solve of no-advection cases: ``jobs`` = (params, domain_type) pairs; the pairs that
     share a mesh and a diffusivity are solved together, up to ``solvers.BATCH`` Robin coefficients per Krylov loop
     (``solvers.presolve_pure_diffusion``), and the fields are parked on the mesh for the ``run_simulation`` calls that
-    follow.  Returns the number of parked fields."""
+    follow.  ``background`` (default ``PRESOLVE_IN_BACKGROUND``): the Krylov loops run on a worker thread / stream and
+    overlap the per-case post-processing of the batches already delivered.  Returns the number of fields."""
+    background = PRESOLVE_IN_BACKGROUND if background is None else bool(background)
     from .fem import FunctionSpace
     from .simulation import _mesh_key, _simulation_generate_mesh
     from .solvers import presolve_pure_diffusion
@@ -357,7 +362,7 @@ def presolve_no_adv(jobs, quiet=True):
             p0, dom = members[0]
             mr = _simulation_generate_mesh(p0, dom)
             mus = sorted({float(p.mu) for p, _ in members})
-            n += presolve_pure_diffusion(mr, FunctionSpace(mr['mesh'], "CG", 2), D, mus)
+            n += presolve_pure_diffusion(mr, FunctionSpace(mr['mesh'], "CG", 2), D, mus, background=background)
     return n
 
 

@@ -129,3 +129,31 @@ def test_batches_are_formed_by_width_and_span_and_results_keep_the_callers_order
     assert [f.values[0] for f, _ in out] == mus                       # caller's order
     assert calls == [[0.1, 0.2, 0.4, 0.8], [1.6, 3.0, 7.0, 50.0], [1000.0]]   # width 4, then the span limit (1000 > 64 * 1.6 would
     assert all(max(c) <= sv.BATCH_SPAN * min(c) for c in calls)               # also have split a wider batch)
+
+
+def test_parked_fields_wait_for_a_background_presolve_and_fall_back_when_it_never_delivers():
+    """solvers._take_presolved / _publish_presolved: a consumer asking for a field a background pre-solve has announced
+    waits for it; one that is not announced returns at once; one that is never delivered gives up (the caller then
+    solves the case itself)."""
+    import threading
+    import time
+    import sulcusfem.solvers as sv
+
+    class M:
+        pass
+    mesh = M()
+    key, other, lost = (1.0, 2.0), (1.0, 3.0), (1.0, 4.0)
+    assert sv._take_presolved(mesh, key) is None                       # nothing parked, nothing pending
+    with sv._presolve_cv:
+        sv._cache(mesh).setdefault('presolve_pending', set()).update([key, lost])
+    t = threading.Timer(0.2, lambda: sv._publish_presolved(mesh, [key], [('field', ['line'])]))
+    t0 = time.perf_counter()
+    t.start()
+    assert sv._take_presolved(mesh, other) is None                     # not announced: no waiting
+    assert time.perf_counter() - t0 < 0.15
+    assert sv._take_presolved(mesh, key) == ('field', ['line'])        # announced: waited for the delivery
+    assert time.perf_counter() - t0 >= 0.19
+    assert sv._take_presolved(mesh, key) is None                       # handed out exactly once
+    assert sv._take_presolved(mesh, lost, timeout=0.1) is None         # never delivered: give up, and stop waiting for it
+    assert lost not in sv._cache(mesh)['presolve_pending']
+    t.join()
