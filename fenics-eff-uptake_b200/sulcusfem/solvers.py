@@ -261,7 +261,8 @@ def pure_diffusion_solver(mesh_results, C, D, mu, mesh_type="sulcus"):
 # The reference's mu sweeps (no_advection_analysis_A.py:1306-1347: 20 mu on one mesh; no_advection_analysis_B.py:110-141:
 # 3 mu per geometry) call pure_diffusion_solver once per mu.  A(mu) = D K + mu M_Gamma differs between the cases in its
 # boundary rows only, so up to BATCH coefficients are solved in ONE Krylov loop (sfem_krylov_cg_batch: interleaved
-# right-hand sides, per-column CG scalars, one shared multigrid hierarchy assembled for the batch's geometric-mean mu).
+# right-hand sides, per-column CG scalars; the multigrid hierarchy assembled for the batch's geometric-mean mu supplies
+# patterns, transfers and the dense coarsest inverse, every column smooths with its own operator on every level).
 BATCH = int(__import__('os').environ.get('SFEM_BATCH', 16))     # coefficients per Krylov loop (library limit: 16)
 BATCH_SPAN = 64.0         # largest mu / smallest mu inside one batch: bounds the Chebyshev steps of the coarsest-level solve
                           # (every column runs on its own operators; iteration counts do not depend on the span -- measured)
