@@ -67,18 +67,25 @@ class HostMesh:
         nv = self.num_vertices
         # local edge i is opposite local vertex i (UFC): e0=(v1,v2), e1=(v0,v2), e2=(v0,v1)
         pairs = np.stack([c[:, [1, 2]], c[:, [0, 2]], c[:, [0, 1]]], axis=1)   # [nc,3,2], sorted
-        keys = pairs[..., 0] * nv + pairs[..., 1]
-        uniq, inv = np.unique(keys.ravel(), return_inverse=True)               # lexicographic
+        keys = (pairs[..., 0] * nv + pairs[..., 1]).ravel()
+        # ONE stable sort of the 3 nc keys gives everything: the unique edges in lexicographic order (= np.unique), the
+        # edge id of every (cell, local edge) slot and the slots of an edge grouped in cell order (what a stable argsort
+        # of those ids followed by two searchsorted passes produced before -- same arrays, half the time)
+        order = np.argsort(keys, kind='stable')
+        sk = keys[order]
+        new_edge = np.ones(len(sk), dtype=bool)
+        new_edge[1:] = sk[1:] != sk[:-1]
+        first = np.flatnonzero(new_edge)
+        uniq = sk[first]
+        ne = len(uniq)
+        inv = np.empty(len(keys), dtype=np.int64)
+        inv[order] = np.cumsum(new_edge) - 1
         self.edges = np.stack([uniq // nv, uniq % nv], axis=1).astype(np.int32)
         self.cell_edges = inv.reshape(-1, 3).astype(np.int32)
-        ne = len(uniq)
         # edge -> (first cell, second cell or -1), first = lowest cell index ('+' side in dolfin)
-        order = np.argsort(inv, kind='stable')
-        sorted_e = inv[order]
         cell_of = (order // 3).astype(np.int32)
         loc_of = (order % 3).astype(np.int8)
-        first = np.searchsorted(sorted_e, np.arange(ne), side='left')
-        count = np.searchsorted(sorted_e, np.arange(ne), side='right') - first
+        count = np.diff(np.append(first, len(sk)))
         if count.max(initial=0) > 2:
             raise ValueError("non-manifold mesh: an edge has more than two cells")
         self.edge_cells = np.full((ne, 2), -1, dtype=np.int32)
@@ -132,9 +139,16 @@ class HostMesh:
         return 0.5 * (self.coords[self.edges[:, 0]] + self.coords[self.edges[:, 1]])
 
     def signed_areas(self) -> np.ndarray:
-        p = self.coords[self.cells]
-        return 0.5 * ((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1])
-                      - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 0, 1]))
+        """Signed cell areas (memoised: check(), the hierarchy, the locator and the Schur set-up all ask; the arrays of
+        a mesh are never modified in place).  The returned array is read-only."""
+        a = getattr(self, '_signed_areas', None)
+        if a is None:
+            p = self.coords[self.cells]
+            a = 0.5 * ((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1])
+                       - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 0, 1]))
+            a.setflags(write=False)
+            self._signed_areas = a
+        return a
 
     def check(self):
         a = np.abs(self.signed_areas())
