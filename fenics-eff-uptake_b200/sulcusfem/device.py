@@ -180,9 +180,14 @@ class DeviceCsr:
 
 
 def cell_geometry(mesh: HostMesh) -> np.ndarray:
-    """[6][nc] SoA vertex coordinates x0,y0,x1,y1,x2,y2."""
-    p = mesh.coords[mesh.cells]
-    return np.ascontiguousarray(p.reshape(mesh.num_cells, 6).T)
+    """[6][nc] SoA vertex coordinates x0,y0,x1,y1,x2,y2 (memoised on the mesh: the velocity level, the scalar level, the
+    Stokes problem and the functional plan of one mesh all upload it)."""
+    g = getattr(mesh, '_cell_geometry', None)
+    if g is None:
+        p = mesh.coords[mesh.cells]
+        g = np.ascontiguousarray(p.reshape(mesh.num_cells, 6).T)
+        mesh._cell_geometry = g                 # (kept writable: torch.from_numpy warns on read-only arrays; nobody writes it)
+    return g
 
 
 def facet_geometry(mesh: HostMesh, facets: np.ndarray) -> np.ndarray:

@@ -227,8 +227,9 @@ def stokes_block_plans(mesh: HostMesh):
     c1v = p1_cell_dofs(mesh).astype(np.int64)                               # [nc, 3]
     pb = memo_pattern(mesh, ('stokes_B',), nv, 2 * n2, [(c1v, il)])         # codes: cell*36 + k*12 + m
     pbt = memo_pattern(mesh, ('stokes_BT',), 2 * n2, nv, [(il, c1v)])       # codes: cell*36 + m*3 + k  -> remap
-    loc = pbt.contrib_code.astype(np.int64) % 36
-    bt_code = ((pbt.contrib_code.astype(np.int64) - loc) + (loc % 3) * 12 + loc // 3).astype(np.int32)
+    code = np.asarray(pbt.contrib_code, dtype=np.int32)                     # < 36 nc: int32 arithmetic throughout
+    loc = code % np.int32(36)
+    bt_code = (code - loc) + (loc % np.int32(3)) * np.int32(12) + loc // np.int32(3)
     c1 = p1_cell_dofs(mesh)
     pmass = memo_pattern(mesh, ('p1_mass',), nv, nv, [(c1, c1)])
     return pb, pbt, bt_code, pmass
